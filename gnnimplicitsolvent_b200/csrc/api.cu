@@ -1,0 +1,550 @@
+// api.cu -- the C ABI of libgnnis.so (include/gnnis.h): handle management, weight packing, workspace and the
+// launch sequence of one batched energy/force evaluation.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gnnis {
+int launch_born_count(Ctx*, const float*, int, cudaStream_t);
+int launch_fill_edges(Ctx*, const float*, int, int*, int*, uint32_t*, float*, int64_t, cudaStream_t);
+int launch_gb_energy(Ctx*, const float*, const float*, int, int, float*, cudaStream_t);
+int launch_born_adjoint(Ctx*, const float*, int, float*, cudaStream_t);
+int launch_reduce_energy(Ctx*, const float*, float*, cudaStream_t);
+int launch_edge_fwd(Ctx*, int, cudaStream_t);
+int launch_edge_bwd(Ctx*, int, int, cudaStream_t);
+int launch_node_pre1(Ctx*, cudaStream_t);
+int launch_node_fwd(Ctx*, int, cudaStream_t);
+int launch_node_bwd(Ctx*, int, cudaStream_t);
+int launch_node_pre1_bwd(Ctx*, cudaStream_t);
+int launch_gb_only_head(Ctx*, cudaStream_t);
+int launch_add_vec(Ctx*, int, const float*, float*, cudaStream_t);
+int launch_bond_forces(Ctx*, const float*, float*, float*, cudaStream_t);
+
+static std::string g_create_err;
+
+enum Stage { kStNeighborBorn = 0, kStEdgeFwd, kStNodeFwd, kStGbEnergy, kStNodeBwd, kStEdgeBwd, kStBornAdjoint, kNumStages };
+static const char* kStageNames[kNumStages] = {"neighbor_born", "edge_fwd", "node_fwd", "gb_energy",
+                                              "node_bwd", "edge_bwd", "born_adjoint"};
+
+struct StageTimer {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> stage;
+  cudaStream_t st;
+  void mark(int s) {   // called BEFORE the launches of stage s; a final mark(-1) closes the last one
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    stage.push_back(s);
+  }
+};
+
+template <typename T>
+static int dev_alloc(Ctx* c, T** p, size_t count) {
+  if (*p) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  if (count == 0) count = 1;
+  GNNIS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return 0;
+}
+template <typename T>
+static void dev_free(T** p) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+}
+
+static int ensure_workspace(Ctx* c) {
+  if (c->N <= 0 || c->R <= 0) return 0;
+  if (c->N > 65535) {
+    c->err = "n_atoms per replica must be <= 65535";
+    return -1;
+  }
+  if (c->N <= kUnitAtomsMax) {
+    c->G = kUnitAtomsMax / c->N;
+    if (c->G > c->R) c->G = c->R;
+    c->smem_tables = true;
+  } else {
+    c->G = 1;
+    c->smem_tables = false;
+  }
+  c->n_units = (c->R + c->G - 1) / c->G;
+  size_t n = (size_t)c->R * c->N;
+  int64_t cap = (int64_t)n * (c->N - 1);
+  if (cap > 2147483000LL) {
+    c->err = "R*N*(N-1) exceeds the int32 CSR range; shard the replicas";
+    return -1;
+  }
+  if (cap < 1) cap = 1;
+  if (n == c->ws_atoms && cap == c->edge_cap) return 0;
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  int nblk = (int)((n + kPairThreads - 1) / kPairThreads);
+  if (dev_alloc(c, &c->deg, n) || dev_alloc(c, &c->row_ptr, n + 1) || dev_alloc(c, &c->blk_sum, (size_t)nblk + 1) ||
+      dev_alloc(c, &c->col, (size_t)cap) || dev_alloc(c, &c->pair, (size_t)cap) || dev_alloc(c, &c->r_e, (size_t)cap))
+    return -1;
+  float** scal[] = {&c->born, &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->e_atom, &c->sa_atom};
+  for (float** p : scal)
+    if (dev_alloc(c, p, n)) return -1;
+  for (int l = 0; l < 3; ++l) {
+    if (dev_alloc(c, &c->P[l], n * 64) || dev_alloc(c, &c->Q[l], n * 64) || dev_alloc(c, &c->a[l], n * 64) ||
+        dev_alloc(c, &c->o[l], n * (l == 2 ? 2 : 64)))
+      return -1;
+  }
+  if (dev_alloc(c, &c->abar, n * 64) || dev_alloc(c, &c->Pbar, n * 64) || dev_alloc(c, &c->Qbar, n * 64) ||
+      dev_alloc(c, &c->rbar, n * (size_t)c->N))
+    return -1;
+  if (dev_alloc(c, &c->h_pos_dev, n * 3) || dev_alloc(c, &c->h_f_dev, n * 3) || dev_alloc(c, &c->h_e_dev, (size_t)c->R))
+    return -1;
+  if (!c->n_edges_dev && dev_alloc(c, &c->n_edges_dev, 1)) return -1;
+  GNNIS_CUDA_OK(cudaMemset(c->sa_atom, 0, n * sizeof(float)));
+  c->ws_atoms = n;
+  c->edge_cap = cap;
+  return 0;
+}
+
+static int check_ready(Ctx* c, bool need_weights) {
+  if (c->N <= 0) {
+    c->err = "gnnis_set_system has not been called";
+    return -1;
+  }
+  if (c->R <= 0) {
+    c->err = "gnnis_set_replicas has not been called";
+    return -1;
+  }
+  if (need_weights && !c->have_weights) {
+    c->err = "gnnis_load_weights has not been called";
+    return -1;
+  }
+  return 0;
+}
+
+int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint32_t flags, cudaStream_t st,
+                      StageTimer* tm) {
+  const bool gb_only = flags & GNNIS_FLAG_GB_ONLY;
+  const bool want_grad = !(flags & GNNIS_FLAG_NO_FORCES);
+  const int delta = (flags & GNNIS_FLAG_DELTA) ? 1 : 0;
+  if (check_ready(c, !gb_only)) return -1;
+  if (want_grad && !force) {
+    c->err = "force_dev is NULL but GNNIS_FLAG_NO_FORCES is not set";
+    return -1;
+  }
+  if (flags & GNNIS_FLAG_MLP_BF16) {
+    c->err = "GNNIS_FLAG_MLP_BF16: the tcgen05 edge-MLP path is not built in this version";
+    return -3;
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  const int n = c->R * c->N;
+  if (tm) tm->mark(kStNeighborBorn);
+  if (launch_born_count(c, pos, 0, st)) return -1;
+  if (!gb_only) {
+    if (launch_fill_edges(c, pos, 0, c->row_ptr, nullptr, c->pair, c->r_e, c->edge_cap, st)) return -1;
+    if (tm) tm->mark(kStNodeFwd);
+    if (launch_node_pre1(c, st)) return -1;
+    for (int l = 0; l < 3; ++l) {
+      if (tm) tm->mark(kStEdgeFwd);
+      if (launch_edge_fwd(c, l, st)) return -1;
+      if (tm) tm->mark(kStNodeFwd);
+      if (launch_node_fwd(c, l, st)) return -1;
+    }
+  } else {
+    if (launch_gb_only_head(c, st)) return -1;
+  }
+  if (tm) tm->mark(kStGbEnergy);
+  if (launch_gb_energy(c, pos, c->born_s, delta, want_grad ? 1 : 0, force, st)) return -1;
+  if (launch_reduce_energy(c, gb_only ? nullptr : c->sa_atom, e_rep, st)) return -1;
+  if (want_grad) {
+    if (gb_only) {
+      if (launch_add_vec(c, n, c->dE_dBs, c->Bbar, st)) return -1;
+    } else {
+      for (int l = 2; l >= 0; --l) {
+        if (tm) tm->mark(kStNodeBwd);
+        if (launch_node_bwd(c, l, st)) return -1;
+        if (tm) tm->mark(kStEdgeBwd);
+        if (launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
+      }
+      if (tm) tm->mark(kStNodeBwd);
+      if (launch_node_pre1_bwd(c, st)) return -1;
+    }
+    if (tm) tm->mark(kStBornAdjoint);
+    if (launch_born_adjoint(c, pos, gb_only ? 0 : 1, force, st)) return -1;
+    if (c->n_bonds > 0 && launch_bond_forces(c, pos, e_rep, force, st)) return -1;
+  } else if (c->n_bonds > 0) {
+    if (launch_bond_forces(c, pos, e_rep, nullptr, st)) return -1;
+  }
+  if (tm) tm->mark(-1);
+  return 0;
+}
+
+}  // namespace gnnis
+
+using namespace gnnis;
+
+extern "C" {
+
+int gnnis_create(gnnis_handle* out, int device) {
+  if (!out) return -1;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_err = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                   " (libgnnis has no CPU fallback by design)";
+    return -1;
+  }
+  if (device < 0 || device >= count) {
+    g_create_err = "device index out of range";
+    return -1;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_err = "libgnnis is built for sm_100a (B200) only; found compute capability " +
+                   std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    return -1;
+  }
+  Ctx* c = new Ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  cudaSetDevice(device);
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "cudaStreamCreate failed";
+    delete c;
+    return -1;
+  }
+  *out = reinterpret_cast<gnnis_handle>(c);
+  return 0;
+}
+
+int gnnis_destroy(gnnis_handle h) {
+  if (!h) return 0;
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  dev_free(&c->wblob);
+  float** f[] = {&c->q, &c->rho, &c->s, &c->alpha, &c->beta, &c->gamma, &c->d0, &c->m0, &c->pref, &c->r_e, &c->born,
+                 &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->abar, &c->Pbar, &c->Qbar, &c->rbar, &c->e_atom,
+                 &c->sa_atom, &c->h_pos_dev, &c->h_e_dev, &c->h_f_dev, &c->bond_r0, &c->bond_k, &c->lb_S, &c->lb_Y,
+                 &c->lb_rho, &c->lb_alpha, &c->lb_g, &c->lb_gprev, &c->lb_xprev, &c->lb_d, &c->lb_e, &c->lb_eprev,
+                 &c->lb_step, &c->lb_ftmp, &c->lb_etmp, &c->masses, &c->gamma_emb};
+  for (float** p : f) dev_free(p);
+  for (int l = 0; l < 3; ++l) {
+    dev_free(&c->P[l]);
+    dev_free(&c->Q[l]);
+    dev_free(&c->a[l]);
+    dev_free(&c->o[l]);
+  }
+  int** ip[] = {&c->radidx, &c->solvent_id, &c->deg, &c->row_ptr, &c->blk_sum, &c->col, &c->bond_idx, &c->lb_state,
+                &c->lb_count, &c->lb_active};
+  for (int** p : ip) dev_free(p);
+  dev_free(&c->pair);
+  dev_free(&c->n_edges_dev);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return 0;
+}
+
+const char* gnnis_last_error(gnnis_handle h) {
+  if (!h) return g_create_err.c_str();
+  return reinterpret_cast<Ctx*>(h)->err.c_str();
+}
+
+int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !w) return -1;
+  if (w->hidden != kH || w->hidden_token != kT || w->n_rbf != kRbf || w->num_solvents < 1) {
+    c->err = "unsupported architecture: this build is specialised for hidden=64, hidden_token=128, 20 RBFs "
+             "(the shipped GNN.pt architecture, train_config.yml)";
+    return -1;
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  const int S = w->num_solvents;
+  std::vector<float> blob;
+  auto reserve = [&](size_t count) {
+    size_t off = blob.size();
+    size_t padded = (count + 63) / 64 * 64;
+    blob.resize(off + padded, 0.0f);
+    return off;
+  };
+  struct Off {
+    size_t Wi_t, Wj_t, Wr_t, b1, W2_t, b2, W3a_t, sbias, W4_t, b4, Wi, Wj, Wr, W2, W3a, W4;
+  } off[3];
+  for (int l = 0; l < 3; ++l) {
+    const int cin = l == 0 ? 3 : kH, cout = l == 2 ? 2 : kH, ld1 = 2 * cin + kRbf;
+    const float *W1 = w->message1_w[l], *W2 = w->message2_w[l], *W3 = w->lin1_w[l], *W4 = w->lin2_w[l];
+    Off& o = off[l];
+    o.Wi_t = reserve((size_t)cin * 64);
+    o.Wj_t = reserve((size_t)cin * 64);
+    o.Wr_t = reserve(kRbf * 64);
+    o.b1 = reserve(64);
+    o.W2_t = reserve(64 * 64);
+    o.b2 = reserve(64);
+    o.W3a_t = reserve(64 * 128);
+    o.sbias = reserve((size_t)S * 128);
+    o.W4_t = reserve((size_t)128 * cout);
+    o.b4 = reserve(cout);
+    o.Wi = reserve((size_t)64 * cin);
+    o.Wj = reserve((size_t)64 * cin);
+    o.Wr = reserve(64 * kRbf);
+    o.W2 = reserve(64 * 64);
+    o.W3a = reserve(128 * 64);
+    o.W4 = reserve((size_t)cout * 128);
+    for (int cc = 0; cc < 64; ++cc) {
+      for (int k = 0; k < cin; ++k) {
+        blob[o.Wi_t + (size_t)k * 64 + cc] = W1[(size_t)cc * ld1 + k];
+        blob[o.Wj_t + (size_t)k * 64 + cc] = W1[(size_t)cc * ld1 + cin + k];
+        blob[o.Wi + (size_t)cc * cin + k] = W1[(size_t)cc * ld1 + k];
+        blob[o.Wj + (size_t)cc * cin + k] = W1[(size_t)cc * ld1 + cin + k];
+      }
+      for (int k = 0; k < kRbf; ++k) {
+        blob[o.Wr_t + (size_t)k * 64 + cc] = W1[(size_t)cc * ld1 + 2 * cin + k];
+        blob[o.Wr + (size_t)cc * kRbf + k] = W1[(size_t)cc * ld1 + 2 * cin + k];
+      }
+      blob[o.b1 + cc] = w->message1_b[l][cc];
+      blob[o.b2 + cc] = w->message2_b[l][cc];
+      for (int k = 0; k < 64; ++k) {
+        blob[o.W2_t + (size_t)k * 64 + cc] = W2[(size_t)cc * 64 + k];
+        blob[o.W2 + (size_t)cc * 64 + k] = W2[(size_t)cc * 64 + k];
+      }
+    }
+    for (int m = 0; m < 128; ++m) {
+      for (int k = 0; k < 64; ++k) {
+        blob[o.W3a_t + (size_t)k * 128 + m] = W3[(size_t)m * 128 + k];
+        blob[o.W3a + (size_t)m * 64 + k] = W3[(size_t)m * 128 + k];
+      }
+      for (int s = 0; s < S; ++s) {
+        double acc = 0.0;
+        for (int k = 0; k < 64; ++k) acc += (double)W3[(size_t)m * 128 + 64 + k] * (double)w->solvent_embedding[(size_t)s * 64 + k];
+        blob[o.sbias + (size_t)s * 128 + m] = (float)(acc + (double)w->lin1_b[l][m]);
+      }
+      for (int cc = 0; cc < cout; ++cc) {
+        blob[o.W4_t + (size_t)m * cout + cc] = W4[(size_t)cc * 128 + m];
+        blob[o.W4 + (size_t)cc * 128 + m] = W4[(size_t)cc * 128 + m];
+      }
+    }
+    for (int cc = 0; cc < cout; ++cc) blob[o.b4 + cc] = w->lin2_b[l][cc];
+  }
+  size_t gamma_off = reserve(S);
+  for (int s = 0; s < S; ++s) blob[gamma_off + s] = w->gamma_embedding[s];
+  if (dev_alloc(c, &c->wblob, blob.size())) return -1;
+  GNNIS_CUDA_OK(cudaMemcpy(c->wblob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  for (int l = 0; l < 3; ++l) {
+    LayerW& L = c->L[l];
+    const Off& o = off[l];
+    L.cin = l == 0 ? 3 : kH;
+    L.cout = l == 2 ? 2 : kH;
+    L.Wi_t = c->wblob + o.Wi_t;
+    L.Wj_t = c->wblob + o.Wj_t;
+    L.Wr_t = c->wblob + o.Wr_t;
+    L.b1 = c->wblob + o.b1;
+    L.W2_t = c->wblob + o.W2_t;
+    L.b2 = c->wblob + o.b2;
+    L.W3a_t = c->wblob + o.W3a_t;
+    L.sbias = c->wblob + o.sbias;
+    L.W4_t = c->wblob + o.W4_t;
+    L.b4 = c->wblob + o.b4;
+    L.Wi = c->wblob + o.Wi;
+    L.Wj = c->wblob + o.Wj;
+    L.Wr = c->wblob + o.Wr;
+    L.W2 = c->wblob + o.W2;
+    L.W3a = c->wblob + o.W3a;
+    L.W4 = c->wblob + o.W4;
+  }
+  // gamma table is a view into the blob; keep a separate pointer that destroy() must not free twice
+  c->gamma_emb = nullptr;
+  if (dev_alloc(c, &c->gamma_emb, (size_t)S)) return -1;
+  GNNIS_CUDA_OK(cudaMemcpy(c->gamma_emb, w->gamma_embedding, S * sizeof(float), cudaMemcpyHostToDevice));
+  c->S = S;
+  c->have_weights = true;
+  return 0;
+}
+
+int gnnis_set_system(gnnis_handle h, int32_t n_atoms, const float* params7, const float* d0, const float* m0,
+                     int32_t n_unique) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (n_atoms < 1 || !params7 || !d0 || !m0 || n_unique < 1) {
+    c->err = "gnnis_set_system: bad arguments";
+    return -1;
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  std::vector<float> col[6];
+  std::vector<int> ridx(n_atoms);
+  for (auto& v : col) v.resize(n_atoms);
+  for (int i = 0; i < n_atoms; ++i) {
+    for (int k = 0; k < 6; ++k) col[k][i] = params7[(size_t)i * 7 + k];
+    int r = (int)params7[(size_t)i * 7 + 6];   // .to(torch.int) truncation, GNN_Layers.py:1023
+    if (r < 0 || r >= n_unique) {
+      c->err = "gnnis_set_system: radindex out of range of the neck tables";
+      return -1;
+    }
+    ridx[i] = r;
+  }
+  float** dst[6] = {&c->q, &c->rho, &c->s, &c->alpha, &c->beta, &c->gamma};
+  for (int k = 0; k < 6; ++k) {
+    if (dev_alloc(c, dst[k], (size_t)n_atoms)) return -1;
+    GNNIS_CUDA_OK(cudaMemcpy(*dst[k], col[k].data(), n_atoms * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (dev_alloc(c, &c->radidx, (size_t)n_atoms)) return -1;
+  GNNIS_CUDA_OK(cudaMemcpy(c->radidx, ridx.data(), n_atoms * sizeof(int), cudaMemcpyHostToDevice));
+  size_t uu = (size_t)n_unique * n_unique;
+  if (dev_alloc(c, &c->d0, uu) || dev_alloc(c, &c->m0, uu)) return -1;
+  GNNIS_CUDA_OK(cudaMemcpy(c->d0, d0, uu * sizeof(float), cudaMemcpyHostToDevice));
+  GNNIS_CUDA_OK(cudaMemcpy(c->m0, m0, uu * sizeof(float), cudaMemcpyHostToDevice));
+  c->N = n_atoms;
+  c->U = n_unique;
+  c->n_bonds = 0;
+  return ensure_workspace(c);
+}
+
+int gnnis_set_replicas(gnnis_handle h, int32_t n_rep, const int32_t* solvent_id, const float* dielectric) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (n_rep < 1 || !solvent_id || !dielectric) {
+    c->err = "gnnis_set_replicas: bad arguments";
+    return -1;
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  std::vector<float> pref(n_rep);
+  for (int r = 0; r < n_rep; ++r) {
+    if (solvent_id[r] < 0 || (c->have_weights && solvent_id[r] >= c->S)) {
+      c->err = "gnnis_set_replicas: solvent id outside the embedding table";
+      return -1;
+    }
+    // fp32 evaluation order of GNN_Layers.py:2133-2139: (-0.5*138.935485) * (1/solute - 1/eps)
+    float inv = 1.0f / dielectric[r];
+    pref[r] = (float)(-0.5 * 138.935485) * (1.0f - inv);
+  }
+  if (dev_alloc(c, &c->solvent_id, (size_t)n_rep) || dev_alloc(c, &c->pref, (size_t)n_rep)) return -1;
+  GNNIS_CUDA_OK(cudaMemcpy(c->solvent_id, solvent_id, n_rep * sizeof(int), cudaMemcpyHostToDevice));
+  GNNIS_CUDA_OK(cudaMemcpy(c->pref, pref.data(), n_rep * sizeof(float), cudaMemcpyHostToDevice));
+  c->R = n_rep;
+  return ensure_workspace(c);
+}
+
+int gnnis_set_model_constants(gnnis_handle h, float fraction, float scaling_factor, float cutoff) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (!(cutoff > 0.0f)) {
+    c->err = "cutoff must be positive";
+    return -1;
+  }
+  c->fraction = fraction;
+  c->scaling = scaling_factor;
+  c->cutoff = cutoff;
+  return 0;
+}
+
+int gnnis_build_neighbors(gnnis_handle h, const float* pos_dev, int32_t predicate, int32_t* row_ptr_dev,
+                          int32_t* col_dev, float* r_dev, int64_t capacity, int64_t* n_edges_host, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (check_ready(c, false)) return -1;
+  if (!pos_dev || !row_ptr_dev || !n_edges_host) {
+    c->err = "gnnis_build_neighbors: NULL argument";
+    return -1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  const int n = c->R * c->N;
+  if (launch_born_count(c, pos_dev, predicate, st)) return -1;
+  if (launch_fill_edges(c, pos_dev, predicate, row_ptr_dev, col_dev, nullptr, r_dev, col_dev ? capacity : 0, st)) return -1;
+  GNNIS_CUDA_OK(cudaMemcpyAsync(row_ptr_dev + n, c->row_ptr + n, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  GNNIS_CUDA_OK(cudaMemcpyAsync(n_edges_host, c->n_edges_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  GNNIS_CUDA_OK(cudaStreamSynchronize(st));
+  if (*n_edges_host > capacity) {
+    c->err = "gnnis_build_neighbors: capacity too small";
+    return -2;
+  }
+  return 0;
+}
+
+int gnnis_energy_force(gnnis_handle h, const float* pos_dev, float* e_rep_dev, float* force_dev, uint32_t flags,
+                       void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (!pos_dev || !e_rep_dev) {
+    c->err = "gnnis_energy_force: NULL argument";
+    return -1;
+  }
+  return energy_force_impl(c, pos_dev, e_rep_dev, force_dev, flags, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int gnnis_energy_force_host(gnnis_handle h, const float* pos_host, float* e_rep_host, float* force_host, uint32_t flags) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (check_ready(c, !(flags & GNNIS_FLAG_GB_ONLY))) return -1;
+  if (!pos_host || !e_rep_host) {
+    c->err = "gnnis_energy_force_host: NULL argument";
+    return -1;
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->own_stream;
+  size_t n = (size_t)c->R * c->N;
+  GNNIS_CUDA_OK(cudaMemcpyAsync(c->h_pos_dev, pos_host, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  bool want = !(flags & GNNIS_FLAG_NO_FORCES);
+  int rc = energy_force_impl(c, c->h_pos_dev, c->h_e_dev, want ? c->h_f_dev : nullptr, flags, st, nullptr);
+  if (rc) return rc;
+  GNNIS_CUDA_OK(cudaMemcpyAsync(e_rep_host, c->h_e_dev, c->R * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (want && force_host)
+    GNNIS_CUDA_OK(cudaMemcpyAsync(force_host, c->h_f_dev, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  GNNIS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gnnis_get_atom_energies(gnnis_handle h, float* e_atom_dev, float* sa_atom_dev, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || check_ready(c, false)) return -1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  size_t n = (size_t)c->R * c->N;
+  if (e_atom_dev) GNNIS_CUDA_OK(cudaMemcpyAsync(e_atom_dev, c->e_atom, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (sa_atom_dev) GNNIS_CUDA_OK(cudaMemcpyAsync(sa_atom_dev, c->sa_atom, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int gnnis_get_born_radii(gnnis_handle h, float* born_dev, float* born_scaled_dev, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || check_ready(c, false)) return -1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  size_t n = (size_t)c->R * c->N;
+  if (born_dev) GNNIS_CUDA_OK(cudaMemcpyAsync(born_dev, c->born, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (born_scaled_dev) GNNIS_CUDA_OK(cudaMemcpyAsync(born_scaled_dev, c->born_s, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int gnnis_last_edge_count(gnnis_handle h, int64_t* n_edges_host, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !n_edges_host || check_ready(c, false)) return -1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GNNIS_CUDA_OK(cudaMemcpyAsync(n_edges_host, c->n_edges_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  GNNIS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int64_t gnnis_launch_count(gnnis_handle h) { return h ? reinterpret_cast<Ctx*>(h)->launches : 0; }
+
+int32_t gnnis_num_stages(void) { return kNumStages; }
+const char* gnnis_stage_name(int32_t i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+
+int gnnis_profile_eval(gnnis_handle h, const float* pos_dev, float* e_rep_dev, float* force_dev, uint32_t flags,
+                       void* stream, float* stage_ms_host, int32_t n_stages) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !stage_ms_host || n_stages < kNumStages) return -1;
+  StageTimer tm;
+  tm.st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = energy_force_impl(c, pos_dev, e_rep_dev, force_dev, flags, tm.st, &tm);
+  cudaStreamSynchronize(tm.st);
+  for (int i = 0; i < n_stages; ++i) stage_ms_host[i] = 0.0f;
+  for (size_t i = 0; i + 1 < tm.ev.size(); ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]);
+    if (tm.stage[i] >= 0) stage_ms_host[tm.stage[i]] += ms;
+  }
+  for (cudaEvent_t e : tm.ev) cudaEventDestroy(e);
+  return rc;
+}
+
+}  // extern "C"

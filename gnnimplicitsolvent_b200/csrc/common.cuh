@@ -1,0 +1,163 @@
+// common.cuh -- context, layouts and device helpers shared by the gnnis kernels (sm_100a).
+//
+// HBM layout (all fp32 unless noted), replica-major, n = R*N atoms:
+//   pos/force        [R][N][3]                         (the reference's flat [R*N,3], GNN_Models.py:873)
+//   per molecule     q, rho, s, alpha, beta, gamma [N]; radidx [N] int32; d0/m0 [U*U]
+//   per replica      solvent_id [R] int32, pref [R] = -0.5*138.935485*(1 - 1/eps)
+//   CSR (GNN graph)  row_ptr [n+1] int32, col [E] int32 (global source), pair [E] u32 = tgt_ul<<16 | src_ul
+//                    (unit-local indices), r_e [E]
+//   node tensors     P_l, Q_l, a_l [n][64] (l = 1..3), o_l [n][64] (l = 1,2), o_3 [n][2], abar [n][64],
+//                    Pbar, Qbar [n][64], born B, dB/dI, B', dE/dB', Bbar [n]
+//   pair adjoint     rbar [n][N]  (slot [target][source-in-replica], only GNN-edge slots are ever read)
+// Per-edge activations are never stored: the adjoint recomputes them tile by tile (SURVEY.md §7 hard part 3).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/gnnis.h"
+
+namespace gnnis {
+
+constexpr float kOffset = 0.0195141f;     // GNN_Layers.py:25,1000,1016
+constexpr float kNeckScale = 0.826836f;   // GNN_Layers.py:1014
+constexpr float kNeckCut = 0.68f;         // GNN_Layers.py:1015
+constexpr float kCoulomb = 138.935485f;   // GNN_Layers.py:2137
+constexpr float kProbe = 0.14f;           // GNN_Models.py:847
+constexpr float kEps = 1e-6f;             // torch.nn.PairwiseDistance eps (GNN_Models.py:78,912)
+constexpr int kH = 64;                    // hidden
+constexpr int kT = 128;                   // hidden_token
+constexpr int kRbf = 20;                  // _NUM_KERNELS (GNN_Layers.py:2153)
+constexpr int kRbfLd = 24;                // padded row of the rbf tile
+constexpr int kTileE = 128;               // edges per tile
+constexpr int kTileLd = 68;               // padded row (floats) of a [128][64] tile
+constexpr int kUnitAtomsMax = 64;         // atoms per work unit held in shared-memory tables
+constexpr int kEdgeThreads = 256;
+constexpr int kNodeRows = 64;
+constexpr int kNodeThreads = 256;
+constexpr int kPairThreads = 128;
+
+struct LayerW {
+  int cin, cout;
+  // forward, reduction-major ("k-major") matrices: M[k][out]
+  float *Wi_t, *Wj_t;  // [cin][64]   message1.weight[:, 0:cin]^T, [:, cin:2cin]^T
+  float *Wr_t;         // [20][64]    message1.weight[:, 2cin:]^T
+  float *b1;           // [64]
+  float *W2_t;         // [64][64]    message2.weight^T
+  float *b2;           // [64]
+  float *W3a_t;        // [64][128]   lin1.weight[:, 0:64]^T
+  float *sbias;        // [S][128]    lin1.weight[:, 64:] @ emb[s] + lin1.bias
+  float *W4_t;         // [128][cout] lin2.weight^T
+  float *b4;           // [cout]
+  // adjoint: the same matrices in torch layout are already reduction-major for the transposed products
+  float *Wi, *Wj;      // [64][cin]
+  float *Wr;           // [64][20]
+  float *W2;           // [64][64]
+  float *W3a;          // [128][64]
+  float *W4;           // [cout][128]
+};
+
+struct Ctx {
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  int num_sms = 148;
+  // model
+  bool have_weights = false;
+  int S = 0;  // num_solvents
+  LayerW L[3];
+  float* gamma_emb = nullptr;  // [S]
+  float fraction = 0.1f, scaling = 2.0f, cutoff = 0.6f;
+  float* wblob = nullptr;  // one allocation backing all weight matrices
+  // system
+  int N = 0, U = 0;
+  float *q = nullptr, *rho = nullptr, *s = nullptr, *alpha = nullptr, *beta = nullptr, *gamma = nullptr;
+  int* radidx = nullptr;
+  float *d0 = nullptr, *m0 = nullptr;
+  // replicas
+  int R = 0;
+  int* solvent_id = nullptr;
+  float* pref = nullptr;
+  // units
+  int G = 1;          // replicas per unit
+  int n_units = 0;
+  bool smem_tables = true;
+  // workspace (sized for R*N atoms, edge capacity grows on demand)
+  size_t ws_atoms = 0;
+  int64_t edge_cap = 0;
+  int *deg = nullptr, *row_ptr = nullptr, *blk_sum = nullptr, *col = nullptr;
+  uint32_t* pair = nullptr;
+  float* r_e = nullptr;
+  float *born = nullptr, *dBdI = nullptr, *born_s = nullptr, *dE_dBs = nullptr, *Bbar = nullptr, *dBs_dB = nullptr;
+  float *P[3] = {nullptr, nullptr, nullptr}, *Q[3] = {nullptr, nullptr, nullptr}, *a[3] = {nullptr, nullptr, nullptr};
+  float *o[3] = {nullptr, nullptr, nullptr};
+  float *abar = nullptr, *Pbar = nullptr, *Qbar = nullptr, *obar3 = nullptr;
+  float *rbar = nullptr;
+  float *e_atom = nullptr, *sa_atom = nullptr;
+  int64_t* n_edges_dev = nullptr;
+  // host-staging for gnnis_energy_force_host
+  float *h_pos_dev = nullptr, *h_e_dev = nullptr, *h_f_dev = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // bonds (optional harmonic terms)
+  int n_bonds = 0;
+  int* bond_idx = nullptr;
+  float *bond_r0 = nullptr, *bond_k = nullptr;
+  // dynamics workspace
+  size_t dyn_atoms = 0;
+  int dyn_hist = 0;
+  float *lb_S = nullptr, *lb_Y = nullptr, *lb_rho = nullptr, *lb_alpha = nullptr;
+  float *lb_g = nullptr, *lb_gprev = nullptr, *lb_xprev = nullptr, *lb_d = nullptr, *lb_e = nullptr, *lb_eprev = nullptr;
+  float *lb_step = nullptr, *lb_ftmp = nullptr, *lb_etmp = nullptr;
+  int *lb_state = nullptr, *lb_count = nullptr, *lb_active = nullptr;
+  float* masses = nullptr;
+};
+
+#define GNNIS_CUDA_OK(call)                                                                   \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+#define GNNIS_LAUNCH_CHECK()                                                                  \
+  do {                                                                                        \
+    c->launches++;                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess) {                                                                  \
+      c->err = std::string("kernel launch failed: ") + cudaGetErrorString(e_);                \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+// ---------------------------------------------------------------- device helpers
+// eps-distance exactly as torch's CPU PairwiseDistance evaluates it (tests/test_oracle.py):
+// d = (x_src - x_tgt) + 1e-6 per component, sqrt(fma(dz,dz,fma(dy,dy,dx*dx))).  Explicit _rn intrinsics so
+// that the compiler cannot re-associate or contract differently (bit-exact neighbour lists).
+__device__ __forceinline__ float eps_dist(float sx, float sy, float sz, float tx, float ty, float tz,
+                                          float& dx, float& dy, float& dz) {
+  dx = __fadd_rn(__fsub_rn(sx, tx), kEps);
+  dy = __fadd_rn(__fsub_rn(sy, ty), kEps);
+  dz = __fadd_rn(__fsub_rn(sz, tz), kEps);
+  float acc = __fmul_rn(dx, dx);
+  acc = __fmaf_rn(dy, dy, acc);
+  acc = __fmaf_rn(dz, dz, acc);
+  return __fsqrt_rn(acc);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// SiLU and its derivative from one exponential: silu(x) = x*sig, silu'(x) = sig*(1 + x*(1-sig))
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoidf_(x); }
+__device__ __forceinline__ void silu_fd(float x, float& f, float& d) {
+  float sg = sigmoidf_(x);
+  f = x * sg;
+  d = sg * (1.0f + x * (1.0f - sg));
+}
+__device__ __forceinline__ float silu_d(float x) {
+  float sg = sigmoidf_(x);
+  return sg * (1.0f + x * (1.0f - sg));
+}
+
+}  // namespace gnnis

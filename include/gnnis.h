@@ -1,0 +1,130 @@
+/* gnnis.h -- C ABI of the B200-native GNN implicit-solvent energy/force engine (libgnnis.so).
+ *
+ * Drop-in boundary for the reference's hot path.  The reference has no FFI: its boundary is a
+ * torch.nn.Module (`forward(positions, solvent_model, solvent_dielectric) -> energy`) consumed by
+ * openmm-torch's TorchForce (Simulation/helper_functions.py:777-785).  The Python classes in
+ * gnnimplicitsolvent_b200/GNN_Models.py keep that contract and call the functions below through ctypes
+ * with raw device pointers (tensor.data_ptr()) and the caller's CUDA stream.  No torch types appear here.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (gnnis_last_error gives the text);
+ * no C++ exception crosses the ABI.  Units: nm, kJ/mol, e.  All floating-point buffers are fp32.
+ * `*_dev` pointers are device memory owned by the caller; `*_host` pointers are host memory.
+ * `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Nothing in
+ * gnnis_energy_force synchronises the host; it is CUDA-graph capturable.
+ */
+#ifndef GNNIS_H_
+#define GNNIS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gnnis_ctx* gnnis_handle;
+
+/* flags for gnnis_energy_force / gnnis_minimize / gnnis_langevin */
+#define GNNIS_FLAG_DELTA 0x1u      /* GNN3_Multisolvent_embedding_run_multiple_Delta (GNN_Models.py:947-1065):
+                                      polar energy = E_GB(B') - E_GB(B)                                    */
+#define GNNIS_FLAG_NO_FORCES 0x2u  /* energy only (skips the adjoint pass)                                */
+#define GNNIS_FLAG_GB_ONLY 0x4u    /* plain GB-Neck2 (GNN_GBNeck_2, GNN_Models.py:173): B' = B, no SA term */
+#define GNNIS_FLAG_MLP_BF16 0x8u   /* edge-MLP GEMMs on tcgen05 tensor cores, bf16 operands / fp32 accum  */
+
+/* The shipped architecture's state dict (MachineLearning/trained_models/GNN.pt["model"]),
+ * as host pointers to the tensors in torch layout (Linear.weight = [out][in], row-major).  Layer l = 0..2
+ * is interaction{l+1} (IN_layer_all_swish_2pass_tokens, GNN_Layers.py:2211-2246). */
+typedef struct gnnis_weights {
+  int32_t hidden;        /* 64  */
+  int32_t hidden_token;  /* 128 */
+  int32_t num_solvents;  /* rows of the embedding tables (42 in GNN.pt) */
+  int32_t n_rbf;         /* 20  */
+  const float* solvent_embedding; /* [num_solvents][hidden]                        GNN_Models.py:361 */
+  const float* gamma_embedding;   /* [num_solvents]                                GNN_Models.py:362 */
+  const float* message1_w[3];     /* [hidden][cin_l + n_rbf], cin = 6, 2*hidden, 2*hidden  GNN_Layers.py:2163 */
+  const float* message1_b[3];     /* [hidden] */
+  const float* message2_w[3];     /* [hidden][hidden]                              GNN_Layers.py:2164 */
+  const float* message2_b[3];
+  const float* lin1_w[3];         /* [hidden_token][hidden + hidden]               GNN_Layers.py:2227 */
+  const float* lin1_b[3];
+  const float* lin2_w[3];         /* [cout_l][hidden_token], cout = hidden, hidden, 2  GNN_Layers.py:2229 */
+  const float* lin2_b[3];
+} gnnis_weights;
+
+int gnnis_create(gnnis_handle* out, int device);
+int gnnis_destroy(gnnis_handle h);
+const char* gnnis_last_error(gnnis_handle h);   /* h may be NULL: returns the last create() error */
+
+/* replaces load_state_dict on the reference module (helper_functions.py:772) */
+int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w);
+
+/* replaces the module constructor's `parameters` table (GNN_Models.py:68-70; format GNN_Trainer.py:829-869):
+ * params7_host [n_atoms][7] = [q, rho, s, alpha, beta, gamma, radindex]; d0/m0 [n_unique*n_unique] are the
+ * resampled neck tables (GNN_Layers.py:913-972; also checkpoint buffers aggregate_information._d0/_m0). */
+int gnnis_set_system(gnnis_handle h, int32_t n_atoms, const float* params7_host,
+                     const float* d0_host, const float* m0_host, int32_t n_unique);
+
+/* replaces set_num_reps(num_reps, solvent_models, solvent_dielectric) (GNN_Models.py:741-769) */
+int gnnis_set_replicas(gnnis_handle h, int32_t n_rep, const int32_t* solvent_id_host,
+                       const float* dielectric_host);
+
+/* ctor args fraction / scaling_factor (GNN_Models.py:704,718) and the GNN cutoff (hard-coded 0.6 at :795) */
+int gnnis_set_model_constants(gnnis_handle h, float fraction, float scaling_factor, float cutoff);
+
+/* replaces torch_cluster.radius_graph / the `edge_attributes < 0.6` boolean compaction (GNN_Models.py:794-804):
+ * sorted CSR by target then source.  predicate 0 = run path  ||x_src - x_tgt + 1e-6|| < cutoff,
+ * predicate 1 = data path  sum((x_i-x_j)^2) < cutoff^2 (torch_cluster semantics).
+ * row_ptr_dev [R*N+1] int32, col_dev [capacity] int32 (global source index), r_dev [capacity] fp32
+ * eps-distance (may be NULL).  *n_edges_host receives E (this call synchronises the stream).
+ * Returns -2 (nothing written to col/r) when capacity < E. */
+int gnnis_build_neighbors(gnnis_handle h, const float* pos_dev, int32_t predicate, int32_t* row_ptr_dev,
+                          int32_t* col_dev, float* r_dev, int64_t capacity, int64_t* n_edges_host, void* stream);
+
+/* replaces forward(positions, -1, .) + energy.backward() (GNN_Models.py:873-885 + autograd):
+ * pos_dev [R][N][3]; e_rep_dev [R] per-replica energies (sum = the reference's scalar);
+ * force_dev [R][N][3] = -dE/dpos (may be NULL with GNNIS_FLAG_NO_FORCES). */
+int gnnis_energy_force(gnnis_handle h, const float* pos_dev, float* e_rep_dev, float* force_dev,
+                       uint32_t flags, void* stream);
+
+/* same call with HOST buffers (pinned or pageable): H2D of positions, evaluation, D2H of energies and
+ * forces, one stream synchronisation at the end.  This is the end-to-end plug-in path bench.py times. */
+int gnnis_energy_force_host(gnnis_handle h, const float* pos_host, float* e_rep_host, float* force_host,
+                            uint32_t flags);
+
+/* ..._run_multiple_split (GNN_Models.py:1068-1083): per-atom polar and SA energies of the LAST evaluation */
+int gnnis_get_atom_energies(gnnis_handle h, float* e_atom_dev, float* sa_atom_dev, void* stream);
+/* Born radii B (GBNeck_interaction output, GNN_Layers.py:982-1008) and scaled B' of the LAST evaluation */
+int gnnis_get_born_radii(gnnis_handle h, float* born_dev, float* born_scaled_dev, void* stream);
+/* number of GNN edges found by the LAST evaluation (synchronises the stream) */
+int gnnis_last_edge_count(gnnis_handle h, int64_t* n_edges_host, void* stream);
+
+/* Batched per-replica L-BFGS (replaces simulation.minimizeEnergy(tolerance, maxIterations) driven by
+ * OpenMM's LocalEnergyMinimizer, helper_functions.py:614-624; semantics differ by design: one optimiser
+ * per replica, SURVEY.md §7 hard part 5).  pos_dev is updated in place.  Stops a replica when its
+ * gradient RMS < grad_tol (kJ/mol/nm) or after max_iter iterations (0 = 1000).
+ * status_dev [R] int32: 0 converged, 1 iteration limit, 2 non-finite energy/force (positions restored).
+ * Optional harmonic bonds k/2 (r-r0)^2 given per molecule (n_bonds, bond_idx_host[2*n_bonds],
+ * bond_r0_host, bond_k_host) stand in for the vacuum force field when testing. */
+int gnnis_set_bonds(gnnis_handle h, int32_t n_bonds, const int32_t* bond_idx_host,
+                    const float* bond_r0_host, const float* bond_k_host);
+int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* status_dev, int32_t* n_iter_host,
+                   float grad_tol, int32_t max_iter, int32_t history, uint32_t flags, void* stream);
+
+/* Batched LangevinMiddle integrator (replaces LangevinMiddleIntegrator(T, gamma, dt) + simulation.step,
+ * helper_functions.py:787-789, Simulator.py:402).  masses_host [N] (amu), temperature K, friction 1/ps,
+ * dt ps.  pos_dev/vel_dev [R][N][3] updated in place; Philox-style counter RNG keyed by (seed, step, atom). */
+int gnnis_langevin(gnnis_handle h, float* pos_dev, float* vel_dev, const float* masses_host,
+                   float temperature, float friction, float dt, int32_t n_steps, uint64_t seed,
+                   uint64_t first_step, uint32_t flags, void* stream);
+
+/* Number of kernels this library launched since the handle was created (bench.py's gpu_launches). */
+int64_t gnnis_launch_count(gnnis_handle h);
+/* Time of the individual kernel families of the last gnnis_profile_eval call, in ms (order: see gnnis_stage_name) */
+int gnnis_profile_eval(gnnis_handle h, const float* pos_dev, float* e_rep_dev, float* force_dev, uint32_t flags,
+                       void* stream, float* stage_ms_host, int32_t n_stages);
+int32_t gnnis_num_stages(void);
+const char* gnnis_stage_name(int32_t i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNIS_H_ */

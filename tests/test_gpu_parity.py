@@ -1,0 +1,174 @@
+"""GPU parity tests (run under gpurun on a B200): the CUDA path through the C ABI vs the golden vectors
+produced by the unmodified reference and vs the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): neighbour lists bit-exact; energies 1e-4 relative;
+forces 1e-3 relative RMS (fp32 mode)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CASES, load_case, rel_rms
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-4
+F_RRMS = 1e-3
+
+
+def _engine(case, weights, **kw):
+    from gnnimplicitsolvent_b200.engine import Engine
+    eng = Engine(case["params"], weights, device=0, **kw)
+    R = case["pos"].shape[0]
+    eng.set_replicas(R, case["solvent_ids"], case["dielectrics"])
+    return eng
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_neighbor_list_bit_exact(name, weights):
+    c = load_case(name)
+    eng = _engine(c, weights)
+    row_ptr, col, r = eng.build_neighbors(torch.from_numpy(c["pos"]).cuda())
+    R, N, _ = c["pos"].shape
+    deg = np.diff(row_ptr.cpu().numpy())
+    tgt = np.repeat(np.arange(R * N), deg)
+    np.testing.assert_array_equal(col.cpu().numpy(), c["edge_src"])
+    np.testing.assert_array_equal(tgt, c["edge_tgt"])
+    np.testing.assert_array_equal(r.cpu().numpy(), c["edge_r"])     # fp32 distances bit-identical
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_energy_forces_vs_golden(name, weights):
+    c = load_case(name)
+    eng = _engine(c, weights)
+    pos = torch.from_numpy(c["pos"]).cuda()
+    e, f = eng.energy_force(pos)
+    torch.cuda.synchronize()
+    assert eng.last_edge_count() == len(c["edge_src"])
+    born, _ = eng.born_radii()
+    np.testing.assert_allclose(born.cpu().numpy(), c["born"], rtol=2e-5)
+    e_atom, sa_atom = eng.atom_energies()
+    np.testing.assert_allclose(sa_atom.cpu().numpy(), c["sa_atom"], rtol=1e-4, atol=1e-5)
+    R, N, _ = c["pos"].shape
+    e_rep_ref = (c["e_atom"] + c["sa_atom"]).reshape(R, N).astype(np.float64).sum(1)
+    np.testing.assert_allclose(e.cpu().numpy(), e_rep_ref, rtol=E_RTOL)
+    assert abs(float(e.double().sum()) - float(c["energy_total"])) <= E_RTOL * abs(float(c["energy_total"]))
+    assert rel_rms(f.cpu().numpy(), c["forces"]) < F_RRMS
+
+
+@pytest.mark.parametrize("name", ["mixed_n21", "c2_n50_water", "n100_mixed"])
+def test_delta_mode_vs_golden(name, weights):
+    c = load_case(name)
+    eng = _engine(c, weights)
+    e, f = eng.energy_force(torch.from_numpy(c["pos"]).cuda(), delta=True)
+    assert abs(float(e.double().sum()) - float(c["energy_total_delta"])) <= E_RTOL * abs(float(c["energy_total_delta"]))
+    assert rel_rms(f.cpu().numpy(), c["forces_delta"]) < F_RRMS
+
+
+def test_single_replica_override(weights):
+    """solvent_model != -1 path (GNN_Models.py:780-786): one replica, one solvent."""
+    c = load_case("mixed_n21")
+    from gnnimplicitsolvent_b200.engine import Engine
+    eng = Engine(c["params"], weights)
+    eng.set_replicas(1, c["solvent_ids"][:1], c["dielectrics"][:1])
+    e, f = eng.energy_force(torch.from_numpy(c["pos"][:1]).cuda())
+    assert abs(float(e[0]) - float(c["energy_rep0_override"])) <= E_RTOL * abs(float(c["energy_rep0_override"]))
+    assert rel_rms(f.cpu().numpy()[0], c["forces_rep0_override"]) < F_RRMS
+
+
+@pytest.mark.parametrize("N,R", [(7, 3), (13, 37), (33, 9), (64, 5), (65, 3), (130, 2)])
+def test_vs_oracle_random_weights(N, R):
+    """Seeded random-init weights, ragged unit packing (R not a multiple of the unit size), both table modes
+    (N <= 64 shared-memory tables, N > 64 global tables)."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    from oracle import gnn_oracle as O
+    sd = O.random_state_dict(seed=N)
+    mol = synth.synth_molecule(N, seed=100 + N)
+    pos = synth.conformers(mol["pos"], R, 0.01, seed=N * 7 + R)
+    sids = [(3 * r) % 39 for r in range(R)]
+    diel = [synth.SOLVENT_DIELECTRICS[s] for s in sids]
+    o = O.evaluate(mol["params"], pos, sids, diel, sd)
+    eng = Engine(mol["params"], sd)
+    eng.set_replicas(R, sids, diel)
+    e, f = eng.energy_force(torch.from_numpy(pos).cuda())
+    np.testing.assert_allclose(e.cpu().numpy(), o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
+    assert rel_rms(f.cpu().numpy(), o["forces"].numpy()) < F_RRMS
+    row_ptr, col, r = eng.build_neighbors(torch.from_numpy(pos).cuda())
+    rp, cl, rr = O.neighbor_list_numpy(pos)
+    np.testing.assert_array_equal(row_ptr.cpu().numpy(), rp)
+    np.testing.assert_array_equal(col.cpu().numpy(), cl)
+
+
+def test_gb_only_mode_vs_oracle():
+    """Plain GB-Neck2 (no GNN): validates the hand-written Born/GB adjoint on its own."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    from oracle import gnn_oracle as O
+    mol = synth.synth_molecule(30, seed=3)
+    R = 4
+    pos = synth.conformers(mol["pos"], R, 0.01, seed=5)
+    x = torch.tensor(mol["params"], dtype=torch.float32).repeat(R, 1)
+    p = torch.tensor(pos.reshape(-1, 3), requires_grad=True)
+    ei = O.all_pairs_index(30, R)
+    r = O.eps_distance(p, ei[0], ei[1])
+    d0, m0 = O.neck_tables()
+    B, _ = O.born_radii(x, ei[0], ei[1], r, d0, m0)
+    diel = torch.full((R * 30, 1), 78.5)
+    e = O.gb_energy(torch.stack((B, x[:, 0]), 1), ei[0], ei[1], r, diel)
+    e.sum().backward()
+    eng = Engine(mol["params"], None)
+    eng.set_replicas(R, [0] * R, [78.5] * R)
+    eg, fg = eng.energy_force(torch.from_numpy(pos).cuda(), gb_only=True)
+    np.testing.assert_allclose(eg.cpu().numpy(), e.detach().reshape(R, 30).sum(1).numpy(), rtol=E_RTOL)
+    assert rel_rms(fg.cpu().numpy(), (-p.grad).reshape(R, 30, 3).numpy()) < F_RRMS
+
+
+def test_data_path_predicate_bit_exact():
+    """torch_cluster.radius_graph semantics (sum of squares < r^2), SURVEY.md §8 a4'."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    from oracle import gnn_oracle as O
+    mol = synth.synth_molecule(40, seed=11)
+    pos = synth.conformers(mol["pos"], 6, 0.02, seed=2)
+    eng = Engine(mol["params"], None)
+    eng.set_replicas(6, [0] * 6, [78.5] * 6)
+    row_ptr, col, _ = eng.build_neighbors(torch.from_numpy(pos).cuda(), predicate="data")
+    rp, cl, _ = O.neighbor_list_numpy(pos, predicate="data")
+    np.testing.assert_array_equal(row_ptr.cpu().numpy(), rp)
+    np.testing.assert_array_equal(col.cpu().numpy(), cl)
+
+
+def test_deterministic_bitwise(weights):
+    """No float atomics anywhere: two evaluations of the same input are bit-identical."""
+    c = load_case("mixed_n50")
+    eng = _engine(c, weights)
+    pos = torch.from_numpy(c["pos"]).cuda()
+    e1, f1 = eng.energy_force(pos)
+    e2, f2 = eng.energy_force(pos)
+    assert torch.equal(e1, e2) and torch.equal(f1, f2)
+
+
+def test_replica_invariance_full_size(weights):
+    """Size-independent property at a large batch: every replica of an identical-conformer batch gives the
+    same energy/forces as a single replica (replicas are independent)."""
+    c = load_case("c2_n50_water")
+    R = 1024
+    pos1 = c["pos"][:1]
+    from gnnimplicitsolvent_b200.engine import Engine
+    eng = Engine(c["params"], weights)
+    eng.set_replicas(R, [0] * R, [78.5] * R)
+    pos = torch.from_numpy(np.repeat(pos1, R, axis=0)).cuda()
+    e, f = eng.energy_force(pos)
+    assert torch.equal(e, e[:1].expand(R)) and torch.equal(f, f[:1].expand(R, -1, -1))
+    assert abs(float(e[0]) - float((c["e_atom"] + c["sa_atom"])[:50].sum())) < E_RTOL * abs(float(e[0]))
+
+
+def test_host_api_matches_device_api(weights):
+    c = load_case("mixed_n21")
+    eng = _engine(c, weights)
+    pos = torch.from_numpy(c["pos"]).pin_memory()
+    e_h = torch.empty(c["pos"].shape[0]).pin_memory()
+    f_h = torch.empty(c["pos"].shape).pin_memory()
+    eng.energy_force_host(pos, e_h, f_h)
+    e, f = eng.energy_force(pos.cuda())
+    assert torch.equal(e.cpu(), e_h) and torch.equal(f.cpu(), f_h)
