@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- force evaluations/s (atoms*evals/s) of the batched GB-Neck2 + GNN energy/force hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation (host cores)
+
+Workload (BASELINE.json configs[1]): drug-sized synthetic molecule, N = 50 atoms,
+R = 4096 conformers per GPU in water (solvent id 0, eps 78.5), shipped GNN.pt weights.  A "step" is ONE batched
+energy+force evaluation of all replicas of the rank, neighbour-list build included.  Multi-GPU: replicas are
+sharded (weak scaling: 4096 per rank), no collective inside the step; one NCCL all_gather of the energies after.
+
+Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps L2 is flushed
+(a 256 MiB buffer is overwritten, untimed) and the step cycles through 4 distinct position sets.  The reported
+time is the sum over the K steps, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_ATOMS = 50
+R_PER_GPU = 4096
+MOL_SEED = 50
+METRIC = "force evals/sec (atoms*evals/s), batched conformers"
+UNIT = "atoms*evals/s"
+
+
+def load_weights():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gnn_weights.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def workload(n_rep, n_sets, seed0):
+    from gnnimplicitsolvent_b200 import synth
+    mol = synth.synth_molecule(N_ATOMS, seed=MOL_SEED)
+    sets = [synth.conformers(mol["pos"], n_rep, 0.01, seed=seed0 + s) for s in range(n_sets)]
+    return mol, sets
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._idx = gpu_index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self._idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+                if out:
+                    f = [x.strip() for x in out[0].split(",")]
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for nm, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_port_eval_time(mol, pos, sids, diel, sd, n_eval, use_reference):
+    """fwd+bwd of the reference's CPU path (imported reference if the tree is present, else the oracle port)
+    on all host cores; returns (median seconds per evaluation, kind)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    if use_reference:
+        from oracle import ref_harness as H
+        model = H.build_reference_run_model(mol["params"].tolist(), sd, pos.shape[0], sids, diel)
+        for i in range(n_eval + 1):
+            p = torch.tensor(pos.reshape(-1, 3), requires_grad=True)
+            t0 = time.perf_counter()
+            e = model(p, torch.tensor(-1), torch.tensor(78.5))
+            e.backward()
+            if i:
+                times.append(time.perf_counter() - t0)
+        return float(np.median(times)), "reference"
+    from oracle import gnn_oracle as O
+    for i in range(n_eval + 1):
+        t0 = time.perf_counter()
+        O.evaluate(mol["params"], pos, sids, diel, sd)
+        if i:
+            times.append(time.perf_counter() - t0)
+    return float(np.median(times)), "port"
+
+
+def reference_available():
+    try:
+        from oracle import ref_harness as H
+        return H.reference_root() is not None
+    except Exception:
+        return False
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import warnings
+    warnings.filterwarnings("ignore")
+    sd = load_weights()
+    r_cpu = 64
+    mol, sets = workload(r_cpu, 1, 9000)
+    sids, diel = [0] * r_cpu, [78.5] * r_cpu
+    use_ref = reference_available()
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_port_eval_time(mol, sets[0], sids, diel, sd, 1, use_ref)
+    t0 = time.perf_counter()
+    per_eval, kind = cpu_port_eval_time(mol, sets[0], sids, diel, sd, args.steps, use_ref)
+    value = r_cpu * N_ATOMS / per_eval
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: N={N_ATOMS} atoms, water, energy+forces; each step = a bounded sample of {r_cpu} of the "
+                               f"{R_PER_GPU} conformers (the reference is linear in R)", "weights": "shipped GNN.pt"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{r_cpu} conformers x {args.steps} fwd+bwd evaluations, median"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--replicas", type=int, default=R_PER_GPU, help="replicas per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from gnnimplicitsolvent_b200.engine import Engine
+    sd = load_weights()
+    R = args.replicas
+    mol, sets = workload(R, 4, 1000 * N_ATOMS + 17 * rank)
+    sids, diel = [0] * R, [78.5] * R
+    eng = Engine(mol["params"], sd, device=local_rank)
+    eng.set_replicas(R, sids, diel)
+    dev_sets = [torch.from_numpy(s).cuda() for s in sets]
+    e_out = torch.empty(R, dtype=torch.float32, device="cuda")
+    f_out = torch.empty(R, N_ATOMS, 3, dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def step(i):
+        eng.energy_force(dev_sets[i % len(dev_sets)], out_energy=e_out, out_force=f_out)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    n_edges = eng.last_edge_count()
+
+    # ---- parity gate on the benchmark inputs (untimed): first 8 replicas vs the CPU oracle
+    parity = None
+    if rank == 0:
+        from oracle import gnn_oracle as O
+        k = 8
+        o = O.evaluate(mol["params"], sets[0][:k], sids[:k], diel[:k], sd)
+        eng.energy_force(dev_sets[0], out_energy=e_out, out_force=f_out)
+        e_err = float(((e_out[:k].cpu() - o["energy_rep"]).abs() / o["energy_rep"].abs()).max())
+        f_err = float(((f_out[:k].cpu() - o["forces"]) ** 2).sum().sqrt() / (o["forces"] ** 2).sum().sqrt())
+        row_ptr, col, _ = eng.build_neighbors(dev_sets[0])
+        rp, cl, _ = O.neighbor_list_numpy(sets[0][:k])
+        nk = k * N_ATOMS
+        nb_ok = bool(np.array_equal(row_ptr[: nk + 1].cpu().numpy(), rp) and np.array_equal(col[: rp[-1]].cpu().numpy(), cl))
+        parity = {"energy_max_rel": e_err, "force_rel_rms": f_err, "neighbors_equal": nb_ok, "replicas_checked": k}
+
+    # ---- device-resident timing
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        for i in range(args.steps):
+            flush.fill_(float(i))          # L2 flush, untimed
+            ev[i][0].record()
+            step(i)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+    launches = eng.launch_count() - launches0
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if dist:
+        dist.barrier()
+
+    # ---- per-kernel-family times (CUDA events inside libgnnis, same stream) for the roofline entry
+    stage_acc = {}
+    n_prof = 5
+    for i in range(n_prof):
+        flush.fill_(1.0)
+        st = eng.profile_eval(dev_sets[i % 4])
+        for k_, v in st.items():
+            stage_acc[k_] = stage_acc.get(k_, 0.0) + v / n_prof
+
+    # ---- end-to-end through the host-buffer C-ABI call (H2D + eval + D2H inside the timed region)
+    pin_pos = [torch.from_numpy(s).pin_memory() for s in sets]
+    pin_e = torch.empty(R, dtype=torch.float32).pin_memory()
+    pin_f = torch.empty(R, N_ATOMS, 3, dtype=torch.float32).pin_memory()
+    for i in range(2):
+        eng.energy_force_host(pin_pos[i], pin_e, pin_f)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.energy_force_host(pin_pos[i % 4], pin_e, pin_f)
+    t_e2e = time.perf_counter() - t0
+    e_check = float(pin_e.double().sum())
+
+    t_all = torch.tensor([t_ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        gathered = [torch.empty_like(e_out) for _ in range(world)]
+        dist.all_gather(gathered, e_out)     # the one collective of the path: final gather of energies
+    t_ms, t_e2e_ms = float(t_all[0]), float(t_all[1])
+
+    if rank == 0:
+        atoms_total = world * R * N_ATOMS
+        value = atoms_total * args.steps / (t_ms * 1e-3)
+        e2e_value = atoms_total * args.steps / (t_e2e_ms * 1e-3)
+        peaks, peak_kind = measured_peaks()
+        # dominant kernel family: edge adjoint (3 launches per evaluation, one per interaction layer).
+        # algorithmic FLOPs per launch (reference formulation, input-gradient only, no recompute counted):
+        #   layer l: 2 * E * (K_l*64 + 64*64), K = 26, 148, 148  (DESIGN.md "roofline accounting")
+        dom = max(stage_acc, key=stage_acc.get) if stage_acc else "edge_bwd"
+        e_per_launch = float(n_edges)
+        flops_edge = [2.0 * e_per_launch * (k_ * 64 + 64 * 64) for k_ in (26, 148, 148)]
+        if dom in ("edge_bwd", "edge_fwd"):
+            flops_launch = sum(flops_edge) / 3.0
+            dur_ms = stage_acc[dom] / 3.0
+        else:
+            flops_launch, dur_ms = float("nan"), stage_acc.get(dom, float("nan"))
+        achieved = flops_launch / (dur_ms * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_kind} bf16 sustained (fp32 CUDA-core kernel)",
+                    "avg_launch_ms": dur_ms, "stage_ms": stage_acc}
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            import warnings
+            warnings.filterwarnings("ignore")
+            r_cpu = 64
+            per_eval, kind = cpu_port_eval_time(mol, sets[0][:r_cpu], sids[:r_cpu], diel[:r_cpu], sd, 3, reference_available())
+            cpu_baseline = {"value": r_cpu * N_ATOMS / per_eval, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                            "sample": f"{r_cpu} of {R} conformers, 3 fwd+bwd evaluations, median ({per_eval * 1e3:.1f} ms each)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2: N={N_ATOMS} atoms x R={R} conformers per GPU, water, energy+forces incl. neighbour build",
+                       "weights": "shipped GNN.pt", "edges_per_eval": n_edges, "l2": "flushed between timed steps (256 MiB write)",
+                       "position_sets": 4, "parallelism": f"replica-sharded x{world}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * N_ATOMS * 12,
+                    "d2h_bytes_per_step": R * N_ATOMS * 12 + R * 4, "ms_per_step": t_e2e_ms / args.steps, "energy_checksum": e_check},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
