@@ -14,6 +14,7 @@ int launch_gb_energy(Ctx*, const float*, const float*, int, int, float*, cudaStr
 int launch_born_adjoint(Ctx*, const float*, int, float*, cudaStream_t);
 int launch_reduce_energy(Ctx*, const float*, float*, cudaStream_t);
 int launch_edge_fwd(Ctx*, int, cudaStream_t);
+int launch_tile_perm(Ctx*, cudaStream_t);
 int launch_edge_bwd(Ctx*, int, int, cudaStream_t);
 int launch_node_pre1(Ctx*, cudaStream_t);
 int launch_node_fwd(Ctx*, int, cudaStream_t);
@@ -84,7 +85,7 @@ static int ensure_workspace(Ctx* c) {
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   int nblk = (int)((n + kPairThreads - 1) / kPairThreads);
   if (dev_alloc(c, &c->deg, n) || dev_alloc(c, &c->row_ptr, n + 1) || dev_alloc(c, &c->blk_sum, (size_t)nblk + 1) ||
-      dev_alloc(c, &c->col, (size_t)cap) || dev_alloc(c, &c->pair, (size_t)cap) || dev_alloc(c, &c->r_e, (size_t)cap))
+      dev_alloc(c, &c->col, (size_t)cap) || dev_alloc(c, &c->pair, (size_t)cap) || dev_alloc(c, &c->perm, (size_t)cap + 128) || dev_alloc(c, &c->r_e, (size_t)cap))
     return -1;
   float** scal[] = {&c->born, &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->e_atom, &c->sa_atom};
   for (float** p : scal)
@@ -142,6 +143,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
   if (launch_born_count(c, pos, 0, st)) return -1;
   if (!gb_only) {
     if (launch_fill_edges(c, pos, 0, c->row_ptr, nullptr, c->pair, c->r_e, c->edge_cap, st)) return -1;
+    if (want_grad && launch_tile_perm(c, st)) return -1;
     if (tm) tm->mark(kStNodeFwd);
     if (launch_node_pre1(c, st)) return -1;
     for (int l = 0; l < 3; ++l) {
@@ -241,6 +243,7 @@ int gnnis_destroy(gnnis_handle h) {
                 &c->lb_count, &c->lb_active};
   for (int** p : ip) dev_free(p);
   dev_free(&c->pair);
+  dev_free(&c->perm);
   dev_free(&c->n_edges_dev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;

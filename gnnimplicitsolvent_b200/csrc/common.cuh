@@ -87,6 +87,7 @@ struct Ctx {
   int64_t edge_cap = 0;
   int *deg = nullptr, *row_ptr = nullptr, *blk_sum = nullptr, *col = nullptr;
   uint32_t* pair = nullptr;
+  uint8_t* perm = nullptr;
   float* r_e = nullptr;
   float *born = nullptr, *dBdI = nullptr, *born_s = nullptr, *dE_dBs = nullptr, *Bbar = nullptr, *dBs_dB = nullptr;
   float *P[3] = {nullptr, nullptr, nullptr}, *Q[3] = {nullptr, nullptr, nullptr}, *a[3] = {nullptr, nullptr, nullptr};
@@ -146,7 +147,8 @@ __device__ __forceinline__ float eps_dist(float sx, float sy, float sz, float tx
   return __fsqrt_rn(acc);
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// sigmoid from MUFU.EX2 + MUFU.RCP (~2 ulp); the parity gates (1e-4 / 1e-3) guard this choice
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // SiLU and its derivative from one exponential: silu(x) = x*sig, silu'(x) = sig*(1 + x*(1-sig))
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoidf_(x); }

@@ -9,9 +9,9 @@
 // Work decomposition.  A *unit* = G consecutive replicas (<= kUnitAtomsMax atoms).  One persistent CTA owns a
 // unit at a time: its P/Q tables (and, in the adjoint, abar / Pbar / Qbar) live in shared memory, its edges are
 // the contiguous CSR range of its atoms and are processed in tiles of 128 edges.  Edges never leave the unit, so
-// every reduction is CTA-local: the segmented add into the target rows walks the tile in CSR order (ascending
-// source per target == the reference's CPU index_add order), the source-side reduction of the adjoint walks it in
-// the same fixed order with ownership partitioned by (index mod 4) -- no atomics, bit-reproducible.
+// every reduction is CTA-local: the segmented add into the target rows walks the tile in CSR order, the
+// source-side reduction of the adjoint walks a precomputed source-sorted permutation of the tile; both use
+// exclusive ownership + a fixed-order carry fix-up (seg_reduce_tile) -- no atomics, bit-reproducible.
 // Per-edge activations are never written to HBM; the adjoint recomputes u, v, w per tile.
 #include "common.cuh"
 
@@ -32,6 +32,8 @@ struct EdgeArgs {
   float *Pbar, *Qbar;   // bwd out: [n][64]
   float* rbar;          // bwd: dense [n][N]
   int rbar_accumulate;
+  const uint8_t* perm;  // [E] tile-local edge index at source-sorted position (tile_perm_kernel)
+  int unit_atoms;       // G*N: rows of the shared-memory tables
 };
 
 // C[128][64] += A[128][K] * B[K][64]; thread (te, tc) owns rows te+32i (i<4), cols tc*4..+3 and 32+tc*4..+3
@@ -72,31 +74,92 @@ __device__ __forceinline__ void zero_acc(float (&acc)[4][8]) {
 }
 
 // radial basis of one edge (GNN_Layers.py:2194-2208): d = r/cutoff, env = 1/d - 28 d^5 + 48 d^6 - 21 d^7,
-// rbf_k = env sin(k pi d); optionally d rbf_k / dr.  Rows are padded to kRbfLd with zeros.
+// rbf_k = env sin(k pi d); optionally d rbf_k / dr.  sin/cos(k pi d) come from one sincospi and the Chebyshev
+// recurrence s_{k+1} = 2 cos(x) s_k - s_{k-1} (2 transcendentals + 40 FMA instead of 20-40 sinf calls; the
+// recurrence error is damped by the envelope, which vanishes cubically at d -> 1).  Rows padded to kRbfLd.
 template <bool DERIV>
 __device__ __forceinline__ void rbf_row(float r, float inv_cutoff, float* __restrict__ out, float* __restrict__ dout) {
-  float d = r * inv_cutoff;
-  float d2 = d * d, d4 = d2 * d2, d5 = d4 * d;
-  float env = 1.0f / d - 28.0f * d5 + 48.0f * (d5 * d) - 21.0f * (d5 * d2);
+  const float d = r * inv_cutoff;
+  const float d2 = d * d, d4 = d2 * d2, d5 = d4 * d;
+  const float env = 1.0f / d - 28.0f * d5 + 48.0f * (d5 * d) - 21.0f * (d5 * d2);
   float denv = 0.0f;
   if (DERIV) denv = -1.0f / d2 - 140.0f * d4 + 288.0f * d5 - 147.0f * (d5 * d);
+  float s1, c1;
+  sincospif(d, &s1, &c1);
+  const float twoc = 2.0f * c1;
+  float sp = 0.0f, sc = s1, cp = 1.0f, cc = c1;
+  float o[kRbfLd], od[kRbfLd];
 #pragma unroll
   for (int k = 0; k < kRbf; ++k) {
-    float fk = 3.14159265358979323846f * (float)(k + 1);   // _FREQUENCIES = pi * arange(1, 21) in fp32
-    float sn, cs;
+    o[k] = env * sc;
+    if (DERIV) od[k] = (denv * sc + env * (3.14159265358979323846f * (float)(k + 1)) * cc) * inv_cutoff;
+    float sn = fmaf(twoc, sc, -sp);
+    sp = sc;
+    sc = sn;
     if (DERIV) {
-      sincosf(fk * d, &sn, &cs);
-      dout[k] = (denv * sn + env * fk * cs) * inv_cutoff;
-    } else {
-      sn = sinf(fk * d);
+      float cn = fmaf(twoc, cc, -cp);
+      cp = cc;
+      cc = cn;
     }
-    out[k] = env * sn;
   }
 #pragma unroll
   for (int k = kRbf; k < kRbfLd; ++k) {
-    out[k] = 0.0f;
-    if (DERIV) dout[k] = 0.0f;
+    o[k] = 0.0f;
+    od[k] = 0.0f;
   }
+#pragma unroll
+  for (int k4 = 0; k4 < kRbfLd / 4; ++k4) {
+    *reinterpret_cast<float4*>(out + 4 * k4) = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
+    if (DERIV)
+      *reinterpret_cast<float4*>(dout + 4 * k4) = make_float4(od[4 * k4], od[4 * k4 + 1], od[4 * k4 + 2], od[4 * k4 + 3]);
+  }
+}
+
+// Segmented add of the rows of a [128][kTileLd] tile into table rows selected by key[]: rows with equal keys are
+// contiguous in walk order (CSR order for targets, the precomputed source-sorted tile permutation for sources).
+// Thread (c, q) walks positions [32q, 32q+32); a run that continues the previous quarter's key is parked in
+// sCarry and added by a fixed-order fix-up pass, so no two threads ever update the same table entry
+// concurrently: deterministic, no atomics.  Ends with the table consistent (trailing __syncthreads).
+template <bool PERM>
+__device__ __forceinline__ void seg_reduce_tile(const float* __restrict__ sX, const int* __restrict__ sKey,
+                                                const uint8_t* __restrict__ sPerm, float* __restrict__ table,
+                                                float* __restrict__ sCarry, int* __restrict__ sCarryKey, int tid) {
+  const int c = tid & 63, q = tid >> 6, p0 = 32 * q;
+  int cur = sKey[PERM ? (int)sPerm[p0] : p0];
+  bool cont = false;
+  if (q > 0 && cur >= 0) cont = sKey[PERM ? (int)sPerm[p0 - 1] : p0 - 1] == cur;
+  if (c == 0) sCarryKey[q] = cont ? cur : -1;
+  bool first = true;
+  float run = 0.0f;
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const int e = PERM ? (int)sPerm[p0 + j] : p0 + j;
+    const int k = sKey[e];
+    const float v = sX[e * kTileLd + c];
+    if (k != cur) {
+      if (cur >= 0) {
+        if (first && cont) sCarry[q * 64 + c] = run;
+        else table[cur * 64 + c] += run;
+      }
+      cur = k;
+      run = 0.0f;
+      first = false;
+    }
+    if (k >= 0) run += v;
+  }
+  if (cur >= 0) {
+    if (first && cont) sCarry[q * 64 + c] = run;
+    else table[cur * 64 + c] += run;
+  }
+  __syncthreads();
+  if (tid < 64) {
+#pragma unroll
+    for (int qq = 1; qq < 4; ++qq) {
+      int k = sCarryKey[qq];
+      if (k >= 0) table[k * 64 + tid] += sCarry[qq * 64 + tid];
+    }
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ void copy_rows(float* __restrict__ dst, const float* __restrict__ src, int nfloat) {
@@ -108,19 +171,51 @@ __device__ __forceinline__ void zero_rows(float* __restrict__ dst, int nfloat) {
     *reinterpret_cast<float4*>(dst + t) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ------------------------------------------------------------------------------------------ tile permutation
+// For every 128-edge tile of every unit: positions sorted by (source, edge) -> tile-local edge index (uint8).
+// Computed once per evaluation (after the CSR fill), reused by the three adjoint launches.
+__global__ void __launch_bounds__(kTileE) tile_perm_kernel(int n_units, int G, int N, int R,
+                                                           const int* __restrict__ row_ptr,
+                                                           const uint32_t* __restrict__ pair,
+                                                           uint8_t* __restrict__ perm) {
+  __shared__ int sKey[kTileE];
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int rep0 = unit * G, rep1 = min(R, rep0 + G);
+    const int atom0 = rep0 * N, natoms = (rep1 - rep0) * N;
+    const int e_begin = row_ptr[atom0], e_end = row_ptr[atom0 + natoms];
+    for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
+      const int e = t0 + threadIdx.x;
+      const int key = e < e_end ? (int)(pair[e] & 0xFFFFu) : 0x7FFFFFFF;
+      sKey[threadIdx.x] = key;
+      __syncthreads();
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < kTileE; ++j) {
+        int kj = sKey[j];
+        rank += (kj < key || (kj == key && j < (int)threadIdx.x)) ? 1 : 0;
+      }
+      if (t0 + rank < e_end) perm[t0 + rank] = (uint8_t)threadIdx.x;
+      __syncthreads();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ forward
-// smem: Wr_t[20*64] W2_t[64*64] b2[64] | rbf[128*24] | V[128*68] | tgt[128] src[128] | (P,Q,acc)[3][A*64]
+// smem: Wr_t[20*64] W2_t[64*64] b2[64] | rbf[128*24] | V[128*68] | carry[4*64] | tgt[128] src[128] ckey[4] |
+//       (P,Q,acc)[3][unit_atoms*64]
 template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(kEdgeThreads, 1) edge_fwd_kernel(EdgeArgs g) {
+__global__ void __launch_bounds__(kEdgeThreads, 2) edge_fwd_kernel(EdgeArgs g) {
   extern __shared__ __align__(16) float sm[];
   float* sWr = sm;
   float* sW2 = sWr + kRbf * 64;
   float* sb2 = sW2 + 64 * 64;
   float* sRbf = sb2 + 64;
   float* sV = sRbf + kTileE * kRbfLd;
-  int* sTgt = reinterpret_cast<int*>(sV + kTileE * kTileLd);
+  float* sCarry = sV + kTileE * kTileLd;
+  int* sTgt = reinterpret_cast<int*>(sCarry + 4 * 64);
   int* sSrc = sTgt + kTileE;
-  float* sTab = reinterpret_cast<float*>(sSrc + kTileE);
+  int* sCKey = sSrc + kTileE;
+  float* sTab = reinterpret_cast<float*>(sCKey + 4);
 
   const int tid = threadIdx.x, tc = tid & 7, te = tid >> 3;
   for (int t = tid; t < kRbf * 64; t += kEdgeThreads) sWr[t] = g.Wr_t[t];
@@ -135,8 +230,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_fwd_kernel(EdgeArgs g) {
     float *tP, *tQ, *tA;
     if (SMEM_TABLES) {
       tP = sTab;
-      tQ = tP + kUnitAtomsMax * 64;
-      tA = tQ + kUnitAtomsMax * 64;
+      tQ = tP + g.unit_atoms * 64;
+      tA = tQ + g.unit_atoms * 64;
       copy_rows(tP, g.P + (size_t)atom0 * 64, natoms * 64);
       copy_rows(tQ, g.Q + (size_t)atom0 * 64, natoms * 64);
       zero_rows(tA, natoms * 64);
@@ -207,26 +302,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_fwd_kernel(EdgeArgs g) {
         }
       }
       __syncthreads();
-      // segmented add into the target rows: thread (c, grp) owns targets with (tgt & 3) == grp; strictly
-      // sequential accumulation in CSR (ascending-source) order, continuing across tiles through the table.
-      {
-        const int c = tid & 63, grp = tid >> 6;
-        int cur = -1;
-        float run = 0.0f;
-        for (int e = 0; e < kTileE; ++e) {
-          int tg = sTgt[e];
-          if (tg < 0) break;
-          if ((tg & 3) != grp) continue;
-          if (tg != cur) {
-            if (cur >= 0) tA[cur * 64 + c] = run;
-            cur = tg;
-            run = tA[tg * 64 + c];
-          }
-          run += sV[e * kTileLd + c];
-        }
-        if (cur >= 0) tA[cur * 64 + c] = run;
-      }
-      __syncthreads();
+      seg_reduce_tile<false>(sV, sTgt, nullptr, tA, sCarry, sCKey, tid);   // a[tgt] += z
     }
     if (SMEM_TABLES) {
       copy_rows(g.a_out + (size_t)atom0 * 64, tA, natoms * 64);
@@ -236,8 +312,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_fwd_kernel(EdgeArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------ adjoint
-// smem: Wr_t[20*64] W2_t[64*64] W2[64*64] WrP[64*24] b2[64] | rbf[128*24] drbf[128*24] | V[128*68] |
-//       tgt[128] src[128] part[256] | (P,Q,abar,Pbar,Qbar)[5][A*64]
+// smem: Wr_t[20*64] W2_t[64*64] W2[64*64] WrP[64*24] b2[64] | rbf[128*24] drbf[128*24] | V[128*68] | carry[4*64] |
+//       tgt[128] src[128] part[256] ckey[4] perm[128 B] | (P,Q,abar,Pbar,Qbar)[5][unit_atoms*64]
 template <bool SMEM_TABLES>
 __global__ void __launch_bounds__(kEdgeThreads, 1) edge_bwd_kernel(EdgeArgs g) {
   extern __shared__ __align__(16) float sm[];
@@ -249,10 +325,13 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_bwd_kernel(EdgeArgs g) {
   float* sRbf = sb2 + 64;
   float* sDrbf = sRbf + kTileE * kRbfLd;
   float* sV = sDrbf + kTileE * kRbfLd;
-  int* sTgt = reinterpret_cast<int*>(sV + kTileE * kTileLd);
+  float* sCarry = sV + kTileE * kTileLd;
+  int* sTgt = reinterpret_cast<int*>(sCarry + 4 * 64);
   int* sSrc = sTgt + kTileE;
   float* sPart = reinterpret_cast<float*>(sSrc + kTileE);
-  float* sTab = sPart + kEdgeThreads;
+  int* sCKey = reinterpret_cast<int*>(sPart + kEdgeThreads);
+  uint8_t* sPerm = reinterpret_cast<uint8_t*>(sCKey + 4);
+  float* sTab = reinterpret_cast<float*>(sPerm + kTileE);
 
   const int tid = threadIdx.x, tc = tid & 7, te = tid >> 3;
   for (int t = tid; t < kRbf * 64; t += kEdgeThreads) sWr[t] = g.Wr_t[t];
@@ -274,10 +353,10 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_bwd_kernel(EdgeArgs g) {
     float *tP, *tQ, *tAb, *tPb, *tQb;
     if (SMEM_TABLES) {
       tP = sTab;
-      tQ = tP + kUnitAtomsMax * 64;
-      tAb = tQ + kUnitAtomsMax * 64;
-      tPb = tAb + kUnitAtomsMax * 64;
-      tQb = tPb + kUnitAtomsMax * 64;
+      tQ = tP + g.unit_atoms * 64;
+      tAb = tQ + g.unit_atoms * 64;
+      tPb = tAb + g.unit_atoms * 64;
+      tQb = tPb + g.unit_atoms * 64;
       copy_rows(tP, g.P + (size_t)atom0 * 64, natoms * 64);
       copy_rows(tQ, g.Q + (size_t)atom0 * 64, natoms * 64);
       copy_rows(tAb, g.abar + (size_t)atom0 * 64, natoms * 64);
@@ -298,7 +377,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_bwd_kernel(EdgeArgs g) {
         bool valid = e < e_end;
         uint32_t pr = valid ? g.pair[e] : 0u;
         sTgt[tid] = valid ? (int)(pr >> 16) : -1;
-        sSrc[tid] = (int)(pr & 0xFFFFu);
+        sSrc[tid] = valid ? (int)(pr & 0xFFFFu) : -1;
+        sPerm[tid] = valid ? g.perm[e] : (uint8_t)tid;   // invalid rows sit at the tail in both orders
         rbf_row<true>(valid ? g.r_e[e] : 0.3f, g.inv_cutoff, sRbf + tid * kRbfLd, sDrbf + tid * kRbfLd);
       }
       __syncthreads();
@@ -426,29 +506,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_bwd_kernel(EdgeArgs g) {
           g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + v : v;
         }
       }
-      // Pbar[tgt] += ubar (contiguous runs), Qbar[src] += ubar (fixed edge order); ownership by index & 3
-      {
-        const int c = tid & 63, grp = tid >> 6;
-        int cur = -1;
-        float run = 0.0f;
-        for (int e = 0; e < kTileE; ++e) {
-          int tg = sTgt[e];
-          if (tg < 0) break;
-          float uv = sV[e * kTileLd + c];
-          if ((tg & 3) == grp) {
-            if (tg != cur) {
-              if (cur >= 0) tPb[cur * 64 + c] = run;
-              cur = tg;
-              run = tPb[tg * 64 + c];
-            }
-            run += uv;
-          }
-          int sr = sSrc[e];
-          if ((sr & 3) == grp) tQb[sr * 64 + c] += uv;
-        }
-        if (cur >= 0) tPb[cur * 64 + c] = run;
-      }
-      __syncthreads();
+      seg_reduce_tile<false>(sV, sTgt, nullptr, tPb, sCarry, sCKey, tid);   // Pbar[tgt] += ubar
+      seg_reduce_tile<true>(sV, sSrc, sPerm, tQb, sCarry, sCKey, tid);      // Qbar[src] += ubar
     }
     if (SMEM_TABLES) {
       copy_rows(g.Pbar + (size_t)atom0 * 64, tPb, natoms * 64);
@@ -459,15 +518,15 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_bwd_kernel(EdgeArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------ launchers
-static size_t edge_fwd_smem(bool smem_tables) {
-  size_t f = kRbf * 64 + 64 * 64 + 64 + kTileE * kRbfLd + kTileE * kTileLd + 2 * kTileE;
-  if (smem_tables) f += 3 * (size_t)kUnitAtomsMax * 64;
+static size_t edge_fwd_smem(const Ctx* c) {
+  size_t f = kRbf * 64 + 64 * 64 + 64 + kTileE * kRbfLd + kTileE * kTileLd + 4 * 64 + 2 * kTileE + 4;
+  if (c->smem_tables) f += 3 * (size_t)c->G * c->N * 64;
   return f * sizeof(float);
 }
-static size_t edge_bwd_smem(bool smem_tables) {
-  size_t f = kRbf * 64 + 2 * 64 * 64 + 64 * kRbfLd + 64 + 2 * kTileE * kRbfLd + kTileE * kTileLd + 2 * kTileE +
-             kEdgeThreads;
-  if (smem_tables) f += 5 * (size_t)kUnitAtomsMax * 64;
+static size_t edge_bwd_smem(const Ctx* c) {
+  size_t f = kRbf * 64 + 2 * 64 * 64 + 64 * kRbfLd + 64 + 2 * kTileE * kRbfLd + kTileE * kTileLd + 4 * 64 +
+             2 * kTileE + kEdgeThreads + 4 + kTileE / 4;
+  if (c->smem_tables) f += 5 * (size_t)c->G * c->N * 64;
   return f * sizeof(float);
 }
 
@@ -493,13 +552,23 @@ static EdgeArgs make_args(Ctx* c, int l) {
   g.Pbar = c->Pbar;
   g.Qbar = c->Qbar;
   g.rbar = c->rbar;
+  g.perm = c->perm;
+  g.unit_atoms = c->G * c->N;
   return g;
+}
+
+int launch_tile_perm(Ctx* c, cudaStream_t st) {
+  int grid = c->n_units < 8 * c->num_sms ? c->n_units : 8 * c->num_sms;
+  tile_perm_kernel<<<grid, kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
+  GNNIS_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_edge_fwd(Ctx* c, int l, cudaStream_t st) {
   EdgeArgs g = make_args(c, l);
-  int grid = c->n_units < c->num_sms ? c->n_units : c->num_sms;
-  size_t smem = edge_fwd_smem(c->smem_tables);
+  size_t smem = edge_fwd_smem(c);
+  int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  int grid = c->n_units < per_sm * c->num_sms ? c->n_units : per_sm * c->num_sms;
   if (c->smem_tables) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     edge_fwd_kernel<true><<<grid, kEdgeThreads, smem, st>>>(g);
@@ -515,7 +584,7 @@ int launch_edge_bwd(Ctx* c, int l, int rbar_accumulate, cudaStream_t st) {
   EdgeArgs g = make_args(c, l);
   g.rbar_accumulate = rbar_accumulate;
   int grid = c->n_units < c->num_sms ? c->n_units : c->num_sms;
-  size_t smem = edge_bwd_smem(c->smem_tables);
+  size_t smem = edge_bwd_smem(c);
   if (c->smem_tables) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     edge_bwd_kernel<true><<<grid, kEdgeThreads, smem, st>>>(g);
