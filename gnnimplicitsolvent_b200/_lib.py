@@ -45,6 +45,7 @@ SIGNATURES = {
                                  C.c_int32, C.c_uint32, C.c_void_p]),
     "gnnis_langevin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_float, C.c_float, C.c_float,
                                  C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "gnnis_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "gnnis_launch_count": (C.c_int64, [C.c_void_p]),
     "gnnis_profile_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                      c_float_p, C.c_int32]),
@@ -52,7 +53,7 @@ SIGNATURES = {
     "gnnis_stage_name": (C.c_char_p, [C.c_int32]),
 }
 
-FLAG_DELTA, FLAG_NO_FORCES, FLAG_GB_ONLY, FLAG_MLP_BF16 = 0x1, 0x2, 0x4, 0x8
+FLAG_DELTA, FLAG_NO_FORCES, FLAG_GB_ONLY, FLAG_MLP_BF16, FLAG_MLP_CUDA_CORES = 0x1, 0x2, 0x4, 0x8, 0x10
 
 _lib = None
 

@@ -2,6 +2,7 @@
 // launch sequence of one batched energy/force evaluation.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -15,6 +16,10 @@ int launch_born_adjoint(Ctx*, const float*, int, float*, cudaStream_t);
 int launch_reduce_energy(Ctx*, const float*, float*, cudaStream_t);
 int launch_edge_fwd(Ctx*, int, cudaStream_t);
 int launch_tile_perm(Ctx*, cudaStream_t);
+int launch_edge_fwd_tc(Ctx*, int, cudaStream_t);
+int launch_edge_bwd_tc(Ctx*, int, int, cudaStream_t);
+int launch_umma_selftest(Ctx*, const float*, const float*, float*, int, int, cudaStream_t);
+bool tc_path_fits(const Ctx*);
 int launch_edge_bwd(Ctx*, int, int, cudaStream_t);
 int launch_node_pre1(Ctx*, cudaStream_t);
 int launch_node_fwd(Ctx*, int, cudaStream_t);
@@ -134,9 +139,13 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     return -1;
   }
   if (flags & GNNIS_FLAG_MLP_BF16) {
-    c->err = "GNNIS_FLAG_MLP_BF16: the tcgen05 edge-MLP path is not built in this version";
+    c->err = "GNNIS_FLAG_MLP_BF16: the bf16 edge-MLP mode is not built in this version (the tcgen05 path runs 3xTF32)";
     return -3;
   }
+  // tensor-core (tcgen05, 3xTF32) edge kernels unless the caller forces the CUDA-core path or the unit's tables
+  // do not fit next to the staged weight operands
+  const bool tc_ok = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && tc_path_fits(c);
+  const bool tc_fwd = tc_ok && (c->tc_mask & 1), tc_bwd = tc_ok && (c->tc_mask & 2);
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
   if (tm) tm->mark(kStNeighborBorn);
@@ -148,7 +157,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     if (launch_node_pre1(c, st)) return -1;
     for (int l = 0; l < 3; ++l) {
       if (tm) tm->mark(kStEdgeFwd);
-      if (launch_edge_fwd(c, l, st)) return -1;
+      if (tc_fwd ? launch_edge_fwd_tc(c, l, st) : launch_edge_fwd(c, l, st)) return -1;
       if (tm) tm->mark(kStNodeFwd);
       if (launch_node_fwd(c, l, st)) return -1;
     }
@@ -166,7 +175,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
         if (tm) tm->mark(kStNodeBwd);
         if (launch_node_bwd(c, l, st)) return -1;
         if (tm) tm->mark(kStEdgeBwd);
-        if (launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
+        if (tc_bwd ? launch_edge_bwd_tc(c, l, l == 2 ? 0 : 1, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
       }
       if (tm) tm->mark(kStNodeBwd);
       if (launch_node_pre1_bwd(c, st)) return -1;
@@ -217,6 +226,7 @@ int gnnis_create(gnnis_handle* out, int device) {
     delete c;
     return -1;
   }
+  if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 fwd, bit1 bwd on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;
 }
@@ -525,6 +535,18 @@ int gnnis_last_edge_count(gnnis_handle h, int64_t* n_edges_host, void* stream) {
   GNNIS_CUDA_OK(cudaMemcpyAsync(n_edges_host, c->n_edges_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   GNNIS_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
+}
+
+int gnnis_umma_selftest(gnnis_handle h, const float* a_dev, const float* b_dev, float* d_dev, int32_t k, int32_t n,
+                        void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if ((k != 32 && k != 64) || (n != 32 && n != 64)) {
+    c->err = "gnnis_umma_selftest: K and N must be 32 or 64";
+    return -1;
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  return launch_umma_selftest(c, a_dev, b_dev, d_dev, k, n, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int64_t gnnis_launch_count(gnnis_handle h) { return h ? reinterpret_cast<Ctx*>(h)->launches : 0; }

@@ -62,6 +62,7 @@ struct Ctx {
   std::string err;
   int64_t launches = 0;
   int num_sms = 148;
+  int tc_mask = 3;   // bit0: forward edge kernel on tcgen05, bit1: adjoint edge kernel on tcgen05
   // model
   bool have_weights = false;
   int S = 0;  // num_solvents

@@ -127,7 +127,7 @@ class Engine:
         self._check(self.lib.gnnis_set_bonds(self._h, idx.shape[0], idx.ctypes.data_as(_lib.c_int32_p), _fp(r0), _fp(k)))
 
     # ------------------------------------------------------------------ hot path
-    def energy_force(self, positions: torch.Tensor, *, delta=False, forces=True, gb_only=False,
+    def energy_force(self, positions: torch.Tensor, *, delta=False, forces=True, gb_only=False, cuda_cores=False,
                      out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
         """positions [R,N,3] (or [R*N,3]) fp32 on the engine's device -> (E[R], F[R,N,3] or None)."""
         p = self._pos(positions)
@@ -135,7 +135,8 @@ class Engine:
         f = None
         if forces:
             f = out_force if out_force is not None else torch.empty_like(p)
-        flags = (_lib.FLAG_DELTA if delta else 0) | (0 if forces else _lib.FLAG_NO_FORCES) | (_lib.FLAG_GB_ONLY if gb_only else 0)
+        flags = ((_lib.FLAG_DELTA if delta else 0) | (0 if forces else _lib.FLAG_NO_FORCES)
+                 | (_lib.FLAG_GB_ONLY if gb_only else 0) | (_lib.FLAG_MLP_CUDA_CORES if cuda_cores else 0))
         self._check(self.lib.gnnis_energy_force(self._h, p.data_ptr(), e.data_ptr(), f.data_ptr() if forces else None,
                                                 flags, self._stream()))
         return e, f
@@ -211,6 +212,15 @@ class Engine:
         self._check(self.lib.gnnis_langevin(self._h, positions.data_ptr(), velocities.data_ptr(), _fp(m),
                                             float(temperature), float(friction), float(dt), int(n_steps), int(seed),
                                             int(first_step), flags, self._stream()))
+
+    def umma_selftest(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """D = A @ B^T through the tcgen05 building blocks (A [128,K], B [N,K], K,N in {32,64})."""
+        a = a.to(self.device, torch.float32).contiguous()
+        b = b.to(self.device, torch.float32).contiguous()
+        d = torch.empty(128, b.shape[0], dtype=torch.float32, device=self.device)
+        self._check(self.lib.gnnis_umma_selftest(self._h, a.data_ptr(), b.data_ptr(), d.data_ptr(), a.shape[1], b.shape[0],
+                                                 self._stream()))
+        return d
 
     def launch_count(self) -> int:
         return int(self.lib.gnnis_launch_count(self._h))

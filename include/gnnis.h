@@ -28,7 +28,9 @@ typedef struct gnnis_ctx* gnnis_handle;
                                       polar energy = E_GB(B') - E_GB(B)                                    */
 #define GNNIS_FLAG_NO_FORCES 0x2u  /* energy only (skips the adjoint pass)                                */
 #define GNNIS_FLAG_GB_ONLY 0x4u    /* plain GB-Neck2 (GNN_GBNeck_2, GNN_Models.py:173): B' = B, no SA term */
-#define GNNIS_FLAG_MLP_BF16 0x8u   /* edge-MLP GEMMs on tcgen05 tensor cores, bf16 operands / fp32 accum  */
+#define GNNIS_FLAG_MLP_BF16 0x8u   /* reserved: bf16-operand edge MLP (not built; returns -3)             */
+#define GNNIS_FLAG_MLP_CUDA_CORES 0x10u /* force the fp32 CUDA-core edge kernels instead of the default
+                                      tcgen05 tensor-core kernels (3xTF32, fp32-accurate)                 */
 
 /* The shipped architecture's state dict (MachineLearning/trained_models/GNN.pt["model"]),
  * as host pointers to the tensors in torch layout (Linear.weight = [out][in], row-major).  Layer l = 0..2
@@ -115,6 +117,11 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
 int gnnis_langevin(gnnis_handle h, float* pos_dev, float* vel_dev, const float* masses_host,
                    float temperature, float friction, float dt, int32_t n_steps, uint64_t seed,
                    uint64_t first_step, uint32_t flags, void* stream);
+
+/* Building-block check of the tensor-core path: D[128][n] = A[128][k] * B[n][k]^T (row-major device buffers)
+ * through TMEM-resident A, 128B-swizzled shared-memory B, 3xTF32 tcgen05.mma.  k, n in {32, 64}. */
+int gnnis_umma_selftest(gnnis_handle h, const float* a_dev, const float* b_dev, float* d_dev, int32_t k, int32_t n,
+                        void* stream);
 
 /* Number of kernels this library launched since the handle was created (bench.py's gpu_launches). */
 int64_t gnnis_launch_count(gnnis_handle h);

@@ -172,3 +172,33 @@ def test_host_api_matches_device_api(weights):
     eng.energy_force_host(pos, e_h, f_h)
     e, f = eng.energy_force(pos.cuda())
     assert torch.equal(e.cpu(), e_h) and torch.equal(f.cpu(), f_h)
+
+
+@pytest.mark.parametrize("K,N", [(32, 64), (64, 64), (64, 32)])
+def test_umma_building_blocks(K, N):
+    """tcgen05 building blocks (TMEM-resident A, 128B-swizzled smem B, 3xTF32): D = A B^T to fp32 accuracy."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    mol = synth.synth_molecule(7, seed=1)
+    eng = Engine(mol["params"], None)
+    g = torch.Generator().manual_seed(K * 100 + N)
+    a = torch.randn(128, K, generator=g) * 3.0
+    b = torch.randn(N, K, generator=g)
+    d = eng.umma_selftest(a, b).cpu().double()
+    ref = a.double() @ b.double().T
+    err = float((d - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, err           # plain TF32 would be ~1e-3
+
+
+@pytest.mark.parametrize("name", ["mixed_n21", "c2_n50_water", "n100_mixed"])
+def test_cuda_core_path_vs_golden(name, weights):
+    """The fp32 CUDA-core edge kernels (GNNIS_FLAG_MLP_CUDA_CORES) stay parity-green next to the tcgen05 default."""
+    c = load_case(name)
+    eng = _engine(c, weights)
+    e, f = eng.energy_force(torch.from_numpy(c["pos"]).cuda(), cuda_cores=True)
+    assert abs(float(e.double().sum()) - float(c["energy_total"])) <= E_RTOL * abs(float(c["energy_total"]))
+    assert rel_rms(f.cpu().numpy(), c["forces"]) < F_RRMS
+    e2, f2 = eng.energy_force(torch.from_numpy(c["pos"]).cuda())
+    # tensor-core (3xTF32) and CUDA-core paths agree to fp32 rounding
+    assert rel_rms(f2.cpu().numpy(), f.cpu().numpy()) < 2e-5
+    np.testing.assert_allclose(e2.cpu().numpy(), e.cpu().numpy(), rtol=2e-6)
