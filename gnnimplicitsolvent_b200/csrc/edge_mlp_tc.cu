@@ -1,22 +1,35 @@
 // edge_mlp_tc.cu -- the edge-message MLP and its adjoint on the 5th-generation tensor cores (tcgen05, sm_100a).
 //
-// Same formulation and work decomposition as edge_mlp.cu (one persistent CTA per unit, 128-edge tiles, tables in
-// shared memory, deterministic segmented reductions), but every dense contraction of the tile runs as
-// tcgen05.mma.kind::tf32 with the accumulator in TMEM:
-//     u  = rbf  . Wr^T      [128 x 24] x [24 x 64]      (A = rbf tile, written to TMEM by its 128 row-owner threads)
-//     w  = v    . W2^T      [128 x 64] x [64 x 64]      (A = v = silu(u + P[tgt] + Q[src]) written back to TMEM)
-//     vb = wbar . W2        [128 x 64] x [64 x 64]      adjoint
-//     rb = ubar . Wr        [128 x 64] x [64 x 24]      adjoint of the radial columns
-// A operands never touch shared memory: the epilogue of one product (tcgen05.ld -> registers -> bias/gather/SiLU)
-// stores the next A operand straight back to TMEM (tcgen05.st), the "TS" form of tcgen05.mma.  B operands (the
-// weights) are staged once per persistent CTA in shared memory in the canonical K-major 128B-swizzle layout.
+// Formulation (per directed edge e = (j -> i), IN_layer_all_swish_2pass_tokens.message, GNN_Layers.py:2186-2192):
+//     u = P[i] + Q[j] + rbf(r_e) Wr^T        P = h W1[:, :cin]^T + b1, Q = h W1[:, cin:2cin]^T  (node kernels)
+//     v = silu(u);  w = v W2^T + b2;  z = silu(w);  a[i] += z
+// and the adjoint, recomputing u, w tile by tile instead of storing per-edge activations:
+//     wbar = abar[i] * silu'(w);  vbar = wbar W2;  ubar = vbar * silu'(u)
+//     Pbar[i] += ubar;  Qbar[j] += ubar;  rbar_e = sum_c ubar_c (d rbf/dr Wr^T)_c
 //
-// Precision: fp32-accurate.  Each product is evaluated as three TF32 MMAs, A_hi B_hi + A_hi B_lo + A_lo B_hi with
-// x_hi = top 19 bits of x and x_lo = x - x_hi ("3xTF32"), accumulated in fp32 in TMEM; the dropped term is
-// O(2^-22).  This is the mode the fp32 parity gates (energy 1e-4, forces 1e-3) are checked in.
+// Work decomposition: one persistent CTA per SM made of TWO independent 128-thread groups.  Each group owns its
+// own units (a unit = G replicas whose tables fit in shared memory), its own 128-edge tile, its own 256 TMEM
+// columns, its own mbarrier and named barrier -- the groups never synchronise with each other, so while one
+// group waits for its tcgen05.mma the other one runs its SiLU epilogue (MUFU) and vice versa.  Inside a group a
+// thread is one edge row (= one TMEM lane) and walks the 64 channels in two halves of 32 columns.
 //
-// Thread mapping: 8 warps; warp w owns TMEM lanes (= tile rows) 32 (w & 3) .. +31 and columns 32 (w >> 2) .. +31,
-// i.e. thread = (edge row, half of the 64 channels) -- the natural tcgen05.ld/st 32x32b shape.
+// Every dense contraction of a tile is tcgen05.mma.kind::tf32 with the accumulator in TMEM and the A operand
+// written back to TMEM by the previous epilogue (tcgen05.st), i.e. A never touches shared memory:
+//     u    = rbf  . Wr^T   [128 x 24] x [24 x 64]
+//     du   = drbf . Wr^T   [128 x 24] x [24 x 64]   (adjoint only: d u / d r, dotted with ubar per row)
+//     w    = v    . W2^T   [128 x 64] x [64 x 64]
+//     vbar = wbar . W2     [128 x 64] x [64 x 64]   (W2^T staged as a second K-major operand: kind::tf32 only
+//                                                    reads MN-major operands in the 128B_BASE32B layout)
+// Weights are staged once per CTA in the canonical K-major 128B-swizzle layout.
+//
+// Precision: fp32-accurate.  Each product is three TF32 MMAs, A_hi B_hi + A_hi B_lo + A_lo B_hi with x_hi = top 19
+// bits of x and x_lo = x - x_hi ("3xTF32"), accumulated in fp32 in TMEM; the dropped term is O(2^-22).
+//
+// Reductions are deterministic (no atomics).  Rows of a tile with equal target are contiguous (CSR order), rows
+// with equal source are contiguous in the precomputed source-sorted permutation of the tile; one warp builds the
+// list of segment starts while the first MMA runs, then every segment is summed by exactly 16 threads (one per
+// column quad) in row order.  Target sums go straight to global memory (a row is complete unless it straddles a
+// tile boundary: then the next tile adds to it), source sums into a shared-memory table of the unit.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -24,7 +37,10 @@ namespace gnnis {
 
 using namespace umma;
 
-constexpr int kTabLd = 68;   // padded row of the shared-memory node tables (bank spread for row-per-lane gathers)
+constexpr int kTabLd = 68;        // padded row of the shared-memory node tables (bank spread for row-per-lane gathers)
+constexpr int kGroupThreads = 128;
+constexpr int kGroups = 2;
+constexpr int kSlots = 8;         // segments summed concurrently (x 16 column quads = 128 threads)
 
 struct EdgeTcArgs {
   int n_units, G, N, R;
@@ -32,7 +48,8 @@ struct EdgeTcArgs {
   const uint32_t* pair;
   const float* r_e;
   float inv_cutoff;
-  const float *Wr, *W2, *b2, *Wr_t, *W2_t;   // torch-layout [64][20], [64][64]; transposed [20][64], [64][64]
+  const float *Wr, *W2, *b2;   // torch layout [64][20], [64][64]
+  const float* W2_t;           // [64][64] transposed
   const float *P, *Q;
   float* a_out;
   const float* abar;
@@ -43,6 +60,31 @@ struct EdgeTcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid = 1 / (1 + 2^(-x log2 e)): one MUFU.EX2 + one MUFU.RCP (~2 ulp); the parity gates guard this choice
+__device__ __forceinline__ float sig_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sig_fast(x); }
+__device__ __forceinline__ void silu_fd_fast(float x, float& f, float& d) {
+  const float sg = sig_fast(x);
+  f = x * sg;
+  d = fmaf(f, 1.0f - sg, sg);              // sg (1 + x (1 - sg))
+}
+__device__ __forceinline__ float silu_d_fast(float x) {
+  const float sg = sig_fast(x);
+  return fmaf(sg, fmaf(-x, sg, x), sg);    // sg + sg x (1 - sg)
+}
+
 // stage a K-major B operand [rows][kdim] (element (n,k) = src[n*ld_n + k*ld_k], zero outside n_valid x k_valid)
 // as hi / lo TF32 parts in the SW128 layout
 __device__ __forceinline__ void stage_b_operand(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int rows,
@@ -58,28 +100,27 @@ __device__ __forceinline__ void stage_b_operand(uint8_t* hi, uint8_t* lo, const 
   }
 }
 
-// issue the three TF32 products of D[128 x N] = A[128 x 8*ksteps] * B^T with A (hi, lo) in TMEM, B (hi, lo) in smem
+// D[128 x N] = A[128 x 8*KSTEPS] * B^T, three TF32 products; A (hi, lo) in TMEM, B (hi, lo) K-major SW128 in smem
+template <int KSTEPS>
 __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_addr,
-                                                  uint32_t b_lo_addr, int ksteps, int b_rows, uint32_t idesc) {
+                                                  uint32_t b_lo_addr, int b_rows, uint32_t idesc) {
   uint32_t acc = 0;
-#pragma unroll 1
+#pragma unroll
   for (int term = 0; term < 3; ++term) {
     const uint32_t a = term == 2 ? a_lo : a_hi;
     const uint32_t b = term == 1 ? b_lo_addr : b_hi_addr;
-#pragma unroll 1
-    for (int s = 0; s < ksteps; ++s) {
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s) {
       uint32_t baddr = b + (uint32_t)(s >> 2) * (uint32_t)b_rows * 128u + (uint32_t)(s & 3) * 32u;
       mma_tf32_ts(d_tmem, a + 8u * (uint32_t)s, smem_desc_k_sw128(baddr), idesc, acc);
       acc = 1;
     }
   }
 }
-
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-
-// radial basis row in registers (see rbf_row in edge_mlp.cu); o[24..31] = 0
+// radial basis row in registers (GNN_Layers.py:2194-2208): d = r/cutoff, env = 1/d - 28 d^5 + 48 d^6 - 21 d^7,
+// rbf_k = env sin(k pi d); sin/cos(k pi d) from one sincospi and the Chebyshev recurrence.  o[20..31] = 0.
 template <bool DERIV>
-__device__ __forceinline__ void rbf_regs(float r, float inv_cutoff, float (&o)[32], float (&od)[24]) {
+__device__ __forceinline__ void rbf_regs(float r, float inv_cutoff, float (&o)[32], float (&od)[32]) {
   const float d = r * inv_cutoff;
   const float d2 = d * d, d4 = d2 * d2, d5 = d4 * d;
   const float env = 1.0f / d - 28.0f * d5 + 48.0f * (d5 * d) - 21.0f * (d5 * d2);
@@ -103,10 +144,9 @@ __device__ __forceinline__ void rbf_regs(float r, float inv_cutoff, float (&o)[3
     }
   }
 #pragma unroll
-  for (int k = kRbf; k < 32; ++k) o[k] = 0.0f;
-  if (DERIV) {
-#pragma unroll
-    for (int k = kRbf; k < 24; ++k) od[k] = 0.0f;
+  for (int k = kRbf; k < 32; ++k) {
+    o[k] = 0.0f;
+    if (DERIV) od[k] = 0.0f;
   }
 }
 
@@ -118,62 +158,104 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
   tmem_st32(t_lo, l);
 }
 
-__device__ __forceinline__ void copy_rows_ld(float* __restrict__ dst, int ld_dst, const float* __restrict__ src,
-                                             int ld_src, int nrows) {
-  for (int t = threadIdx.x; t < nrows * 16; t += blockDim.x) {
+// group-wide row copies / zero fill of [nrows][64] blocks (16-byte vectors)
+__device__ __forceinline__ void copy_rows_grp(float* __restrict__ dst, int ld_dst, const float* __restrict__ src,
+                                              int ld_src, int nrows, int gt) {
+  for (int t = gt; t < nrows * 16; t += kGroupThreads) {
     int r = t >> 4, c4 = t & 15;
     *reinterpret_cast<float4*>(dst + (size_t)r * ld_dst + c4 * 4) =
         *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c4 * 4);
   }
 }
-__device__ __forceinline__ void zero_rows_ld(float* __restrict__ dst, int ld_dst, int nrows) {
-  for (int t = threadIdx.x; t < nrows * 16; t += blockDim.x) {
+__device__ __forceinline__ void zero_rows_grp(float* __restrict__ dst, int ld_dst, int nrows, int gt) {
+  for (int t = gt; t < nrows * 16; t += kGroupThreads) {
     int r = t >> 4, c4 = t & 15;
     *reinterpret_cast<float4*>(dst + (size_t)r * ld_dst + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
-// segmented add of tile rows into table rows (see seg_reduce_tile in edge_mlp.cu), table row stride `ld`
+// Per-tile keys (double-buffered by tile parity so that the reduction of tile t may overlap the set-up of t+1)
+struct TileKeys {
+  int tgt[kTileE];        // unit-local target of row e (-1 past the end of the unit)
+  int src[kTileE];        // unit-local source
+  uint8_t perm[kTileE];   // row at source-sorted position p
+  uint8_t seg_t[kTileE + 8];   // starts of the target segments (row order), then the number of valid rows
+  uint8_t seg_s[kTileE + 8];   // starts of the source segments (permuted order), then the number of valid rows
+  int n_seg_t, n_seg_s, cont_prev, pad;
+};
+
+// One warp: list the starts of the runs of equal keys among the valid rows (valid rows come first).
 template <bool PERM>
-__device__ __forceinline__ void seg_reduce_ld(const float* __restrict__ sX, const int* __restrict__ sKey,
-                                              const uint8_t* __restrict__ sPerm, float* __restrict__ table, int ld,
-                                              float* __restrict__ sCarry, int* __restrict__ sCarryKey, int tid) {
-  const int c = tid & 63, q = tid >> 6, p0 = 32 * q;
-  int cur = sKey[PERM ? (int)sPerm[p0] : p0];
-  bool cont = false;
-  if (q > 0 && cur >= 0) cont = sKey[PERM ? (int)sPerm[p0 - 1] : p0 - 1] == cur;
-  if (c == 0) sCarryKey[q] = cont ? cur : -1;
-  bool first = true;
-  float run = 0.0f;
-#pragma unroll 8
-  for (int j = 0; j < 32; ++j) {
-    const int e = PERM ? (int)sPerm[p0 + j] : p0 + j;
-    const int k = sKey[e];
-    const float v = sX[e * kTileLd + c];
-    if (k != cur) {
-      if (cur >= 0) {
-        if (first && cont) sCarry[q * 64 + c] = run;
-        else table[cur * ld + c] += run;
-      }
-      cur = k;
-      run = 0.0f;
-      first = false;
-    }
-    if (k >= 0) run += v;
-  }
-  if (cur >= 0) {
-    if (first && cont) sCarry[q * 64 + c] = run;
-    else table[cur * ld + c] += run;
-  }
-  __syncthreads();
-  if (tid < 64) {
+__device__ __forceinline__ int build_segments(const int* __restrict__ key, const uint8_t* __restrict__ perm,
+                                              uint8_t* __restrict__ seg, int n_valid, int lane) {
+  int base = 0;
 #pragma unroll
-    for (int qq = 1; qq < 4; ++qq) {
-      int k = sCarryKey[qq];
-      if (k >= 0) table[k * ld + tid] += sCarry[qq * 64 + tid];
-    }
+  for (int c = 0; c < 4; ++c) {
+    const int p = 32 * c + lane;
+    const int k = key[PERM ? (int)perm[p] : p];
+    const int kprev = p > 0 ? key[PERM ? (int)perm[p - 1] : p - 1] : -2;
+    const bool flag = p < n_valid && k != kprev;
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    if (flag) seg[base + __popc(b & ((1u << lane) - 1u))] = (uint8_t)p;
+    base += __popc(b);
   }
-  __syncthreads();
+  if (lane == 0) seg[base] = (uint8_t)n_valid;   // <= 128
+  return base;
+}
+
+// Target-segment sums straight to global rows out[key][64]: segment s is summed by the 16 threads of slot s % 8.
+// A segment is stored (first touch of its row) unless it continues the last row of the previous tile (cont_prev,
+// segment 0 only), in which case it is added.  Rows without edges keep the zero written at the start of the unit.
+__device__ __forceinline__ void reduce_targets_global(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
+                                                      float* __restrict__ out, int gt) {
+  const int cq = gt & 15, slot = gt >> 4;
+  const int nseg = tk->n_seg_t;
+  for (int s = slot; s < nseg; s += kSlots) {
+    const int p0 = tk->seg_t[s], p1 = tk->seg_t[s + 1];
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0; p < p1; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
+      run.x += v.x;
+      run.y += v.y;
+      run.z += v.z;
+      run.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)tk->tgt[p0] * 64 + 4 * cq);
+    if (s == 0 && tk->cont_prev) {
+      float4 t = *dst;
+      run.x += t.x;
+      run.y += t.y;
+      run.z += t.z;
+      run.w += t.w;
+    }
+    *dst = run;
+  }
+}
+
+// Source-segment sums into table rows (shared memory or global): every distinct source of the tile is one segment,
+// so no two threads touch the same entry.
+__device__ __forceinline__ void reduce_sources_table(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
+                                                     float* __restrict__ table, int ld, int gt) {
+  const int cq = gt & 15, slot = gt >> 4;
+  const int nseg = tk->n_seg_s;
+  for (int s = slot; s < nseg; s += kSlots) {
+    const int p0 = tk->seg_s[s], p1 = tk->seg_s[s + 1];
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0; p < p1; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + (int)tk->perm[p] * kTileLd + 4 * cq);
+      run.x += v.x;
+      run.y += v.y;
+      run.z += v.z;
+      run.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(table + (size_t)tk->src[tk->perm[p0]] * ld + 4 * cq);
+    float4 t = *dst;
+    t.x += run.x;
+    t.y += run.y;
+    t.z += run.z;
+    t.w += run.w;
+    *dst = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- self test
@@ -211,10 +293,12 @@ __global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __re
   __syncthreads();
   if (tid == 0) {
     fence_after_sync();
-    issue_gemm_3xtf32(tm + ACC, tm + AH, tm + AL, smem_u32(bh), smem_u32(bl), K / 8, N, idesc_tf32(128, N));
+    if (K == 64) issue_gemm_3xtf32<8>(tm + ACC, tm + AH, tm + AL, smem_u32(bh), smem_u32(bl), N, idesc_tf32(128, N));
+    else issue_gemm_3xtf32<4>(tm + ACC, tm + AH, tm + AL, smem_u32(bh), smem_u32(bl), N, idesc_tf32(128, N));
     mma_commit(&bar);
   }
   mbar_wait(&bar, 0);
+  __syncwarp();
   fence_after_sync();
   if (32 * ch < N) {
     uint32_t r[32];
@@ -228,30 +312,48 @@ __global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __re
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
+// ---------------------------------------------------------------------------------------------- shared memory map
+// common (1024-aligned): WrH 8K | WrL 8K | W2H 16K | W2L 16K | [adjoint: W2tH 16K | W2tL 16K] | b2[64]
+// per group:             X[128][68] | TileKeys[2] | tables
+//   forward tables  : Q          [unit_atoms][68]
+//   adjoint tables  : Q, Qbar    [unit_atoms][68] each
+constexpr uint32_t kFwdWeights = 49152, kBwdWeights = 81920;
+constexpr uint32_t kGrpX = 0;
+constexpr uint32_t kGrpKeys = kGrpX + kTileE * kTileLd * 4;
+constexpr uint32_t kGrpTab = kGrpKeys + 2 * (uint32_t)sizeof(TileKeys);
+static_assert(sizeof(TileKeys) % 16 == 0, "TileKeys must keep the tables 16-byte aligned");
+
+static size_t group_bytes(const Ctx* c, int ntables) {
+  size_t b = kGrpTab;
+  if (c->smem_tables) b += (size_t)ntables * c->G * c->N * kTabLd * 4;
+  return (b + 15) / 16 * 16;
+}
+static size_t fwd_tc_smem(const Ctx* c) { return kFwdWeights + 256 + kGroups * group_bytes(c, 1) + 1024; }
+static size_t bwd_tc_smem(const Ctx* c) { return kBwdWeights + 256 + kGroups * group_bytes(c, 2) + 1024; }
+
 // ---------------------------------------------------------------------------------------------- forward
-// smem (1024-aligned): WrH 8K | WrL 8K | W2H 16K | W2L 16K | Z[128][68] | carry[256] | tgt[128] src[128] ckey[4] |
-//                      b2[64] | (P, Q, acc)[3][unit_atoms][68]
-constexpr uint32_t kFwdOffZ = 49152;
 template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(kEdgeThreads, 1) edge_fwd_tc_kernel(EdgeTcArgs g) {
+__global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_fwd_tc_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   extern __shared__ uint8_t smraw[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bars[kGroups];
   __shared__ uint32_t tmem_slot;
   uint32_t base = smem_u32(smraw);
   uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
   uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
-  float* sZ = reinterpret_cast<float*>(sm + kFwdOffZ);
-  float* sCarry = sZ + kTileE * kTileLd;
-  int* sTgt = reinterpret_cast<int*>(sCarry + 256);
-  int* sSrc = sTgt + kTileE;
-  int* sCKey = sSrc + kTileE;
-  float* sb2 = reinterpret_cast<float*>(sCKey + 4);
-  float* sTab = sb2 + 64;
+  float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, ch = warp >> 2;
+  const int grp = tid >> 7, gt = tid & 127, wq = warp & 3, row = gt;
+  uint8_t* gsm = sm + kFwdWeights + 256 + (size_t)grp * grp_bytes;
+  float* sZ = reinterpret_cast<float*>(gsm + kGrpX);
+  TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
+  float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
+
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) mbar_init(&bar, 1);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+  }
   stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);     // B[n = c][k] = Wr[c][k]
   stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);         // B[n = c][k] = W2[c][k]
   if (tid < 64) sb2[tid] = g.b2[tid];
@@ -259,364 +361,359 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_fwd_tc_kernel(EdgeTcArgs
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tm = tmem_slot;
-  const uint32_t lane_addr = tm + ((uint32_t)(32 * (warp & 3)) << 16);
-  constexpr uint32_t ACC_U = 0, ACC_W = 64, A1H = 128, A1L = 160, VH = 192, VL = 256;
+  const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;            // this group's 256 columns
+  const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
+  constexpr uint32_t ACC = 0, VH = 64, VL = 128;                   // rbf A operand aliases V[0..31]
   constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+  uint64_t* bar = &bars[grp];
   uint32_t phase = 0;
+  int parity = 0;
 
-  for (int unit = blockIdx.x; unit < g.n_units; unit += gridDim.x) {
+  for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
     const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
     const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
     const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
-    float *tP, *tQ, *tA;
+    const float* gP = g.P + (size_t)atom0 * 64;
+    float* gA = g.a_out + (size_t)atom0 * 64;
+    const float* tQ;
     int ld;
     if (SMEM_TABLES) {
       ld = kTabLd;
-      tP = sTab;
-      tQ = tP + g.unit_atoms * kTabLd;
-      tA = tQ + g.unit_atoms * kTabLd;
-      copy_rows_ld(tP, ld, g.P + (size_t)atom0 * 64, 64, natoms);
-      copy_rows_ld(tQ, ld, g.Q + (size_t)atom0 * 64, 64, natoms);
-      zero_rows_ld(tA, ld, natoms);
+      copy_rows_grp(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt);
+      tQ = sTab;
     } else {
       ld = 64;
-      tP = const_cast<float*>(g.P) + (size_t)atom0 * 64;
-      tQ = const_cast<float*>(g.Q) + (size_t)atom0 * 64;
-      tA = g.a_out + (size_t)atom0 * 64;
-      zero_rows_ld(tA, ld, natoms);
+      tQ = g.Q + (size_t)atom0 * 64;
     }
-    __syncthreads();
+    zero_rows_grp(gA, 64, natoms, gt);
+    group_sync(grp);
 
     for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-      // ---- A: edge rows, radial basis -> TMEM (warps 0-3 own the 128 rows)
-      if (ch == 0) {
-        int e = t0 + row;
-        bool valid = e < e_end;
-        uint32_t pr = valid ? g.pair[e] : 0u;
-        sTgt[row] = valid ? (int)(pr >> 16) : -1;
-        sSrc[row] = valid ? (int)(pr & 0xFFFFu) : -1;
-        float o[32], od[24];
+      TileKeys* tk = keys + parity;
+      parity ^= 1;
+      // ---- A: this thread's edge, radial basis -> TMEM
+      const int e = t0 + row;
+      const bool valid = e < e_end;
+      const uint32_t pr = valid ? g.pair[e] : 0u;
+      const int tg = valid ? (int)(pr >> 16) : -1, sr = (int)(pr & 0xFFFFu), tgc = valid ? tg : 0;
+      tk->tgt[row] = tg;
+      {
+        float o[32], od[32];
         rbf_regs<false>(valid ? g.r_e[e] : 0.3f, g.inv_cutoff, o, od);
-        st_split(lane_addr + A1H, lane_addr + A1L, o);
+        st_split(lane_addr + VH, lane_addr + VL, o);
         tmem_st_wait();
       }
       fence_before_sync();
-      __syncthreads();
-      // ---- B: u = rbf . Wr^T
-      if (tid == 0) {
+      group_sync(grp);
+      // ---- B: u = rbf . Wr^T   (one warp lists the target segments meanwhile)
+      if (gt == 0) {
         fence_after_sync();
-        issue_gemm_3xtf32(tm + ACC_U, tm + A1H, tm + A1L, smem_u32(sWrH), smem_u32(sWrL), 3, 64, idesc64);
-        mma_commit(&bar);
+        issue_gemm_3xtf32<3>(tm + ACC, tm + VH, tm + VL, smem_u32(sWrH), smem_u32(sWrL), 64, idesc64);
+        mma_commit(bar);
       }
-      mbar_wait(&bar, phase);
+      if (wq == 1) {
+        const int n_valid = min(kTileE, e_end - t0);
+        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, n_valid, lane);
+        if (lane == 0) {
+          tk->n_seg_t = ns;
+          tk->cont_prev = (t0 > e_begin && (int)(g.pair[t0 - 1] >> 16) == tk->tgt[0]) ? 1 : 0;
+        }
+      }
+      mbar_wait(bar, phase);
+      __syncwarp();
       phase ^= 1;
       fence_after_sync();
-      // ---- C: v = silu(u + P[tgt] + Q[src]) -> TMEM
-      {
+      // ---- C: v = silu(u + P[tgt] + Q[src]) -> TMEM   (rows past the end use atom 0: finite, never reduced)
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
         uint32_t ur[32];
-        tmem_ld32(lane_addr + ACC_U + 32 * ch, ur);
-        tmem_ld_wait();
+        tmem_ld32(lane_addr + ACC + 32 * h, ur);
         float v[32];
-        const int tg = sTgt[row], sr = sSrc[row];
-        if (tg >= 0) {
-          const float* pp = tP + tg * ld + 32 * ch;
-          const float* qq = tQ + sr * ld + 32 * ch;
+        const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + 32 * h);
+        const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + 32 * h);
+        float4 p[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float4 p = *reinterpret_cast<const float4*>(pp + 4 * j4);
-            float4 q = *reinterpret_cast<const float4*>(qq + 4 * j4);
-            v[4 * j4 + 0] = silu_f(__uint_as_float(ur[4 * j4 + 0]) + (p.x + q.x));
-            v[4 * j4 + 1] = silu_f(__uint_as_float(ur[4 * j4 + 1]) + (p.y + q.y));
-            v[4 * j4 + 2] = silu_f(__uint_as_float(ur[4 * j4 + 2]) + (p.z + q.z));
-            v[4 * j4 + 3] = silu_f(__uint_as_float(ur[4 * j4 + 3]) + (p.w + q.w));
-          }
-        } else {
+        for (int j4 = 0; j4 < 8; ++j4) p[j4] = __ldg(pp + j4);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 q = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+          v[4 * j4 + 0] = silu_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q.x));
+          v[4 * j4 + 1] = silu_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q.y));
+          v[4 * j4 + 2] = silu_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q.z));
+          v[4 * j4 + 3] = silu_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q.w));
         }
-        st_split(lane_addr + VH + 32 * ch, lane_addr + VL + 32 * ch, v);
-        tmem_st_wait();
+        st_split(lane_addr + VH + 32 * h, lane_addr + VL + 32 * h, v);
       }
+      tmem_st_wait();
       fence_before_sync();
-      __syncthreads();
+      group_sync(grp);
       // ---- D: w = v . W2^T
-      if (tid == 0) {
+      if (gt == 0) {
         fence_after_sync();
-        issue_gemm_3xtf32(tm + ACC_W, tm + VH, tm + VL, smem_u32(sW2H), smem_u32(sW2L), 8, 64, idesc64);
-        mma_commit(&bar);
+        issue_gemm_3xtf32<8>(tm + ACC, tm + VH, tm + VL, smem_u32(sW2H), smem_u32(sW2L), 64, idesc64);
+        mma_commit(bar);
       }
-      mbar_wait(&bar, phase);
+      mbar_wait(bar, phase);
+      __syncwarp();
       phase ^= 1;
       fence_after_sync();
       // ---- E: z = silu(w + b2) -> smem tile
-      {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
         uint32_t wr[32];
-        tmem_ld32(lane_addr + ACC_W + 32 * ch, wr);
+        tmem_ld32(lane_addr + ACC + 32 * h, wr);
         tmem_ld_wait();
-        float* zrow = sZ + row * kTileLd + 32 * ch;
-        const float* bb = sb2 + 32 * ch;
+        float* zrow = sZ + row * kTileLd + 32 * h;
+        const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * h);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float4 b = *reinterpret_cast<const float4*>(bb + 4 * j4);
+          float4 b = bb[j4];
           float4 z;
-          z.x = silu_f(__uint_as_float(wr[4 * j4 + 0]) + b.x);
-          z.y = silu_f(__uint_as_float(wr[4 * j4 + 1]) + b.y);
-          z.z = silu_f(__uint_as_float(wr[4 * j4 + 2]) + b.z);
-          z.w = silu_f(__uint_as_float(wr[4 * j4 + 3]) + b.w);
+          z.x = silu_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x);
+          z.y = silu_fast(__uint_as_float(wr[4 * j4 + 1]) + b.y);
+          z.z = silu_fast(__uint_as_float(wr[4 * j4 + 2]) + b.z);
+          z.w = silu_fast(__uint_as_float(wr[4 * j4 + 3]) + b.w);
           *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
         }
       }
       fence_before_sync();
-      __syncthreads();
+      group_sync(grp);
       // ---- F: a[tgt] += z
-      seg_reduce_ld<false>(sZ, sTgt, nullptr, tA, ld, sCarry, sCKey, tid);
+      reduce_targets_global(sZ, tk, gA, gt);
+      // no barrier here: the next tile touches the other TileKeys buffer, and sZ is rewritten only two
+      // group barriers later
     }
-    if (SMEM_TABLES) {
-      copy_rows_ld(g.a_out + (size_t)atom0 * 64, 64, tA, ld, natoms);
-      __syncthreads();
-    }
+    group_sync(grp);   // all rows of the unit written before its tables are replaced
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
+  if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- adjoint
-// smem (1024-aligned): WrH 8K WrL 8K | W2H 16K W2L 16K | W2tH 16K W2tL 16K | WrtH 8K WrtL 8K | U[128][68] |
-//   carry[256] | tgt[128] src[128] ckey[4] | b2[64] | perm[128 B] | (P, Q, abar, Pbar, Qbar)[5][unit_atoms][68]
-constexpr uint32_t kBwdOffU = 98304;
 template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(kEdgeThreads, 1) edge_bwd_tc_kernel(EdgeTcArgs g) {
+__global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_bwd_tc_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   extern __shared__ uint8_t smraw[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bars[kGroups];
   __shared__ uint32_t tmem_slot;
   uint32_t base = smem_u32(smraw);
   uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
   uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
-  uint8_t *sW2tH = sm + 49152, *sW2tL = sm + 65536, *sWrtH = sm + 81920, *sWrtL = sm + 90112;
-  float* sU = reinterpret_cast<float*>(sm + kBwdOffU);
-  float* sCarry = sU + kTileE * kTileLd;
-  int* sTgt = reinterpret_cast<int*>(sCarry + 256);
-  int* sSrc = sTgt + kTileE;
-  int* sCKey = sSrc + kTileE;
-  float* sb2 = reinterpret_cast<float*>(sCKey + 4);
-  uint8_t* sPerm = reinterpret_cast<uint8_t*>(sb2 + 64);
-  float* sTab = reinterpret_cast<float*>(sPerm + kTileE);
+  uint8_t *sW2tH = sm + 49152, *sW2tL = sm + 65536;
+  float* sb2 = reinterpret_cast<float*>(sm + kBwdWeights);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, ch = warp >> 2;
+  const int grp = tid >> 7, gt = tid & 127, wq = warp & 3, row = gt;
+  uint8_t* gsm = sm + kBwdWeights + 256 + (size_t)grp * grp_bytes;
+  float* sU = reinterpret_cast<float*>(gsm + kGrpX);
+  TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
+  float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
+
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) mbar_init(&bar, 1);
-  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);      // u    : B[n = c ][k    ] = Wr[c][k]
-  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);          // w    : B[n = c ][k    ] = W2[c][k]
-  stage_b_operand(sW2tH, sW2tL, g.W2_t, 64, 64, 64, 64, 64, 1);      // vbar : B[n = k'][k = c] = W2[c][k'] = W2_t[k'][c]
-  stage_b_operand(sWrtH, sWrtL, g.Wr_t, 32, 64, kRbf, 64, 64, 1);    // rbfb : B[n = k'][k = c] = Wr[c][k'] = Wr_t[k'][c]
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+  }
+  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);      // u, du : B[n = c ][k    ] = Wr[c][k]
+  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);          // w     : B[n = c ][k    ] = W2[c][k]
+  stage_b_operand(sW2tH, sW2tL, g.W2_t, 64, 64, 64, 64, 64, 1);      // vbar  : B[n = k'][k = c] = W2[c][k'] = W2_t[k'][c]
   if (tid < 64) sb2[tid] = g.b2[tid];
   fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tm = tmem_slot;
-  const uint32_t lane_addr = tm + ((uint32_t)(32 * (warp & 3)) << 16);
-  constexpr uint32_t ACC0 = 0, ACC1 = 64, ACCR = 128, A1H = 160, A1L = 192, XH = 224, XL = 288;
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64), idesc32 = idesc_tf32(128, 32);
+  const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
+  const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
+  // ACC: u, then w, then vbar.  DU: d u / d r (kept until the last epilogue).  X: A operands (rbf | drbf, v, wbar)
+  constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
+  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+  uint64_t* bar = &bars[grp];
   uint32_t phase = 0;
+  int parity = 0;
 
-  for (int unit = blockIdx.x; unit < g.n_units; unit += gridDim.x) {
+  for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
     const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
     const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
     const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
-    float *tP, *tQ, *tAb, *tPb, *tQb;
+    const float* gP = g.P + (size_t)atom0 * 64;
+    const float* gAb = g.abar + (size_t)atom0 * 64;
+    float* gPb = g.Pbar + (size_t)atom0 * 64;
+    const float* tQ;
+    float* tQb;
     int ld;
     if (SMEM_TABLES) {
       ld = kTabLd;
-      tP = sTab;
-      tQ = tP + g.unit_atoms * kTabLd;
-      tAb = tQ + g.unit_atoms * kTabLd;
-      tPb = tAb + g.unit_atoms * kTabLd;
-      tQb = tPb + g.unit_atoms * kTabLd;
-      copy_rows_ld(tP, ld, g.P + (size_t)atom0 * 64, 64, natoms);
-      copy_rows_ld(tQ, ld, g.Q + (size_t)atom0 * 64, 64, natoms);
-      copy_rows_ld(tAb, ld, g.abar + (size_t)atom0 * 64, 64, natoms);
+      tQb = sTab + g.unit_atoms * kTabLd;
+      copy_rows_grp(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt);
+      tQ = sTab;
     } else {
       ld = 64;
-      tP = const_cast<float*>(g.P) + (size_t)atom0 * 64;
-      tQ = const_cast<float*>(g.Q) + (size_t)atom0 * 64;
-      tAb = const_cast<float*>(g.abar) + (size_t)atom0 * 64;
-      tPb = g.Pbar + (size_t)atom0 * 64;
+      tQ = g.Q + (size_t)atom0 * 64;
       tQb = g.Qbar + (size_t)atom0 * 64;
     }
-    zero_rows_ld(tPb, ld, natoms);
-    zero_rows_ld(tQb, ld, natoms);
-    __syncthreads();
+    zero_rows_grp(gPb, 64, natoms, gt);
+    zero_rows_grp(tQb, ld, natoms, gt);
+    group_sync(grp);
 
     for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-      float drbf[24];   // d rbf_k / dr of this thread's row (used by warps 0-3 only)
-      if (ch == 0) {
-        int e = t0 + row;
-        bool valid = e < e_end;
-        uint32_t pr = valid ? g.pair[e] : 0u;
-        sTgt[row] = valid ? (int)(pr >> 16) : -1;
-        sSrc[row] = valid ? (int)(pr & 0xFFFFu) : -1;
-        sPerm[row] = valid ? g.perm[e] : (uint8_t)row;
-        float o[32];
-        rbf_regs<true>(valid ? g.r_e[e] : 0.3f, g.inv_cutoff, o, drbf);
-        st_split(lane_addr + A1H, lane_addr + A1L, o);
+      TileKeys* tk = keys + parity;
+      parity ^= 1;
+      const int e = t0 + row;
+      const bool valid = e < e_end;
+      const uint32_t pr = valid ? g.pair[e] : 0u;
+      const int tg = valid ? (int)(pr >> 16) : -1, sr = (int)(pr & 0xFFFFu), tgc = valid ? tg : 0;
+      tk->tgt[row] = tg;
+      tk->src[row] = valid ? sr : -1;
+      tk->perm[row] = valid ? g.perm[e] : (uint8_t)row;
+      {
+        float o[32], od[32];
+        rbf_regs<true>(valid ? g.r_e[e] : 0.3f, g.inv_cutoff, o, od);
+        st_split(lane_addr + XH, lane_addr + XL, o);
+        st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
         tmem_st_wait();
       }
       fence_before_sync();
-      __syncthreads();
-      // ---- u = rbf . Wr^T
-      if (tid == 0) {
+      group_sync(grp);
+      // ---- u = rbf . Wr^T ; du = drbf . Wr^T   (two warps list the target / source segments meanwhile)
+      if (gt == 0) {
         fence_after_sync();
-        issue_gemm_3xtf32(tm + ACC0, tm + A1H, tm + A1L, smem_u32(sWrH), smem_u32(sWrL), 3, 64, idesc64);
-        mma_commit(&bar);
+        issue_gemm_3xtf32<3>(tm + ACC, tm + XH, tm + XL, smem_u32(sWrH), smem_u32(sWrL), 64, idesc64);
+        issue_gemm_3xtf32<3>(tm + DU, tm + XH + 32, tm + XL + 32, smem_u32(sWrH), smem_u32(sWrL), 64, idesc64);
+        mma_commit(bar);
       }
-      mbar_wait(&bar, phase);
+      if (wq == 1) {
+        const int n_valid = min(kTileE, e_end - t0);
+        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, n_valid, lane);
+        if (lane == 0) {
+          tk->n_seg_t = ns;
+          tk->cont_prev = (t0 > e_begin && (int)(g.pair[t0 - 1] >> 16) == tk->tgt[0]) ? 1 : 0;
+        }
+      } else if (wq == 2) {
+        const int n_valid = min(kTileE, e_end - t0);
+        const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, n_valid, lane);
+        if (lane == 0) tk->n_seg_s = ns;
+      }
+      mbar_wait(bar, phase);
+      __syncwarp();
       phase ^= 1;
       fence_after_sync();
-      const int tg = sTgt[row], sr = sSrc[row];
-      float dsu[32];
-      {
+      // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM ; keep silu'(u)
+      float dsu[64];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
         uint32_t ur[32];
-        tmem_ld32(lane_addr + ACC0 + 32 * ch, ur);
-        tmem_ld_wait();
+        tmem_ld32(lane_addr + ACC + 32 * h, ur);
         float v[32];
-        if (tg >= 0) {
-          const float* pp = tP + tg * ld + 32 * ch;
-          const float* qq = tQ + sr * ld + 32 * ch;
+        const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + 32 * h);
+        const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + 32 * h);
+        float4 p[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float4 p = *reinterpret_cast<const float4*>(pp + 4 * j4);
-            float4 q = *reinterpret_cast<const float4*>(qq + 4 * j4);
-            silu_fd(__uint_as_float(ur[4 * j4 + 0]) + (p.x + q.x), v[4 * j4 + 0], dsu[4 * j4 + 0]);
-            silu_fd(__uint_as_float(ur[4 * j4 + 1]) + (p.y + q.y), v[4 * j4 + 1], dsu[4 * j4 + 1]);
-            silu_fd(__uint_as_float(ur[4 * j4 + 2]) + (p.z + q.z), v[4 * j4 + 2], dsu[4 * j4 + 2]);
-            silu_fd(__uint_as_float(ur[4 * j4 + 3]) + (p.w + q.w), v[4 * j4 + 3], dsu[4 * j4 + 3]);
-          }
-        } else {
+        for (int j4 = 0; j4 < 8; ++j4) p[j4] = __ldg(pp + j4);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = 0.0f;
-            dsu[j] = 0.0f;
-          }
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 q = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q.x), v[4 * j4 + 0], dsu[32 * h + 4 * j4 + 0]);
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q.y), v[4 * j4 + 1], dsu[32 * h + 4 * j4 + 1]);
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q.z), v[4 * j4 + 2], dsu[32 * h + 4 * j4 + 2]);
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q.w), v[4 * j4 + 3], dsu[32 * h + 4 * j4 + 3]);
         }
-        st_split(lane_addr + XH + 32 * ch, lane_addr + XL + 32 * ch, v);
-        tmem_st_wait();
+        st_split(lane_addr + XH + 32 * h, lane_addr + XL + 32 * h, v);
       }
+      tmem_st_wait();
       fence_before_sync();
-      __syncthreads();
+      group_sync(grp);
       // ---- w = v . W2^T ; wbar = abar[tgt] * silu'(w + b2)
-      if (tid == 0) {
+      if (gt == 0) {
         fence_after_sync();
-        issue_gemm_3xtf32(tm + ACC1, tm + XH, tm + XL, smem_u32(sW2H), smem_u32(sW2L), 8, 64, idesc64);
-        mma_commit(&bar);
+        issue_gemm_3xtf32<8>(tm + ACC, tm + XH, tm + XL, smem_u32(sW2H), smem_u32(sW2L), 64, idesc64);
+        mma_commit(bar);
       }
-      mbar_wait(&bar, phase);
+      mbar_wait(bar, phase);
+      __syncwarp();
+      phase ^= 1;
+      fence_after_sync();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t wr[32];
+        tmem_ld32(lane_addr + ACC + 32 * h, wr);
+        float wb[32];
+        const float4* ab = reinterpret_cast<const float4*>(gAb + (size_t)tgc * 64 + 32 * h);
+        const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * h);
+        float4 a[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) a[j4] = __ldg(ab + j4);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 b = bb[j4];
+          wb[4 * j4 + 0] = a[j4].x * silu_d_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x);
+          wb[4 * j4 + 1] = a[j4].y * silu_d_fast(__uint_as_float(wr[4 * j4 + 1]) + b.y);
+          wb[4 * j4 + 2] = a[j4].z * silu_d_fast(__uint_as_float(wr[4 * j4 + 2]) + b.z);
+          wb[4 * j4 + 3] = a[j4].w * silu_d_fast(__uint_as_float(wr[4 * j4 + 3]) + b.w);
+        }
+        st_split(lane_addr + XH + 32 * h, lane_addr + XL + 32 * h, wb);
+      }
+      tmem_st_wait();
+      fence_before_sync();
+      group_sync(grp);
+      // ---- vbar = wbar . W2 ; ubar = vbar * silu'(u) ; rbar = ubar . du
+      if (gt == 0) {
+        fence_after_sync();
+        issue_gemm_3xtf32<8>(tm + ACC, tm + XH, tm + XL, smem_u32(sW2tH), smem_u32(sW2tL), 64, idesc64);
+        mma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      __syncwarp();
       phase ^= 1;
       fence_after_sync();
       {
-        uint32_t wr[32];
-        tmem_ld32(lane_addr + ACC1 + 32 * ch, wr);
-        tmem_ld_wait();
-        float wb[32];
-        if (tg >= 0) {
-          const float* ab = tAb + tg * ld + 32 * ch;
-          const float* bb = sb2 + 32 * ch;
+        float racc = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t vr[32], dr[32];
+          tmem_ld32(lane_addr + ACC + 32 * h, vr);
+          tmem_ld32(lane_addr + DU + 32 * h, dr);
+          tmem_ld_wait();
+          float* urow = sU + row * kTileLd + 32 * h;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            float4 a = *reinterpret_cast<const float4*>(ab + 4 * j4);
-            float4 b = *reinterpret_cast<const float4*>(bb + 4 * j4);
-            wb[4 * j4 + 0] = a.x * silu_d(__uint_as_float(wr[4 * j4 + 0]) + b.x);
-            wb[4 * j4 + 1] = a.y * silu_d(__uint_as_float(wr[4 * j4 + 1]) + b.y);
-            wb[4 * j4 + 2] = a.z * silu_d(__uint_as_float(wr[4 * j4 + 2]) + b.z);
-            wb[4 * j4 + 3] = a.w * silu_d(__uint_as_float(wr[4 * j4 + 3]) + b.w);
+            float4 ub;
+            ub.x = __uint_as_float(vr[4 * j4 + 0]) * dsu[32 * h + 4 * j4 + 0];
+            ub.y = __uint_as_float(vr[4 * j4 + 1]) * dsu[32 * h + 4 * j4 + 1];
+            ub.z = __uint_as_float(vr[4 * j4 + 2]) * dsu[32 * h + 4 * j4 + 2];
+            ub.w = __uint_as_float(vr[4 * j4 + 3]) * dsu[32 * h + 4 * j4 + 3];
+            racc = fmaf(ub.x, __uint_as_float(dr[4 * j4 + 0]), racc);
+            racc = fmaf(ub.y, __uint_as_float(dr[4 * j4 + 1]), racc);
+            racc = fmaf(ub.z, __uint_as_float(dr[4 * j4 + 2]), racc);
+            racc = fmaf(ub.w, __uint_as_float(dr[4 * j4 + 3]), racc);
+            *reinterpret_cast<float4*>(urow + 4 * j4) = ub;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) wb[j] = 0.0f;
         }
-        st_split(lane_addr + XH + 32 * ch, lane_addr + XL + 32 * ch, wb);
-        tmem_st_wait();
-      }
-      fence_before_sync();
-      __syncthreads();
-      // ---- vbar = wbar . W2 ; ubar = vbar * silu'(u)
-      if (tid == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32(tm + ACC0, tm + XH, tm + XL, smem_u32(sW2tH), smem_u32(sW2tL), 8, 64, idesc64);
-        mma_commit(&bar);
-      }
-      mbar_wait(&bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-      {
-        uint32_t vr[32];
-        tmem_ld32(lane_addr + ACC0 + 32 * ch, vr);
-        tmem_ld_wait();
-        float ub[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ub[j] = __uint_as_float(vr[j]) * dsu[j];
-        float* urow = sU + row * kTileLd + 32 * ch;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<float4*>(urow + 4 * j4) = make_float4(ub[4 * j4], ub[4 * j4 + 1], ub[4 * j4 + 2], ub[4 * j4 + 3]);
-        st_split(lane_addr + XH + 32 * ch, lane_addr + XL + 32 * ch, ub);
-        tmem_st_wait();
-      }
-      fence_before_sync();
-      __syncthreads();
-      // ---- rbfbar = ubar . Wr  (runs while the segmented reductions below use the smem copy of ubar)
-      if (tid == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32(tm + ACCR, tm + XH, tm + XL, smem_u32(sWrtH), smem_u32(sWrtL), 8, 32, idesc32);
-        mma_commit(&bar);
-      }
-      seg_reduce_ld<false>(sU, sTgt, nullptr, tPb, ld, sCarry, sCKey, tid);   // Pbar[tgt] += ubar
-      seg_reduce_ld<true>(sU, sSrc, sPerm, tQb, ld, sCarry, sCKey, tid);      // Qbar[src] += ubar
-      mbar_wait(&bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-      if (ch == 0) {
-        uint32_t rr[32];
-        tmem_ld32(lane_addr + ACCR, rr);
-        tmem_ld_wait();
-        if (tg >= 0) {
-          float acc = 0.0f;
-#pragma unroll
-          for (int k = 0; k < kRbf; ++k) acc = fmaf(__uint_as_float(rr[k]), drbf[k], acc);
+        if (valid) {
           int repl = tg / g.N;
           size_t slot = ((size_t)atom0 + tg) * g.N + (sr - repl * g.N);
-          g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + acc : acc;
+          g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + racc : racc;
         }
       }
       fence_before_sync();
-      __syncthreads();
+      group_sync(grp);
+      reduce_targets_global(sU, tk, gPb, gt);            // Pbar[tgt] += ubar
+      reduce_sources_table(sU, tk, tQb, ld, gt);         // Qbar[src] += ubar
     }
+    group_sync(grp);
     if (SMEM_TABLES) {
-      copy_rows_ld(g.Pbar + (size_t)atom0 * 64, 64, tPb, ld, natoms);
-      copy_rows_ld(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms);
-      __syncthreads();
+      copy_rows_grp(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt);
+      group_sync(grp);
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
+  if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- launchers
-static size_t fwd_tc_smem(const Ctx* c) {
-  size_t b = kFwdOffZ + (size_t)(kTileE * kTileLd + 256 + 2 * kTileE + 4 + 64) * 4 + 1024;
-  if (c->smem_tables) b += 3 * (size_t)c->G * c->N * kTabLd * 4;
-  return b;
-}
-static size_t bwd_tc_smem(const Ctx* c) {
-  size_t b = kBwdOffU + (size_t)(kTileE * kTileLd + 256 + 2 * kTileE + 4 + 64) * 4 + kTileE + 1024;
-  if (c->smem_tables) b += 5 * (size_t)c->G * c->N * kTabLd * 4;
-  return b;
-}
-
 static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   EdgeTcArgs g{};
   g.n_units = c->n_units;
@@ -629,9 +726,8 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   g.inv_cutoff = (float)(1.0 / (double)c->cutoff);
   g.Wr = c->L[l].Wr;
   g.W2 = c->L[l].W2;
-  g.b2 = c->L[l].b2;
-  g.Wr_t = c->L[l].Wr_t;
   g.W2_t = c->L[l].W2_t;
+  g.b2 = c->L[l].b2;
   g.P = c->P[l];
   g.Q = c->Q[l];
   g.a_out = c->a[l];
@@ -646,16 +742,21 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
 
 bool tc_path_fits(const Ctx* c) { return fwd_tc_smem(c) <= 227 * 1024 && bwd_tc_smem(c) <= 227 * 1024; }
 
+static int tc_grid(const Ctx* c) {
+  int want = (c->n_units + kGroups - 1) / kGroups;
+  return want < c->num_sms ? want : c->num_sms;
+}
+
 int launch_edge_fwd_tc(Ctx* c, int l, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
-  int grid = c->n_units < c->num_sms ? c->n_units : c->num_sms;
   size_t smem = fwd_tc_smem(c);
+  uint32_t gb = (uint32_t)group_bytes(c, 1);
   if (c->smem_tables) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_tc_kernel<true><<<grid, kEdgeThreads, smem, st>>>(g);
+    edge_fwd_tc_kernel<true><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
   } else {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_tc_kernel<false><<<grid, kEdgeThreads, smem, st>>>(g);
+    edge_fwd_tc_kernel<false><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
   }
   GNNIS_LAUNCH_CHECK();
   return 0;
@@ -664,14 +765,14 @@ int launch_edge_fwd_tc(Ctx* c, int l, cudaStream_t st) {
 int launch_edge_bwd_tc(Ctx* c, int l, int rbar_accumulate, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
   g.rbar_accumulate = rbar_accumulate;
-  int grid = c->n_units < c->num_sms ? c->n_units : c->num_sms;
   size_t smem = bwd_tc_smem(c);
+  uint32_t gb = (uint32_t)group_bytes(c, 2);
   if (c->smem_tables) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_tc_kernel<true><<<grid, kEdgeThreads, smem, st>>>(g);
+    edge_bwd_tc_kernel<true><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
   } else {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_tc_kernel<false><<<grid, kEdgeThreads, smem, st>>>(g);
+    edge_bwd_tc_kernel<false><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
   }
   GNNIS_LAUNCH_CHECK();
   return 0;

@@ -30,10 +30,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// bounded wait: a wrong descriptor / lost commit traps (error reported to the host) instead of hanging the GPU
+// bounded wait: a wrong descriptor / lost commit traps after ~2 s (error reported to the host) instead of hanging
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -43,8 +49,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
+    if ((it & 255u) == 255u) {
+      uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) __trap();
+    }
   }
-  __trap();
 }
 // arrive on the mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -57,6 +67,15 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major operand, 128-byte swizzle (cute::UMMA canonical ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 4 fp32):
+// for one k, 32 consecutive n are contiguous (128 B); 8 k-rows form a 1024-B atom (SBO = 1024 B between k-groups);
+// 32-wide n panels are `lbo_bytes` apart.  A matrix staged K-major with sw128_offset(n', k', rows) is, byte for
+// byte, the MN-major operand with (n, k) = (k', n') and LBO = rows * 128.  `addr` = panel base + 1024 * (k / 8).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+constexpr uint32_t kIdescBMajorMN = 1u << 16;   // instruction-descriptor bit: B operand is MN-major
 // kind::tf32, fp32 accumulate, A and B K-major, M x N tile
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
