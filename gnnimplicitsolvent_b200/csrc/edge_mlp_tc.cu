@@ -100,23 +100,26 @@ __device__ __forceinline__ void stage_b_operand(uint8_t* hi, uint8_t* lo, const 
   }
 }
 
-// D[128 x N] = A[128 x 8*KSTEPS] * B^T, three TF32 products; A (hi, lo) in TMEM, B (hi, lo) K-major SW128 in smem
-template <int KSTEPS>
+// D[128 x N] (+)= A[128 x k in [8 S0, 8 S1)] * B^T, three TF32 products; A (hi, lo) in TMEM, B (hi, lo) K-major SW128
+// in smem.  `accumulate` = 0 overwrites D with the first product.
+template <int S0, int S1>
 __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_addr,
-                                                  uint32_t b_lo_addr, int b_rows, uint32_t idesc) {
-  uint32_t acc = 0;
+                                                  uint32_t b_lo_addr, int b_rows, uint32_t idesc, uint32_t accumulate) {
+  uint32_t acc = accumulate;
 #pragma unroll
   for (int term = 0; term < 3; ++term) {
     const uint32_t a = term == 2 ? a_lo : a_hi;
     const uint32_t b = term == 1 ? b_lo_addr : b_hi_addr;
 #pragma unroll
-    for (int s = 0; s < KSTEPS; ++s) {
+    for (int s = S0; s < S1; ++s) {
       uint32_t baddr = b + (uint32_t)(s >> 2) * (uint32_t)b_rows * 128u + (uint32_t)(s & 3) * 32u;
       mma_tf32_ts(d_tmem, a + 8u * (uint32_t)s, smem_desc_k_sw128(baddr), idesc, acc);
       acc = 1;
     }
   }
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // radial basis row in registers (GNN_Layers.py:2194-2208): d = r/cutoff, env = 1/d - 28 d^5 + 48 d^6 - 21 d^7,
 // rbf_k = env sin(k pi d); sin/cos(k pi d) from one sincospi and the Chebyshev recurrence.  o[20..31] = 0.
 template <bool DERIV>
@@ -212,14 +215,32 @@ __device__ __forceinline__ void reduce_targets_global(const float* __restrict__ 
   const int nseg = tk->n_seg_t;
   for (int s = slot; s < nseg; s += kSlots) {
     const int p0 = tk->seg_t[s], p1 = tk->seg_t[s + 1];
-    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = p0; p < p1; ++p) {
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f), run2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = p0;
+#pragma unroll 2
+    for (; p + 1 < p1; p += 2) {   // two interleaved partial sums, fixed order
+      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
+      const float4 w = *reinterpret_cast<const float4*>(sX + (p + 1) * kTileLd + 4 * cq);
+      run.x += v.x;
+      run.y += v.y;
+      run.z += v.z;
+      run.w += v.w;
+      run2.x += w.x;
+      run2.y += w.y;
+      run2.z += w.z;
+      run2.w += w.w;
+    }
+    if (p < p1) {
       const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
       run.x += v.x;
       run.y += v.y;
       run.z += v.z;
       run.w += v.w;
     }
+    run.x += run2.x;
+    run.y += run2.y;
+    run.z += run2.z;
+    run.w += run2.w;
     float4* dst = reinterpret_cast<float4*>(out + (size_t)tk->tgt[p0] * 64 + 4 * cq);
     if (s == 0 && tk->cont_prev) {
       float4 t = *dst;
@@ -293,8 +314,8 @@ __global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __re
   __syncthreads();
   if (tid == 0) {
     fence_after_sync();
-    if (K == 64) issue_gemm_3xtf32<8>(tm + ACC, tm + AH, tm + AL, smem_u32(bh), smem_u32(bl), N, idesc_tf32(128, N));
-    else issue_gemm_3xtf32<4>(tm + ACC, tm + AH, tm + AL, smem_u32(bh), smem_u32(bl), N, idesc_tf32(128, N));
+    if (K == 64) issue_gemm_3xtf32<0, 8>(tm + ACC, tm + AH, tm + AL, smem_u32(bh), smem_u32(bl), N, idesc_tf32(128, N), 0u);
+    else issue_gemm_3xtf32<0, 4>(tm + ACC, tm + AH, tm + AL, smem_u32(bh), smem_u32(bl), N, idesc_tf32(128, N), 0u);
     mma_commit(&bar);
   }
   mbar_wait(&bar, 0);
@@ -332,6 +353,13 @@ static size_t fwd_tc_smem(const Ctx* c) { return kFwdWeights + 256 + kGroups * g
 static size_t bwd_tc_smem(const Ctx* c) { return kBwdWeights + 256 + kGroups * group_bytes(c, 2) + 1024; }
 
 // ---------------------------------------------------------------------------------------------- forward
+// TMEM columns of a group: B0 64 | B1 64 | V hi 64 | V lo 64.  Tile t has u in B[t & 1]; w goes to the other buffer
+// (so the first K half of w may be issued while the second half of u is still being read); once u has been read
+// its buffer receives the radial basis (hi 32 | lo 32) of tile t+1, whose u lands in the buffer w has left.
+// Per tile t:  wait u(t) -> v half 0 -> issue w k[0,32) -> v half 1 -> issue w k[32,64) -> rbf(t+1) ->
+//              wait w(t) -> load w to registers -> issue u(t+1) -> z = silu(w + b2) -> segmented sums of tile t.
+// so the tensor pipe works on the second half of w while the first half of the next epilogue is computed, and u of
+// the next tile is produced under the second epilogue and the reduction.
 template <bool SMEM_TABLES>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_fwd_tc_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   extern __shared__ uint8_t smraw[];
@@ -363,8 +391,10 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_fwd_tc_kernel
   fence_after_sync();
   const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;            // this group's 256 columns
   const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-  constexpr uint32_t ACC = 0, VH = 64, VL = 128;                   // rbf A operand aliases V[0..31]
+  constexpr uint32_t VH = 128, VL = 192;
+  uint32_t cur = 0;   // buffer (column offset 0 or 64) holding u of the current tile
   constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+  const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
   uint64_t* bar = &bars[grp];
   uint32_t phase = 0;
   int parity = 0;
@@ -386,103 +416,159 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_fwd_tc_kernel
       tQ = g.Q + (size_t)atom0 * 64;
     }
     zero_rows_grp(gA, 64, natoms, gt);
+    if (e_begin >= e_end) {   // no edges in this unit
+      group_sync(grp);
+      continue;
+    }
+    // ---- prologue: keys, radial basis and u of the first tile; edge data of the second tile in flight
+    uint32_t pr = 0u, pr_n = 0u;
+    float r = 0.3f, r_n = 0.3f;
+    bool valid = e_begin + row < e_end;
+    if (valid) {
+      pr = g.pair[e_begin + row];
+      r = g.r_e[e_begin + row];
+    }
+    if (e_begin + kTileE + row < e_end) {
+      pr_n = g.pair[e_begin + kTileE + row];
+      r_n = g.r_e[e_begin + kTileE + row];
+    }
+    TileKeys* tk = keys + parity;
+    tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
+    prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64);
+    prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32);
+    {
+      float o[32], od[32];
+      rbf_regs<false>(r, g.inv_cutoff, o, od);
+      st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
+      tmem_st_wait();
+    }
+    fence_before_sync();
     group_sync(grp);
+    if (gt == 0) {
+      fence_after_sync();
+      issue_gemm_3xtf32<0, 3>(tm + cur, tm + (cur ^ 64u), tm + (cur ^ 64u) + 32, aWrH, aWrL, 64, idesc64, 0u);
+      mma_commit(bar);
+    }
 
     for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-      TileKeys* tk = keys + parity;
-      parity ^= 1;
-      // ---- A: this thread's edge, radial basis -> TMEM
-      const int e = t0 + row;
-      const bool valid = e < e_end;
-      const uint32_t pr = valid ? g.pair[e] : 0u;
-      const int tg = valid ? (int)(pr >> 16) : -1, sr = (int)(pr & 0xFFFFu), tgc = valid ? tg : 0;
-      tk->tgt[row] = tg;
-      {
-        float o[32], od[32];
-        rbf_regs<false>(valid ? g.r_e[e] : 0.3f, g.inv_cutoff, o, od);
-        st_split(lane_addr + VH, lane_addr + VL, o);
-        tmem_st_wait();
-      }
-      fence_before_sync();
-      group_sync(grp);
-      // ---- B: u = rbf . Wr^T   (one warp lists the target segments meanwhile)
-      if (gt == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32<3>(tm + ACC, tm + VH, tm + VL, smem_u32(sWrH), smem_u32(sWrL), 64, idesc64);
-        mma_commit(bar);
-      }
+      const bool has_next = t0 + kTileE < e_end;
+      const int tgc = valid ? (int)(pr >> 16) : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
       if (wq == 1) {
-        const int n_valid = min(kTileE, e_end - t0);
-        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, n_valid, lane);
+        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
         if (lane == 0) {
           tk->n_seg_t = ns;
-          tk->cont_prev = (t0 > e_begin && (int)(g.pair[t0 - 1] >> 16) == tk->tgt[0]) ? 1 : 0;
+          tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
         }
       }
       mbar_wait(bar, phase);
       __syncwarp();
       phase ^= 1;
       fence_after_sync();
-      // ---- C: v = silu(u + P[tgt] + Q[src]) -> TMEM   (rows past the end use atom 0: finite, never reduced)
-#pragma unroll 1
+      // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM, w issued in two K halves
+#pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t ur[32];
-        tmem_ld32(lane_addr + ACC + 32 * h, ur);
-        float v[32];
+        tmem_ld32(lane_addr + cur + 32 * h, ur);
         const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + 32 * h);
         const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + 32 * h);
-        float4 p[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) p[j4] = __ldg(pp + j4);
-        tmem_ld_wait();
+        float4 p[8], q[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float4 q = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
-          v[4 * j4 + 0] = silu_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q.x));
-          v[4 * j4 + 1] = silu_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q.y));
-          v[4 * j4 + 2] = silu_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q.z));
-          v[4 * j4 + 3] = silu_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q.w));
+          p[j4] = __ldg(pp + j4);
+          q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          v[4 * j4 + 0] = silu_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x));
+          v[4 * j4 + 1] = silu_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y));
+          v[4 * j4 + 2] = silu_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z));
+          v[4 * j4 + 3] = silu_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
         }
         st_split(lane_addr + VH + 32 * h, lane_addr + VL + 32 * h, v);
+        tmem_st_wait();
+        fence_before_sync();
+        group_sync(grp);
+        if (gt == 0) {
+          fence_after_sync();
+          if (h == 0) {
+            issue_gemm_3xtf32<0, 4>(tm + (cur ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
+          } else {
+            issue_gemm_3xtf32<4, 8>(tm + (cur ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 1u);
+            mma_commit(bar);
+          }
+        }
       }
-      tmem_st_wait();
-      fence_before_sync();
-      group_sync(grp);
-      // ---- D: w = v . W2^T
-      if (gt == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32<8>(tm + ACC, tm + VH, tm + VL, smem_u32(sW2H), smem_u32(sW2L), 64, idesc64);
-        mma_commit(bar);
+      // ---- look ahead: keys and radial basis of the next tile while w runs
+      TileKeys* tkn = keys + (parity ^ 1);
+      bool valid_n = false;
+      uint32_t pr_nn = 0u;
+      float r_nn = 0.3f;
+      if (has_next) {
+        valid_n = t0 + kTileE + row < e_end;
+        tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
+        const float* pn = gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64;
+        prefetch_l1(pn);
+        prefetch_l1(pn + 32);
+        if (t0 + 2 * kTileE + row < e_end) {
+          pr_nn = g.pair[t0 + 2 * kTileE + row];
+          r_nn = g.r_e[t0 + 2 * kTileE + row];
+        }
+        float o[32], od[32];
+        rbf_regs<false>(r_n, g.inv_cutoff, o, od);
+        st_split(lane_addr + cur, lane_addr + cur + 32, o);   // u of this tile has been consumed
       }
       mbar_wait(bar, phase);
       __syncwarp();
       phase ^= 1;
       fence_after_sync();
-      // ---- E: z = silu(w + b2) -> smem tile
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        uint32_t wr[32];
-        tmem_ld32(lane_addr + ACC + 32 * h, wr);
-        tmem_ld_wait();
-        float* zrow = sZ + row * kTileLd + 32 * h;
-        const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * h);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          float4 b = bb[j4];
-          float4 z;
-          z.x = silu_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x);
-          z.y = silu_fast(__uint_as_float(wr[4 * j4 + 1]) + b.y);
-          z.z = silu_fast(__uint_as_float(wr[4 * j4 + 2]) + b.z);
-          z.w = silu_fast(__uint_as_float(wr[4 * j4 + 3]) + b.w);
-          *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
+      // ---- w -> registers, then u of the next tile may overwrite the accumulator
+      uint32_t wr[64];
+      tmem_ld32(lane_addr + (cur ^ 64u), *reinterpret_cast<uint32_t(*)[32]>(&wr[0]));
+      tmem_ld32(lane_addr + (cur ^ 64u) + 32, *reinterpret_cast<uint32_t(*)[32]>(&wr[32]));
+      tmem_ld_wait();
+      if (has_next) {
+        tmem_st_wait();
+        fence_before_sync();
+        group_sync(grp);
+        if (gt == 0) {
+          fence_after_sync();
+          issue_gemm_3xtf32<0, 3>(tm + (cur ^ 64u), tm + cur, tm + cur + 32, aWrH, aWrL, 64, idesc64, 0u);
+          mma_commit(bar);
         }
       }
-      fence_before_sync();
+      // ---- z = silu(w + b2) -> smem tile
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * h);
+        float4 b[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) b[j4] = bb[j4];
+        float4 z[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          z[j4].x = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 0]) + b[j4].x);
+          z[j4].y = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 1]) + b[j4].y);
+          z[j4].z = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 2]) + b[j4].z);
+          z[j4].w = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 3]) + b[j4].w);
+        }
+        float* zrow = sZ + row * kTileLd + 32 * h;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(zrow + 4 * j4) = z[j4];
+      }
       group_sync(grp);
-      // ---- F: a[tgt] += z
+      // ---- a[tgt] += z
       reduce_targets_global(sZ, tk, gA, gt);
-      // no barrier here: the next tile touches the other TileKeys buffer, and sZ is rewritten only two
-      // group barriers later
+      // no barrier here: the next tile uses the other TileKeys buffer and rewrites sZ only after two more barriers
+      pr = pr_n;
+      r = r_n;
+      valid = valid_n;
+      pr_n = pr_nn;
+      r_n = r_nn;
+      tk = tkn;
+      parity ^= 1;
+      cur ^= 64u;
     }
     group_sync(grp);   // all rows of the unit written before its tables are replaced
   }
@@ -492,6 +578,10 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_fwd_tc_kernel
 }
 
 // ---------------------------------------------------------------------------------------------- adjoint
+// TMEM columns of a group: ACC (u, then w, then vbar) 64 | DU (d u / d r) 64 | X hi 64 | X lo 64, where X holds the
+// A operands in turn: rbf | drbf (32 + 32 columns), v, wbar.
+// Per tile t:  wait u, du -> v -> issue w -> wait w -> wbar -> issue vbar -> wait vbar ->
+//              ubar = vbar silu'(u), rbar = ubar . du -> rbf, drbf (t+1) -> issue u, du (t+1) -> segmented sums of t.
 template <bool SMEM_TABLES>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_bwd_tc_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   extern __shared__ uint8_t smraw[];
@@ -525,9 +615,10 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_bwd_tc_kernel
   fence_after_sync();
   const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
   const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-  // ACC: u, then w, then vbar.  DU: d u / d r (kept until the last epilogue).  X: A operands (rbf | drbf, v, wbar)
   constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
   constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+  const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
+  const uint32_t aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
   uint64_t* bar = &bars[grp];
   uint32_t phase = 0;
   int parity = 0;
@@ -554,153 +645,227 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_bwd_tc_kernel
     }
     zero_rows_grp(gPb, 64, natoms, gt);
     zero_rows_grp(tQb, ld, natoms, gt);
+    if (e_begin >= e_end) {
+      group_sync(grp);
+      if (SMEM_TABLES) {
+        copy_rows_grp(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt);
+        group_sync(grp);
+      }
+      continue;
+    }
+    // ---- prologue: keys, rbf / drbf and u / du of the first tile; edge data of the second tile in flight
+    uint32_t pr = 0u, pr_n = 0u;
+    float r = 0.3f, r_n = 0.3f;
+    uint8_t pm = (uint8_t)row, pm_n = (uint8_t)row;
+    bool valid = e_begin + row < e_end;
+    if (valid) {
+      pr = g.pair[e_begin + row];
+      r = g.r_e[e_begin + row];
+      pm = g.perm[e_begin + row];
+    }
+    if (e_begin + kTileE + row < e_end) {
+      pr_n = g.pair[e_begin + kTileE + row];
+      r_n = g.r_e[e_begin + kTileE + row];
+      pm_n = g.perm[e_begin + kTileE + row];
+    }
+    TileKeys* tk = keys + parity;
+    tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
+    tk->src[row] = valid ? (int)(pr & 0xFFFFu) : -1;
+    tk->perm[row] = pm;
+    {
+      const size_t t_ = (size_t)(valid ? (pr >> 16) : 0u) * 64;
+      prefetch_l1(gP + t_);
+      prefetch_l1(gP + t_ + 32);
+      prefetch_l1(gAb + t_);
+      prefetch_l1(gAb + t_ + 32);
+      float o[32], od[32];
+      rbf_regs<true>(r, g.inv_cutoff, o, od);
+      st_split(lane_addr + XH, lane_addr + XL, o);
+      st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
+      tmem_st_wait();
+    }
+    fence_before_sync();
     group_sync(grp);
+    if (gt == 0) {
+      fence_after_sync();
+      issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
+      issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
+      mma_commit(bar);
+    }
 
     for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-      TileKeys* tk = keys + parity;
-      parity ^= 1;
-      const int e = t0 + row;
-      const bool valid = e < e_end;
-      const uint32_t pr = valid ? g.pair[e] : 0u;
-      const int tg = valid ? (int)(pr >> 16) : -1, sr = (int)(pr & 0xFFFFu), tgc = valid ? tg : 0;
-      tk->tgt[row] = tg;
-      tk->src[row] = valid ? sr : -1;
-      tk->perm[row] = valid ? g.perm[e] : (uint8_t)row;
-      {
-        float o[32], od[32];
-        rbf_regs<true>(valid ? g.r_e[e] : 0.3f, g.inv_cutoff, o, od);
-        st_split(lane_addr + XH, lane_addr + XL, o);
-        st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
-        tmem_st_wait();
-      }
-      fence_before_sync();
-      group_sync(grp);
-      // ---- u = rbf . Wr^T ; du = drbf . Wr^T   (two warps list the target / source segments meanwhile)
-      if (gt == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32<3>(tm + ACC, tm + XH, tm + XL, smem_u32(sWrH), smem_u32(sWrL), 64, idesc64);
-        issue_gemm_3xtf32<3>(tm + DU, tm + XH + 32, tm + XL + 32, smem_u32(sWrH), smem_u32(sWrL), 64, idesc64);
-        mma_commit(bar);
-      }
+      const bool has_next = t0 + kTileE < e_end;
+      const int tg = valid ? (int)(pr >> 16) : -1, tgc = valid ? tg : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
       if (wq == 1) {
-        const int n_valid = min(kTileE, e_end - t0);
-        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, n_valid, lane);
+        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
         if (lane == 0) {
           tk->n_seg_t = ns;
-          tk->cont_prev = (t0 > e_begin && (int)(g.pair[t0 - 1] >> 16) == tk->tgt[0]) ? 1 : 0;
+          tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
         }
       } else if (wq == 2) {
-        const int n_valid = min(kTileE, e_end - t0);
-        const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, n_valid, lane);
+        const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, min(kTileE, e_end - t0), lane);
         if (lane == 0) tk->n_seg_s = ns;
       }
       mbar_wait(bar, phase);
       __syncwarp();
       phase ^= 1;
       fence_after_sync();
-      // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM ; keep silu'(u)
+      // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM ; keep silu'(u); w issued in two K halves
       float dsu[64];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t ur[32];
         tmem_ld32(lane_addr + ACC + 32 * h, ur);
-        float v[32];
         const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + 32 * h);
         const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + 32 * h);
-        float4 p[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) p[j4] = __ldg(pp + j4);
-        tmem_ld_wait();
+        float4 p[8], q[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float4 q = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q.x), v[4 * j4 + 0], dsu[32 * h + 4 * j4 + 0]);
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q.y), v[4 * j4 + 1], dsu[32 * h + 4 * j4 + 1]);
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q.z), v[4 * j4 + 2], dsu[32 * h + 4 * j4 + 2]);
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q.w), v[4 * j4 + 3], dsu[32 * h + 4 * j4 + 3]);
+          p[j4] = __ldg(pp + j4);
+          q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x), v[4 * j4 + 0], dsu[32 * h + 4 * j4 + 0]);
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y), v[4 * j4 + 1], dsu[32 * h + 4 * j4 + 1]);
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z), v[4 * j4 + 2], dsu[32 * h + 4 * j4 + 2]);
+          silu_fd_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w), v[4 * j4 + 3], dsu[32 * h + 4 * j4 + 3]);
         }
         st_split(lane_addr + XH + 32 * h, lane_addr + XL + 32 * h, v);
       }
       tmem_st_wait();
       fence_before_sync();
       group_sync(grp);
-      // ---- w = v . W2^T ; wbar = abar[tgt] * silu'(w + b2)
       if (gt == 0) {
         fence_after_sync();
-        issue_gemm_3xtf32<8>(tm + ACC, tm + XH, tm + XL, smem_u32(sW2H), smem_u32(sW2L), 64, idesc64);
+        issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2H, aW2L, 64, idesc64, 0u);
         mma_commit(bar);
       }
       mbar_wait(bar, phase);
       __syncwarp();
       phase ^= 1;
       fence_after_sync();
-#pragma unroll 1
+      // ---- wbar = abar[tgt] * silu'(w + b2) -> TMEM ; vbar issued in two K halves
+#pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t wr[32];
         tmem_ld32(lane_addr + ACC + 32 * h, wr);
-        float wb[32];
         const float4* ab = reinterpret_cast<const float4*>(gAb + (size_t)tgc * 64 + 32 * h);
         const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * h);
-        float4 a[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) a[j4] = __ldg(ab + j4);
-        tmem_ld_wait();
+        float4 a[8], b[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float4 b = bb[j4];
-          wb[4 * j4 + 0] = a[j4].x * silu_d_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x);
-          wb[4 * j4 + 1] = a[j4].y * silu_d_fast(__uint_as_float(wr[4 * j4 + 1]) + b.y);
-          wb[4 * j4 + 2] = a[j4].z * silu_d_fast(__uint_as_float(wr[4 * j4 + 2]) + b.z);
-          wb[4 * j4 + 3] = a[j4].w * silu_d_fast(__uint_as_float(wr[4 * j4 + 3]) + b.w);
+          a[j4] = __ldg(ab + j4);
+          b[j4] = bb[j4];
+        }
+        tmem_ld_wait();
+        float wb[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          wb[4 * j4 + 0] = a[j4].x * silu_d_fast(__uint_as_float(wr[4 * j4 + 0]) + b[j4].x);
+          wb[4 * j4 + 1] = a[j4].y * silu_d_fast(__uint_as_float(wr[4 * j4 + 1]) + b[j4].y);
+          wb[4 * j4 + 2] = a[j4].z * silu_d_fast(__uint_as_float(wr[4 * j4 + 2]) + b[j4].z);
+          wb[4 * j4 + 3] = a[j4].w * silu_d_fast(__uint_as_float(wr[4 * j4 + 3]) + b[j4].w);
         }
         st_split(lane_addr + XH + 32 * h, lane_addr + XL + 32 * h, wb);
       }
       tmem_st_wait();
       fence_before_sync();
       group_sync(grp);
-      // ---- vbar = wbar . W2 ; ubar = vbar * silu'(u) ; rbar = ubar . du
       if (gt == 0) {
         fence_after_sync();
-        issue_gemm_3xtf32<8>(tm + ACC, tm + XH, tm + XL, smem_u32(sW2tH), smem_u32(sW2tL), 64, idesc64);
+        issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2tH, aW2tL, 64, idesc64, 0u);
         mma_commit(bar);
+      }
+      // edge data of the tile after next (registers), while vbar runs
+      TileKeys* tkn = keys + (parity ^ 1);
+      bool valid_n = false;
+      uint32_t pr_nn = 0u;
+      float r_nn = 0.3f;
+      uint8_t pm_nn = (uint8_t)row;
+      if (has_next) {
+        valid_n = t0 + kTileE + row < e_end;
+        tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
+        tkn->src[row] = valid_n ? (int)(pr_n & 0xFFFFu) : -1;
+        tkn->perm[row] = valid_n ? pm_n : (uint8_t)row;
+        const size_t t_ = (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64;
+        prefetch_l1(gP + t_);
+        prefetch_l1(gP + t_ + 32);
+        prefetch_l1(gAb + t_);
+        prefetch_l1(gAb + t_ + 32);
+        if (t0 + 2 * kTileE + row < e_end) {
+          pr_nn = g.pair[t0 + 2 * kTileE + row];
+          r_nn = g.r_e[t0 + 2 * kTileE + row];
+          pm_nn = g.perm[t0 + 2 * kTileE + row];
+        }
       }
       mbar_wait(bar, phase);
       __syncwarp();
       phase ^= 1;
       fence_after_sync();
-      {
-        float racc = 0.0f;
+      // ---- ubar = vbar * silu'(u) -> smem tile ; rbar = ubar . du
+      float racc = 0.0f;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t vr[32], dr[32];
-          tmem_ld32(lane_addr + ACC + 32 * h, vr);
-          tmem_ld32(lane_addr + DU + 32 * h, dr);
-          tmem_ld_wait();
-          float* urow = sU + row * kTileLd + 32 * h;
+      for (int h = 0; h < 2; ++h) {
+        uint32_t vr[32], dr[32];
+        tmem_ld32(lane_addr + ACC + 32 * h, vr);
+        tmem_ld32(lane_addr + DU + 32 * h, dr);
+        tmem_ld_wait();
+        float4 ub[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float4 ub;
-            ub.x = __uint_as_float(vr[4 * j4 + 0]) * dsu[32 * h + 4 * j4 + 0];
-            ub.y = __uint_as_float(vr[4 * j4 + 1]) * dsu[32 * h + 4 * j4 + 1];
-            ub.z = __uint_as_float(vr[4 * j4 + 2]) * dsu[32 * h + 4 * j4 + 2];
-            ub.w = __uint_as_float(vr[4 * j4 + 3]) * dsu[32 * h + 4 * j4 + 3];
-            racc = fmaf(ub.x, __uint_as_float(dr[4 * j4 + 0]), racc);
-            racc = fmaf(ub.y, __uint_as_float(dr[4 * j4 + 1]), racc);
-            racc = fmaf(ub.z, __uint_as_float(dr[4 * j4 + 2]), racc);
-            racc = fmaf(ub.w, __uint_as_float(dr[4 * j4 + 3]), racc);
-            *reinterpret_cast<float4*>(urow + 4 * j4) = ub;
-          }
+        for (int j4 = 0; j4 < 8; ++j4) {
+          ub[j4].x = __uint_as_float(vr[4 * j4 + 0]) * dsu[32 * h + 4 * j4 + 0];
+          ub[j4].y = __uint_as_float(vr[4 * j4 + 1]) * dsu[32 * h + 4 * j4 + 1];
+          ub[j4].z = __uint_as_float(vr[4 * j4 + 2]) * dsu[32 * h + 4 * j4 + 2];
+          ub[j4].w = __uint_as_float(vr[4 * j4 + 3]) * dsu[32 * h + 4 * j4 + 3];
         }
-        if (valid) {
-          int repl = tg / g.N;
-          size_t slot = ((size_t)atom0 + tg) * g.N + (sr - repl * g.N);
-          g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + racc : racc;
+        float ra = 0.0f, rb = 0.0f;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          ra = fmaf(ub[j4].x, __uint_as_float(dr[4 * j4 + 0]), ra);
+          rb = fmaf(ub[j4].y, __uint_as_float(dr[4 * j4 + 1]), rb);
+          ra = fmaf(ub[j4].z, __uint_as_float(dr[4 * j4 + 2]), ra);
+          rb = fmaf(ub[j4].w, __uint_as_float(dr[4 * j4 + 3]), rb);
         }
+        racc += ra + rb;
+        float* urow = sU + row * kTileLd + 32 * h;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(urow + 4 * j4) = ub[j4];
+      }
+      if (valid) {
+        int repl = tg / g.N;
+        size_t slot = ((size_t)atom0 + tg) * g.N + (sr - repl * g.N);
+        g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + racc : racc;
+      }
+      // ---- rbf / drbf of the next tile, u / du issued under the reductions of this one
+      if (has_next) {
+        float o[32], od[32];
+        rbf_regs<true>(r_n, g.inv_cutoff, o, od);
+        st_split(lane_addr + XH, lane_addr + XL, o);
+        st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
+        tmem_st_wait();
       }
       fence_before_sync();
       group_sync(grp);
+      if (has_next && gt == 0) {
+        fence_after_sync();
+        issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
+        issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
+        mma_commit(bar);
+      }
       reduce_targets_global(sU, tk, gPb, gt);            // Pbar[tgt] += ubar
       reduce_sources_table(sU, tk, tQb, ld, gt);         // Qbar[src] += ubar
+      pr = pr_n;
+      r = r_n;
+      pm = pm_n;
+      valid = valid_n;
+      pr_n = pr_nn;
+      r_n = r_nn;
+      pm_n = pm_nn;
+      tk = tkn;
+      parity ^= 1;
     }
     group_sync(grp);
     if (SMEM_TABLES) {
