@@ -1,0 +1,311 @@
+"""Drop-in host-side mirror of the reference's model classes for the energy/force hot path.
+
+Same class names, constructor arguments, `set_num_reps`, `forward` signatures, return values and state-dict
+keys as MachineLearning/GNN_Models.py of the reference, but the arithmetic is done by the hand-written
+sm_100a kernels of libgnnis.so through the C ABI (include/gnnis.h); PyTorch only carries tensors, streams
+and autograd plumbing.  There is no CPU / eager fallback: calling `forward` without the CUDA library or
+without a GPU raises.
+
+    reference class (MachineLearning/GNN_Models.py)                 here
+    GNN_GBNeck_2                                     :173           GB-only engine mode
+    GNN3_Multisolvent_embedding                      :326-498       forward(data) -> (energy, forces)
+    GNN3_Multisolvent_embedding_run_multiple         :700-944       forward(positions, solvent_model, dielectric)
+    GNN3_Multisolvent_embedding_run_multiple_Delta   :947-1065      forward(positions)
+    GNN3_Multisolvent_embedding_run_multiple_split   :1068-1083     -> (E_atom[n,1], SA_atom[n,1])
+
+Gradient contract (openmm-torch TorchForce): the returned energy carries a
+torch.autograd.Function node whose backward is `grad_out * dE/dpos`, with dE/dpos = -forces taken from the
+analytic adjoint kernels of the same evaluation; `energy.backward()` therefore fills `positions.grad`
+without a second pass.  `energy_force(positions[R,N,3]) -> (E[R], F[R,N,3])` is the native batched call.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import gbneck
+from .engine import Engine, GnnisError
+
+DEFAULT_UNIQUE_RADII = list(gbneck.DEFAULT_UNIQUE_RADII)   # GNN_Models.py:38 (unsorted on purpose)
+
+
+class _EnergyFunction(torch.autograd.Function):
+    """E[R] = engine(positions); backward: dE/dpos = -F scaled by the incoming per-replica gradient."""
+
+    @staticmethod
+    def forward(ctx, positions, module, delta):
+        eng = module._engine_ready()
+        e, f = eng.energy_force(positions, delta=delta, gb_only=module._gb_only, data_predicate=module._data_predicate)
+        ctx.save_for_backward(f)
+        ctx.in_shape = positions.shape
+        ctx.in_dtype = positions.dtype
+        return e
+
+    @staticmethod
+    def backward(ctx, grad_e):
+        (f,) = ctx.saved_tensors
+        g = -(f * grad_e.to(f.dtype).reshape(-1, 1, 1))
+        return g.reshape(ctx.in_shape).to(ctx.in_dtype), None, None
+
+
+class _Tables(torch.nn.Module):
+    """GBNeck_interaction / GBNeck_energies_no_dielectric buffers (GNN_Layers.py:913-972, 1978-1980)."""
+
+    def __init__(self, d0, m0, with_dielectrics):
+        super().__init__()
+        self.register_buffer("_d0", torch.from_numpy(np.array(d0, dtype=np.float32)))
+        self.register_buffer("_m0", torch.from_numpy(np.array(m0, dtype=np.float32)))
+        if with_dielectrics:
+            self.register_buffer("_soluteDielectric", torch.tensor(1.0))
+            self.register_buffer("_solventDielectric", torch.tensor(78.5))
+
+
+class _Interaction(torch.nn.Module):
+    """Parameter container of IN_layer_all_swish_2pass_tokens (GNN_Layers.py:2143-2246): message1/2, lin1/2."""
+
+    def __init__(self, in_channels, out_channels, hidden, hidden_token, n_rbf=20):
+        super().__init__()
+        self.register_buffer("_FREQUENCIES", math.pi * torch.arange(1, n_rbf + 1, dtype=torch.float32))
+        self.message1 = torch.nn.Linear(in_channels + n_rbf, hidden)
+        self.message2 = torch.nn.Linear(hidden, hidden)
+        self.lin1 = torch.nn.Linear(hidden + hidden, hidden_token)
+        self.lin2 = torch.nn.Linear(hidden_token, out_channels)
+
+
+class GNN3_Multisolvent_embedding(torch.nn.Module):
+    """Data-path model (GNN_Models.py:326-498): forward(data) -> (energy [1,1] or [B,1], forces [n,3]).
+
+    `data` needs `.pos [n,3]`, `.atom_features [n,7]`, `.batch [n]`, `.solvent_model_tensor [n]`,
+    `.solvent_dielectric [n]`.  Graphs of one call must be conformers of ONE molecule (equal atom count and
+    identical atom_features per graph): the engine keeps one parameter table per handle.  Ragged batches
+    (a13 in SURVEY.md §8) are not built yet and raise NotImplementedError."""
+
+    _gb_only = False
+    _data_predicate = True     # torch_cluster.radius_graph semantics for the GNN graph (GNN_Models.py:345-357)
+
+    def __init__(self, fraction=0.1, radius=0.6, max_num_neighbors=10000, parameters=None, device=None,
+                 jittable=False, unique_radii=DEFAULT_UNIQUE_RADII, hidden=64, num_solvents=39, dropout_rate=0.0,
+                 hidden_token=128, scaling_factor=2.0, no_batch=True):
+        super().__init__()
+        if dropout_rate != 0.0:
+            raise NotImplementedError("dropout is a training feature; the inference engine evaluates with p = 0")
+        if hidden != 64 or hidden_token != 128:
+            raise NotImplementedError("libgnnis is specialised for hidden=64, hidden_token=128 (shipped GNN.pt)")
+        self._fraction = float(fraction)
+        self._scaling_factor = float(scaling_factor)
+        self._gnn_radius = float(radius)
+        self._max_num_neighbors = max_num_neighbors
+        self._nobatch = bool(no_batch)
+        self._unique_radii = list(unique_radii)
+        self._device = torch.device(device) if device is not None else torch.device(
+            "cuda" if torch.cuda.is_available() else "cpu")
+        self._gbparameters = None
+        if parameters is not None:
+            self._gbparameters = torch.tensor(np.asarray(parameters, dtype=np.float64), dtype=torch.float32)
+        d0, m0, _ = gbneck.neck_tables(self._unique_radii)
+        self.aggregate_information = _Tables(d0, m0, False)
+        self.calculate_energies = _Tables(d0, m0, True)
+        self.lin = torch.nn.Linear(1, 1)        # present in the checkpoint, unused by forward (GNN_Models.py:62)
+        self.solvent_embedding = torch.nn.Embedding(num_solvents, hidden)
+        self.gamma_embedding = torch.nn.Embedding(num_solvents, 1)
+        self.interaction1 = _Interaction(3 + 3, hidden, hidden, hidden_token)
+        self.interaction2 = _Interaction(hidden + hidden, hidden, hidden, hidden_token)
+        self.interaction3 = _Interaction(hidden + hidden, 2, hidden, hidden_token)
+        self.register_buffer("_num_solvents", torch.tensor(num_solvents, dtype=torch.int32))
+        self.register_buffer("_no_batch", torch.tensor(bool(no_batch), dtype=torch.bool))
+        self._engine: Optional[Engine] = None
+        self._engine_params = None
+        self._weights_dirty = True
+        self._rep_cfg = None
+        self._rep_dirty = True
+
+    # ------------------------------------------------------------------ engine management
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._weights_dirty = True
+        return out
+
+    def _engine_ready(self, parameters=None) -> Engine:
+        if not torch.cuda.is_available():
+            raise GnnisError("no CUDA device: the gnnis hot path has no CPU fallback")
+        dev = self._device if self._device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        params = parameters if parameters is not None else self._gbparameters
+        if params is None:
+            raise ValueError("model was built without `parameters`")
+        p = np.asarray(params.detach().cpu().numpy() if isinstance(params, torch.Tensor) else params, dtype=np.float32)
+        if self._engine is None or self._engine_params is None or not np.array_equal(self._engine_params, p):
+            if self._engine is not None:
+                self._engine.close()
+            sd = None if self._gb_only else {k: v.detach().cpu() for k, v in self.state_dict().items()}
+            self._engine = Engine(p, sd, device=dev, unique_radii=self._unique_radii, fraction=self._fraction,
+                                  scaling_factor=self._scaling_factor, cutoff=0.6 if not self._data_predicate
+                                  else self._gnn_radius)
+            self._engine_params = p.copy()
+            self._weights_dirty = False
+            self._rep_dirty = True
+        elif self._weights_dirty and not self._gb_only:
+            self._engine.load_state_dict({k: v.detach().cpu() for k, v in self.state_dict().items()})
+            self._weights_dirty = False
+        if self._rep_dirty and self._rep_cfg is not None:
+            self._engine.set_replicas(*self._rep_cfg)
+            self._rep_dirty = False
+        return self._engine
+
+    def _set_replica_config(self, num_reps, solvent_models, dielectrics):
+        cfg = (int(num_reps), [int(s) for s in solvent_models], [float(d) for d in dielectrics])
+        if cfg != self._rep_cfg:
+            self._rep_cfg = cfg
+            self._rep_dirty = True
+
+    # ------------------------------------------------------------------ data path
+    def forward(self, data):
+        pos = data.pos
+        n = pos.shape[0]
+        batch = getattr(data, "batch", None)
+        if batch is None:
+            batch = torch.zeros(n, dtype=torch.int64)
+        b = batch.detach().cpu().numpy()
+        n_graphs = int(b.max()) + 1 if n else 0
+        if n_graphs < 1 or n % n_graphs != 0 or not np.array_equal(b, np.repeat(np.arange(n_graphs), n // n_graphs)):
+            raise NotImplementedError("data batches must be R contiguous graphs of equal size (ragged batches: SURVEY a13)")
+        N = n // n_graphs
+        feats = data.atom_features.detach().cpu().to(torch.float32).reshape(n_graphs, N, 7)
+        if not bool((feats == feats[:1]).all()):
+            raise NotImplementedError("all graphs of one call must share atom_features (one molecule per engine handle)")
+        sid = data.solvent_model_tensor.detach().cpu().reshape(n_graphs, N)[:, 0].tolist()
+        die = data.solvent_dielectric.detach().cpu().to(torch.float32).reshape(n_graphs, N)[:, 0].tolist()
+        eng = self._engine_ready(feats[0])
+        self._set_replica_config(n_graphs, sid, die)
+        eng = self._engine_ready(feats[0])
+        e_rep, f = eng.energy_force(pos, gb_only=self._gb_only, data_predicate=self._data_predicate)
+        forces = f.reshape(n, 3)
+        if self._nobatch:
+            energy = e_rep.sum().reshape(1, 1)
+        else:
+            energy = e_rep.reshape(n_graphs, 1)
+        return energy, forces
+
+    # ------------------------------------------------------------------ native batched call
+    def energy_force(self, positions: torch.Tensor, delta: bool = False):
+        """positions [R,N,3] (or [R*N,3]) -> (E[R], F[R,N,3]) on the GPU; no autograd graph."""
+        eng = self._engine_ready()
+        return eng.energy_force(positions, delta=delta, gb_only=self._gb_only, data_predicate=False)
+
+
+class GNN_GBNeck_2(GNN3_Multisolvent_embedding):
+    """Plain GB-Neck2 (GNN_Models.py:173-229): Born radii + GB energy, fixed solvent dielectric 78.5."""
+
+    _gb_only = True
+
+    def forward(self, data):
+        n = data.pos.shape[0]
+        if not hasattr(data, "solvent_dielectric"):
+            data.solvent_dielectric = torch.full((n,), 78.5)
+        if not hasattr(data, "solvent_model_tensor"):
+            data.solvent_model_tensor = torch.zeros(n, dtype=torch.int64)
+        return super().forward(data)
+
+
+class GNN3_Multisolvent_embedding_run_multiple(GNN3_Multisolvent_embedding):
+    """Run model consumed by TorchForce (GNN_Models.py:700-944).
+
+    forward(positions [R*N,3] nm, solvent_model scalar, solvent_dielectric scalar) -> scalar kJ/mol.
+    `solvent_model == -1` uses the per-replica solvents of `set_num_reps`; any other value evaluates every
+    replica in that solvent with the given dielectric (the reference's single-replica override, :780-786)."""
+
+    _data_predicate = False     # eps-distance `r < 0.6` compaction of the all-pairs list (GNN_Models.py:795)
+    _delta = False
+
+    def __init__(self, fraction=0.1, radius=0.6, max_num_neighbors=10000, parameters=None, device=None,
+                 jittable=False, num_reps=1, gbneck_radius=10.0, unique_radii=DEFAULT_UNIQUE_RADII, hidden=64,
+                 solvent_dielectric=[78.5], num_solvents=1, solvent_models=[0], hidden_token=128,
+                 scaling_factor=2.0):
+        super().__init__(fraction=fraction, radius=radius, max_num_neighbors=max_num_neighbors,
+                         parameters=parameters, device=device, jittable=jittable, unique_radii=unique_radii,
+                         hidden=hidden, num_solvents=num_solvents, hidden_token=hidden_token,
+                         scaling_factor=scaling_factor)
+        if parameters is None:
+            raise ValueError("run models need the [N,7] `parameters` table")
+        self.set_num_reps(num_reps, solvent_models, solvent_dielectric)
+
+    def set_num_reps(self, num_reps=1, solvent_models: Sequence[int] = (0,), solvent_dielectric: Sequence[float] = (78.5,)):
+        """GNN_Models.py:741-769.  O(1): no [2, R*N*(N-1)] index is materialised."""
+        if len(solvent_models) < num_reps or len(solvent_dielectric) < num_reps:
+            raise IndexError("need one solvent model and one dielectric per replica")
+        self._num_reps = int(num_reps)
+        self._solvent_models = [int(s) for s in solvent_models[:num_reps]]
+        self._solvent_dielectrics = [float(d) for d in solvent_dielectric[:num_reps]]
+        self._set_replica_config(self._num_reps, self._solvent_models, self._solvent_dielectrics)
+        return 0
+
+    def _select_solvents(self, solvent_model, solvent_dielectric):
+        sm = int(solvent_model) if solvent_model is not None else -1
+        if sm != -1:
+            self._set_replica_config(self._num_reps, [sm] * self._num_reps, [float(solvent_dielectric)] * self._num_reps)
+        else:
+            self._set_replica_config(self._num_reps, self._solvent_models, self._solvent_dielectrics)
+
+    def _energy_per_replica(self, positions, solvent_model, solvent_dielectric):
+        self._select_solvents(solvent_model, solvent_dielectric)
+        n = self._num_reps * self._gbparameters.shape[0]
+        if positions.shape[0] * (positions.shape[1] if positions.dim() == 3 else 1) != n:
+            raise ValueError(f"positions must hold {n} atoms ({self._num_reps} replicas)")
+        return _EnergyFunction.apply(positions, self, self._delta)
+
+    def forward(self, positions, solvent_model=-1, solvent_dielectric=78.5):
+        return self._energy_per_replica(positions, solvent_model, solvent_dielectric).sum()
+
+    def energy_force(self, positions: torch.Tensor, solvent_model=-1, solvent_dielectric=78.5):
+        self._select_solvents(solvent_model, solvent_dielectric)
+        eng = self._engine_ready()
+        return eng.energy_force(positions, delta=self._delta)
+
+    # batched drivers that keep every replica resident on the GPU
+    def minimize(self, positions, grad_tol=1.0, max_iter=500, history=8):
+        self._select_solvents(-1, 78.5)
+        return self._engine_ready().minimize(positions, grad_tol=grad_tol, max_iter=max_iter, history=history,
+                                             delta=self._delta)
+
+    def langevin(self, positions, velocities, masses, n_steps, **kw):
+        self._select_solvents(-1, 78.5)
+        return self._engine_ready().langevin(positions, velocities, masses, n_steps, delta=self._delta, **kw)
+
+
+class GNN3_Multisolvent_embedding_run_multiple_Delta(GNN3_Multisolvent_embedding_run_multiple):
+    """GNN - GBNeck2 difference + SA (GNN_Models.py:947-1065): forward(positions) only."""
+
+    _delta = True
+
+    def forward(self, positions):
+        return self._energy_per_replica(positions, -1, 78.5).sum()
+
+
+class GNN3_Multisolvent_embedding_run_multiple_split(GNN3_Multisolvent_embedding_run_multiple):
+    """Per-atom polar / apolar energies (GNN_Models.py:1068-1083): -> (energies [n,1], sa_energies [n,1])."""
+
+    def forward(self, positions, solvent_model=-1, solvent_dielectric=78.5):
+        self._select_solvents(solvent_model, solvent_dielectric)
+        eng = self._engine_ready()
+        eng.energy_force(positions, forces=False)
+        e, sa = eng.atom_energies()
+        return e.reshape(-1, 1), sa.reshape(-1, 1)
+
+
+def create_gnn_model(parameters, state_dict, num_reps=1, solvent_models: List[int] = (0,),
+                     solvent_dielectric: List[float] = (78.5,), cls=GNN3_Multisolvent_embedding_run_multiple,
+                     device=None, fraction=0.1, scaling_factor=2.0):
+    """The model-building half of Simulation/helper_functions.py:create_gnn_model / create_gnn_sim (:750-790):
+    instantiate a run model for `num_reps` replicas, load the checkpoint's state dict, freeze it."""
+    num_solvents = int(state_dict["solvent_embedding.weight"].shape[0])
+    model = cls(fraction=fraction, radius=0.6, max_num_neighbors=10000, parameters=parameters, device=device,
+                num_reps=num_reps, unique_radii=DEFAULT_UNIQUE_RADII, hidden=64,
+                solvent_dielectric=list(solvent_dielectric), num_solvents=num_solvents,
+                solvent_models=list(solvent_models), hidden_token=128, scaling_factor=scaling_factor)
+    model.load_state_dict(state_dict)
+    model.eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model

@@ -133,6 +133,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
   const bool gb_only = flags & GNNIS_FLAG_GB_ONLY;
   const bool want_grad = !(flags & GNNIS_FLAG_NO_FORCES);
   const int delta = (flags & GNNIS_FLAG_DELTA) ? 1 : 0;
+  const int predicate = (flags & GNNIS_FLAG_DATA_PREDICATE) ? 1 : 0;
   if (check_ready(c, !gb_only)) return -1;
   if (want_grad && !force) {
     c->err = "force_dev is NULL but GNNIS_FLAG_NO_FORCES is not set";
@@ -149,9 +150,9 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
   if (tm) tm->mark(kStNeighborBorn);
-  if (launch_born_count(c, pos, 0, st)) return -1;
+  if (launch_born_count(c, pos, predicate, st)) return -1;
   if (!gb_only) {
-    if (launch_fill_edges(c, pos, 0, c->row_ptr, nullptr, c->pair, c->r_e, c->edge_cap, st)) return -1;
+    if (launch_fill_edges(c, pos, predicate, c->row_ptr, nullptr, c->pair, c->r_e, c->edge_cap, st)) return -1;
     if (want_grad && launch_tile_perm(c, st)) return -1;
     if (tm) tm->mark(kStNodeFwd);
     if (launch_node_pre1(c, st)) return -1;

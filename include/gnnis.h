@@ -29,6 +29,8 @@ typedef struct gnnis_ctx* gnnis_handle;
 #define GNNIS_FLAG_NO_FORCES 0x2u  /* energy only (skips the adjoint pass)                                */
 #define GNNIS_FLAG_GB_ONLY 0x4u    /* plain GB-Neck2 (GNN_GBNeck_2, GNN_Models.py:173): B' = B, no SA term */
 #define GNNIS_FLAG_MLP_BF16 0x8u   /* reserved: bf16-operand edge MLP (not built; returns -3)             */
+#define GNNIS_FLAG_DATA_PREDICATE 0x20u /* GNN graph by torch_cluster.radius_graph semantics, sum((x_i-x_j)^2) < r^2
+                                      (data path, GNN_Models.py:345-357), instead of eps-distance r < cutoff */
 #define GNNIS_FLAG_MLP_CUDA_CORES 0x10u /* force the fp32 CUDA-core edge kernels instead of the default
                                       tcgen05 tensor-core kernels (3xTF32, fp32-accurate)                 */
 

@@ -227,7 +227,7 @@ def gb_energy(Bq, src, tgt, r, diel):
 
 
 def evaluate(params, pos, solvent_ids, dielectrics, state_dict, *, dtype=torch.float32, delta=False,
-             fraction=0.1, scaling_factor=2.0, forces=True, keep_intermediates=False):
+             fraction=0.1, scaling_factor=2.0, forces=True, keep_intermediates=False, predicate="run"):
     """One batched evaluation, the oracle of `gnnis_energy_force`.
 
     params [N,7] (any float), pos [R,N,3], solvent_ids [R] int, dielectrics [R] float.
@@ -245,7 +245,12 @@ def evaluate(params, pos, solvent_ids, dielectrics, state_dict, *, dtype=torch.f
     ei = all_pairs_index(N, R)
     src, tgt = ei[0], ei[1]
     r = eps_distance(flat, src, tgt)
-    gnn = r < 0.6
+    if predicate == "run":      # run models: boolean compaction of the eps-distance (GNN_Models.py:795)
+        gnn = r < 0.6
+    else:                       # data model: torch_cluster.radius_graph, strict < on the squared fp32 distance
+        dd = (flat.detach()[tgt] - flat.detach()[src]).to(torch.float32)
+        sq = dd * dd
+        gnn = ((sq[:, 0] + sq[:, 1]) + sq[:, 2]) < torch.tensor(0.6, dtype=torch.float32) ** 2
     g_src, g_tgt, g_r = src[gnn], tgt[gnn], r[gnn].unsqueeze(1)
 
     d0 = W["aggregate_information._d0"]
