@@ -18,6 +18,8 @@ int launch_edge_fwd(Ctx*, int, cudaStream_t);
 int launch_tile_perm(Ctx*, cudaStream_t);
 int launch_edge_fwd_tc(Ctx*, int, cudaStream_t);
 int launch_edge_bwd_tc(Ctx*, int, int, cudaStream_t);
+int launch_edge_fwd_ws(Ctx*, int, cudaStream_t);
+int launch_edge_bwd_ws(Ctx*, int, int, cudaStream_t);
 int launch_umma_selftest(Ctx*, const float*, const float*, float*, int, int, cudaStream_t);
 bool tc_path_fits(const Ctx*);
 int launch_edge_bwd(Ctx*, int, int, cudaStream_t);
@@ -158,7 +160,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     if (launch_node_pre1(c, st)) return -1;
     for (int l = 0; l < 3; ++l) {
       if (tm) tm->mark(kStEdgeFwd);
-      if (tc_fwd ? launch_edge_fwd_tc(c, l, st) : launch_edge_fwd(c, l, st)) return -1;
+      if (tc_fwd ? ((c->tc_mask & 4) ? launch_edge_fwd_ws(c, l, st) : launch_edge_fwd_tc(c, l, st)) : launch_edge_fwd(c, l, st)) return -1;
       if (tm) tm->mark(kStNodeFwd);
       if (launch_node_fwd(c, l, st)) return -1;
     }
@@ -176,7 +178,8 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
         if (tm) tm->mark(kStNodeBwd);
         if (launch_node_bwd(c, l, st)) return -1;
         if (tm) tm->mark(kStEdgeBwd);
-        if (tc_bwd ? launch_edge_bwd_tc(c, l, l == 2 ? 0 : 1, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
+        if (tc_bwd ? ((c->tc_mask & 8) ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, st) : launch_edge_bwd_tc(c, l, l == 2 ? 0 : 1, st))
+                 : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
       }
       if (tm) tm->mark(kStNodeBwd);
       if (launch_node_pre1_bwd(c, st)) return -1;

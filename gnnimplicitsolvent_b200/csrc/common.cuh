@@ -62,7 +62,7 @@ struct Ctx {
   std::string err;
   int64_t launches = 0;
   int num_sms = 148;
-  int tc_mask = 3;   // bit0: forward edge kernel on tcgen05, bit1: adjoint edge kernel on tcgen05
+  int tc_mask = 15;  // bit0 / bit1: forward / adjoint edge kernel on tcgen05; bit2 / bit3: warp-specialised variant
   // model
   bool have_weights = false;
   int S = 0;  // num_solvents

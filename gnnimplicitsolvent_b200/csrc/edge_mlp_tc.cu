@@ -943,6 +943,750 @@ int launch_edge_bwd_tc(Ctx* c, int l, int rbar_accumulate, cudaStream_t st) {
   return 0;
 }
 
+// ================================================================================================================
+// Warp-specialised variant (default): 2 groups x 8 epilogue warps + 1 MMA-issuer warp per CTA.
+//
+// A thread is (edge row, 32-column half): warps 0-3 of a group take channels 0..31, warps 4-7 channels 32..63 of
+// the same 128 rows, so 16 epilogue warps share the four schedulers of the SM instead of 8.  All tcgen05.mma are
+// issued by lane 0 of warp 16, which polls (mbarrier.test_wait) the two groups in turn; the epilogue warps hand
+// operands over with mbarrier arrivals and never block on the issue itself:
+//     u_ok   (12 arrivals) : rbf operand of the next tile written (4 warps) + accumulators drained (8 warps)
+//     a_full ( 8 arrivals) : A operand (v, wbar) written by all warps
+//     d_full ( tcgen05.commit ) : products of the last issue are in TMEM
+// Only two group-wide named barriers per tile remain, both around the shared-memory tile of the reduction.
+constexpr int kWsGroupThreads = 256;
+constexpr int kWsThreads = kGroups * kWsGroupThreads + 32;
+
+struct WsBars {
+  uint64_t d_full[kGroups], a_full[kGroups], u_ok[kGroups];
+};
+
+__device__ __forceinline__ void ws_group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
+// one arrival per warp, after the warp's outstanding TMEM traffic has been waited for by the caller
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void st_split16(uint32_t t_hi, uint32_t t_lo, const float (&x)[16]) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split_tf32(x[j], h[j], l[j]);
+  tmem_st16(t_hi, h);
+  tmem_st16(t_lo, l);
+}
+__device__ __forceinline__ void copy_rows_n(float* __restrict__ dst, int ld_dst, const float* __restrict__ src,
+                                            int ld_src, int nrows, int t0, int nthreads) {
+  for (int t = t0; t < nrows * 16; t += nthreads) {
+    int r = t >> 4, c4 = t & 15;
+    *reinterpret_cast<float4*>(dst + (size_t)r * ld_dst + c4 * 4) =
+        *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c4 * 4);
+  }
+}
+__device__ __forceinline__ void zero_rows_n(float* __restrict__ dst, int ld_dst, int nrows, int t0, int nthreads) {
+  for (int t = t0; t < nrows * 16; t += nthreads) {
+    int r = t >> 4, c4 = t & 15;
+    *reinterpret_cast<float4*>(dst + (size_t)r * ld_dst + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// target-segment sums to global rows, 256 threads: 32 column pairs x 8 segment slots (see reduce_targets_global)
+__device__ __forceinline__ void reduce_targets_global_256(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
+                                                          float* __restrict__ out, int gt) {
+  const int cp = gt & 31, slot = gt >> 5;
+  const int nseg = tk->n_seg_t;
+  for (int s = slot; s < nseg; s += 8) {
+    const int p0 = tk->seg_t[s], p1 = tk->seg_t[s + 1];
+    float2 run = make_float2(0.f, 0.f), run2 = make_float2(0.f, 0.f);
+    int p = p0;
+#pragma unroll 2
+    for (; p + 1 < p1; p += 2) {
+      const float2 v = *reinterpret_cast<const float2*>(sX + p * kTileLd + 2 * cp);
+      const float2 w = *reinterpret_cast<const float2*>(sX + (p + 1) * kTileLd + 2 * cp);
+      run.x += v.x;
+      run.y += v.y;
+      run2.x += w.x;
+      run2.y += w.y;
+    }
+    if (p < p1) {
+      const float2 v = *reinterpret_cast<const float2*>(sX + p * kTileLd + 2 * cp);
+      run.x += v.x;
+      run.y += v.y;
+    }
+    run.x += run2.x;
+    run.y += run2.y;
+    float2* dst = reinterpret_cast<float2*>(out + (size_t)tk->tgt[p0] * 64 + 2 * cp);
+    if (s == 0 && tk->cont_prev) {
+      float2 t = *dst;
+      run.x += t.x;
+      run.y += t.y;
+    }
+    *dst = run;
+  }
+}
+// source-segment sums into table rows, 256 threads: 16 column quads x 16 segment slots
+__device__ __forceinline__ void reduce_sources_table_256(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
+                                                         float* __restrict__ table, int ld, int gt) {
+  const int cq = gt & 15, slot = gt >> 4;
+  const int nseg = tk->n_seg_s;
+  for (int s = slot; s < nseg; s += 16) {
+    const int p0 = tk->seg_s[s], p1 = tk->seg_s[s + 1];
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0; p < p1; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + (int)tk->perm[p] * kTileLd + 4 * cq);
+      run.x += v.x;
+      run.y += v.y;
+      run.z += v.z;
+      run.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(table + (size_t)tk->src[tk->perm[p0]] * ld + 4 * cq);
+    float4 t = *dst;
+    t.x += run.x;
+    t.y += run.y;
+    t.z += run.z;
+    t.w += run.w;
+    *dst = t;
+  }
+}
+
+// issuer-side walk over the units of one group (must visit exactly the tiles the epilogue warps visit)
+struct IssueState {
+  int unit, t0, e_end, stage;
+  uint32_t ph_a, ph_u, cur;
+  bool done;
+};
+__device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs& g) {
+  for (;;) {
+    if (x.unit >= g.n_units) {
+      x.done = true;
+      return;
+    }
+    const int rep0 = x.unit * g.G, rep1 = min(g.R, rep0 + g.G);
+    const int e_begin = g.row_ptr[rep0 * g.N], e_end = g.row_ptr[rep1 * g.N];
+    if (e_begin < e_end) {
+      x.t0 = e_begin;
+      x.e_end = e_end;
+      return;
+    }
+    x.unit += gridDim.x * kGroups;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward (ws)
+template <bool SMEM_TABLES>
+__global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+  extern __shared__ uint8_t smraw[];
+  __shared__ WsBars bars;
+  __shared__ uint32_t tmem_slot;
+  uint32_t base = smem_u32(smraw);
+  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
+  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
+  float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) {
+      mbar_init(&bars.d_full[i], 1);
+      mbar_init(&bars.a_full[i], 8);
+      mbar_init(&bars.u_ok[i], 12);
+    }
+  }
+  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);
+  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);
+  if (tid < 64) sb2[tid] = g.b2[tid];
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  constexpr uint32_t VH = 128, VL = 192;
+  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+
+  if (warp == 2 * 8) {
+    // ===================================== MMA issuer =====================================
+    // the whole warp walks the state machine (converged); one elected lane issues
+    {
+      const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
+      IssueState st[kGroups];
+      for (int i = 0; i < kGroups; ++i) {
+        st[i] = IssueState{(int)blockIdx.x * kGroups + i, 0, 0, 0, 0u, 0u, 0u, false};
+        issue_next_unit(st[i], g);
+      }
+      while (!(st[0].done && st[1].done)) {
+#pragma unroll
+        for (int i = 0; i < kGroups; ++i) {
+          IssueState& x = st[i];
+          if (x.done) continue;
+          const uint32_t tm = tmem_slot + (uint32_t)i * 256u;
+          if (x.stage == 0) {
+            if (!mbar_test(&bars.u_ok[i], x.ph_u)) continue;
+            x.ph_u ^= 1u;
+            fence_after_sync();
+            if (elect_one()) {
+              issue_gemm_3xtf32<0, 3>(tm + x.cur, tm + (x.cur ^ 64u), tm + (x.cur ^ 64u) + 32, aWrH, aWrL, 64, idesc64, 0u);
+              mma_commit(&bars.d_full[i]);
+            }
+            __syncwarp();
+            x.stage = 1;
+          } else {
+            if (!mbar_test(&bars.a_full[i], x.ph_a)) continue;
+            x.ph_a ^= 1u;
+            fence_after_sync();
+            if (elect_one()) {
+              issue_gemm_3xtf32<0, 8>(tm + (x.cur ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
+              mma_commit(&bars.d_full[i]);
+            }
+            __syncwarp();
+            x.stage = 0;
+            x.cur ^= 64u;
+            x.t0 += kTileE;
+            if (x.t0 >= x.e_end) {
+              x.unit += gridDim.x * kGroups;
+              issue_next_unit(x, g);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue warps =====================================
+    const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
+    uint8_t* gsm = sm + kFwdWeights + 256 + (size_t)grp * grp_bytes;
+    float* sZ = reinterpret_cast<float*>(gsm + kGrpX);
+    TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
+    float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
+    const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
+    const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
+    uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp];
+    uint32_t ph_d = 0, ph_a = 0, cur = 0;
+    int parity = 0;
+
+    for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
+      const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
+      const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
+      const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
+      const float* gP = g.P + (size_t)atom0 * 64;
+      float* gA = g.a_out + (size_t)atom0 * 64;
+      const float* tQ;
+      int ld;
+      if (SMEM_TABLES) {
+        ld = kTabLd;
+        copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
+        tQ = sTab;
+      } else {
+        ld = 64;
+        tQ = g.Q + (size_t)atom0 * 64;
+      }
+      zero_rows_n(gA, 64, natoms, gt, kWsGroupThreads);
+      if (e_begin >= e_end) {
+        ws_group_sync(grp);
+        continue;
+      }
+      // ---- prologue: keys + radial basis of the first tile; edge data of the second tile in flight
+      uint32_t pr = 0u, pr_n = 0u;
+      float r = 0.3f, r_n = 0.3f;
+      bool valid = e_begin + row < e_end;
+      if (valid) {
+        pr = g.pair[e_begin + row];
+        if (ch == 0) r = g.r_e[e_begin + row];
+      }
+      if (e_begin + kTileE + row < e_end) {
+        pr_n = g.pair[e_begin + kTileE + row];
+        if (ch == 0) r_n = g.r_e[e_begin + kTileE + row];
+      }
+      TileKeys* tk = keys + parity;
+      if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
+      prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
+      warp_arrive(u_ok, lane);                       // accumulators are free
+      if (ch == 0) {
+        float o[32], od[32];
+        rbf_regs<false>(r, g.inv_cutoff, o, od);
+        st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
+        tmem_st_wait();
+        warp_arrive(u_ok, lane);
+      }
+      ws_group_sync(grp);                            // tables + keys of the first tile visible
+
+      for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
+        const bool has_next = t0 + kTileE < e_end;
+        const int tgc = valid ? (int)(pr >> 16) : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
+        if (w8 == 4) {
+          const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
+          if (lane == 0) {
+            tk->n_seg_t = ns;
+            tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
+          }
+        }
+        mbar_wait(d_full, ph_d);
+        __syncwarp();
+        ph_d ^= 1u;
+        fence_after_sync();
+        // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM (this thread's 32 channels, two chunks of 16)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = 32 * ch + 16 * c;
+          uint32_t ur[16];
+          tmem_ld16(lane_addr + cur + col0, ur);
+          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + col0);
+          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
+          float4 p[4], q[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            p[j4] = __ldg(pp + j4);
+            q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+          }
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            v[4 * j4 + 0] = silu_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x));
+            v[4 * j4 + 1] = silu_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y));
+            v[4 * j4 + 2] = silu_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z));
+            v[4 * j4 + 3] = silu_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
+          }
+          st_split16(lane_addr + VH + col0, lane_addr + VL + col0, v);
+        }
+        tmem_st_wait();
+        warp_arrive(a_full, lane);
+        // ---- look ahead: keys / radial basis of the next tile while w runs
+        TileKeys* tkn = keys + (parity ^ 1);
+        bool valid_n = false;
+        uint32_t pr_nn = 0u;
+        float r_nn = 0.3f;
+        if (has_next) {
+          valid_n = t0 + kTileE + row < e_end;
+          if (ch == 0) tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
+          prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
+          if (t0 + 2 * kTileE + row < e_end) {
+            pr_nn = g.pair[t0 + 2 * kTileE + row];
+            if (ch == 0) r_nn = g.r_e[t0 + 2 * kTileE + row];
+          }
+          if (ch == 0) {
+            float o[32], od[32];
+            rbf_regs<false>(r_n, g.inv_cutoff, o, od);
+            mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
+            __syncwarp();
+            st_split(lane_addr + cur, lane_addr + cur + 32, o);
+            tmem_st_wait();
+            warp_arrive(u_ok, lane);
+          }
+        }
+        ph_a ^= 1u;
+        mbar_wait(d_full, ph_d);
+        __syncwarp();
+        ph_d ^= 1u;
+        fence_after_sync();
+        // ---- w -> registers; the accumulator may then be overwritten by u of the next tile
+        uint32_t wr[32];
+        tmem_ld32(lane_addr + (cur ^ 64u) + 32 * ch, wr);
+        tmem_ld_wait();
+        if (has_next) warp_arrive(u_ok, lane);
+        ws_group_sync(grp);                          // (A) the reduction of the previous tile is complete
+        {
+          const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * ch);
+          float* zrow = sZ + row * kTileLd + 32 * ch;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = bb[j4];
+            float4 z;
+            z.x = silu_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x);
+            z.y = silu_fast(__uint_as_float(wr[4 * j4 + 1]) + b.y);
+            z.z = silu_fast(__uint_as_float(wr[4 * j4 + 2]) + b.z);
+            z.w = silu_fast(__uint_as_float(wr[4 * j4 + 3]) + b.w);
+            *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
+          }
+        }
+        ws_group_sync(grp);                          // (B) tile complete
+        reduce_targets_global_256(sZ, tk, gA, gt);
+        pr = pr_n;
+        r = r_n;
+        valid = valid_n;
+        pr_n = pr_nn;
+        r_n = r_nn;
+        tk = tkn;
+        parity ^= 1;
+        cur ^= 64u;
+      }
+      ws_group_sync(grp);   // all rows of the unit written before its tables are replaced
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- adjoint (ws)
+template <bool SMEM_TABLES>
+__global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+  extern __shared__ uint8_t smraw[];
+  __shared__ WsBars bars;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float sPart[kGroups][kTileE];
+  uint32_t base = smem_u32(smraw);
+  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
+  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
+  uint8_t *sW2tH = sm + 49152, *sW2tL = sm + 65536;
+  float* sb2 = reinterpret_cast<float*>(sm + kBwdWeights);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) {
+      mbar_init(&bars.d_full[i], 1);
+      mbar_init(&bars.a_full[i], 8);
+      mbar_init(&bars.u_ok[i], 12);
+    }
+  }
+  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);
+  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);
+  stage_b_operand(sW2tH, sW2tL, g.W2_t, 64, 64, 64, 64, 64, 1);
+  if (tid < 64) sb2[tid] = g.b2[tid];
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
+  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+
+  if (warp == 2 * 8) {
+    {
+      const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
+      const uint32_t aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
+      IssueState st[kGroups];
+      for (int i = 0; i < kGroups; ++i) {
+        st[i] = IssueState{(int)blockIdx.x * kGroups + i, 0, 0, 0, 0u, 0u, 0u, false};
+        issue_next_unit(st[i], g);
+      }
+      while (!(st[0].done && st[1].done)) {
+#pragma unroll
+        for (int i = 0; i < kGroups; ++i) {
+          IssueState& x = st[i];
+          if (x.done) continue;
+          const uint32_t tm = tmem_slot + (uint32_t)i * 256u;
+          if (x.stage == 0) {          // u = rbf . Wr^T ; du = drbf . Wr^T
+            if (!mbar_test(&bars.u_ok[i], x.ph_u)) continue;
+            x.ph_u ^= 1u;
+            fence_after_sync();
+            if (elect_one()) {
+              issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
+              issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
+              mma_commit(&bars.d_full[i]);
+            }
+            __syncwarp();
+            x.stage = 1;
+          } else {
+            if (!mbar_test(&bars.a_full[i], x.ph_a)) continue;
+            x.ph_a ^= 1u;
+            fence_after_sync();
+            if (x.stage == 1) {        // w = v . W2^T
+              if (elect_one()) {
+                issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2H, aW2L, 64, idesc64, 0u);
+                mma_commit(&bars.d_full[i]);
+              }
+              __syncwarp();
+              x.stage = 2;
+            } else {                   // vbar = wbar . W2
+              if (elect_one()) {
+                issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2tH, aW2tL, 64, idesc64, 0u);
+                mma_commit(&bars.d_full[i]);
+              }
+              __syncwarp();
+              x.stage = 0;
+              x.t0 += kTileE;
+              if (x.t0 >= x.e_end) {
+                x.unit += gridDim.x * kGroups;
+                issue_next_unit(x, g);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
+    uint8_t* gsm = sm + kBwdWeights + 256 + (size_t)grp * grp_bytes;
+    float* sU = reinterpret_cast<float*>(gsm + kGrpX);
+    TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
+    float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
+    const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
+    const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
+    uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp];
+    uint32_t ph_d = 0;
+    int parity = 0;
+
+    for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
+      const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
+      const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
+      const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
+      const float* gP = g.P + (size_t)atom0 * 64;
+      const float* gAb = g.abar + (size_t)atom0 * 64;
+      float* gPb = g.Pbar + (size_t)atom0 * 64;
+      const float* tQ;
+      float* tQb;
+      int ld;
+      if (SMEM_TABLES) {
+        ld = kTabLd;
+        tQb = sTab + g.unit_atoms * kTabLd;
+        copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
+        tQ = sTab;
+      } else {
+        ld = 64;
+        tQ = g.Q + (size_t)atom0 * 64;
+        tQb = g.Qbar + (size_t)atom0 * 64;
+      }
+      zero_rows_n(gPb, 64, natoms, gt, kWsGroupThreads);
+      zero_rows_n(tQb, ld, natoms, gt, kWsGroupThreads);
+      if (e_begin >= e_end) {
+        ws_group_sync(grp);
+        if (SMEM_TABLES) {
+          copy_rows_n(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt, kWsGroupThreads);
+          ws_group_sync(grp);
+        }
+        continue;
+      }
+      uint32_t pr = 0u, pr_n = 0u;
+      float r = 0.3f, r_n = 0.3f;
+      uint8_t pm = (uint8_t)row, pm_n = (uint8_t)row;
+      bool valid = e_begin + row < e_end;
+      if (valid) {
+        pr = g.pair[e_begin + row];
+        if (ch == 0) {
+          r = g.r_e[e_begin + row];
+          pm = g.perm[e_begin + row];
+        }
+      }
+      if (e_begin + kTileE + row < e_end) {
+        pr_n = g.pair[e_begin + kTileE + row];
+        if (ch == 0) {
+          r_n = g.r_e[e_begin + kTileE + row];
+          pm_n = g.perm[e_begin + kTileE + row];
+        }
+      }
+      TileKeys* tk = keys + parity;
+      if (ch == 0) {
+        tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
+        tk->src[row] = valid ? (int)(pr & 0xFFFFu) : -1;
+        tk->perm[row] = pm;
+      }
+      {
+        const size_t t_ = (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch;
+        prefetch_l1(gP + t_);
+        prefetch_l1(gAb + t_);
+      }
+      warp_arrive(u_ok, lane);
+      if (ch == 0) {
+        float o[32], od[32];
+        rbf_regs<true>(r, g.inv_cutoff, o, od);
+        st_split(lane_addr + XH, lane_addr + XL, o);
+        st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
+        tmem_st_wait();
+        warp_arrive(u_ok, lane);
+      }
+      ws_group_sync(grp);
+
+      for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
+        const bool has_next = t0 + kTileE < e_end;
+        const int tg = valid ? (int)(pr >> 16) : -1, tgc = valid ? tg : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
+        if (w8 == 4) {
+          const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
+          if (lane == 0) {
+            tk->n_seg_t = ns;
+            tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
+          }
+        } else if (w8 == 5) {
+          const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, min(kTileE, e_end - t0), lane);
+          if (lane == 0) tk->n_seg_s = ns;
+        }
+        mbar_wait(d_full, ph_d);
+        __syncwarp();
+        ph_d ^= 1u;
+        fence_after_sync();
+        // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM ; keep silu'(u)
+        float dsu[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = 32 * ch + 16 * c;
+          uint32_t ur[16];
+          tmem_ld16(lane_addr + ACC + col0, ur);
+          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + col0);
+          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
+          float4 p[4], q[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            p[j4] = __ldg(pp + j4);
+            q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+          }
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            silu_fd_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x), v[4 * j4 + 0], dsu[16 * c + 4 * j4 + 0]);
+            silu_fd_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y), v[4 * j4 + 1], dsu[16 * c + 4 * j4 + 1]);
+            silu_fd_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z), v[4 * j4 + 2], dsu[16 * c + 4 * j4 + 2]);
+            silu_fd_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w), v[4 * j4 + 3], dsu[16 * c + 4 * j4 + 3]);
+          }
+          st_split16(lane_addr + XH + col0, lane_addr + XL + col0, v);
+        }
+        tmem_st_wait();
+        warp_arrive(a_full, lane);
+        mbar_wait(d_full, ph_d);
+        __syncwarp();
+        ph_d ^= 1u;
+        fence_after_sync();
+        // ---- wbar = abar[tgt] * silu'(w + b2) -> TMEM
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = 32 * ch + 16 * c;
+          uint32_t wr[16];
+          tmem_ld16(lane_addr + ACC + col0, wr);
+          const float4* ab = reinterpret_cast<const float4*>(gAb + (size_t)tgc * 64 + col0);
+          const float4* bb = reinterpret_cast<const float4*>(sb2 + col0);
+          float4 a[4], b[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            a[j4] = __ldg(ab + j4);
+            b[j4] = bb[j4];
+          }
+          tmem_ld_wait();
+          float wb[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            wb[4 * j4 + 0] = a[j4].x * silu_d_fast(__uint_as_float(wr[4 * j4 + 0]) + b[j4].x);
+            wb[4 * j4 + 1] = a[j4].y * silu_d_fast(__uint_as_float(wr[4 * j4 + 1]) + b[j4].y);
+            wb[4 * j4 + 2] = a[j4].z * silu_d_fast(__uint_as_float(wr[4 * j4 + 2]) + b[j4].z);
+            wb[4 * j4 + 3] = a[j4].w * silu_d_fast(__uint_as_float(wr[4 * j4 + 3]) + b[j4].w);
+          }
+          st_split16(lane_addr + XH + col0, lane_addr + XL + col0, wb);
+        }
+        tmem_st_wait();
+        warp_arrive(a_full, lane);
+        // ---- edge data of the following tiles while vbar runs
+        TileKeys* tkn = keys + (parity ^ 1);
+        bool valid_n = false;
+        uint32_t pr_nn = 0u;
+        float r_nn = 0.3f;
+        uint8_t pm_nn = (uint8_t)row;
+        if (has_next) {
+          valid_n = t0 + kTileE + row < e_end;
+          if (ch == 0) {
+            tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
+            tkn->src[row] = valid_n ? (int)(pr_n & 0xFFFFu) : -1;
+            tkn->perm[row] = valid_n ? pm_n : (uint8_t)row;
+          }
+          const size_t t_ = (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch;
+          prefetch_l1(gP + t_);
+          prefetch_l1(gAb + t_);
+          if (t0 + 2 * kTileE + row < e_end) {
+            pr_nn = g.pair[t0 + 2 * kTileE + row];
+            if (ch == 0) {
+              r_nn = g.r_e[t0 + 2 * kTileE + row];
+              pm_nn = g.perm[t0 + 2 * kTileE + row];
+            }
+          }
+        }
+        mbar_wait(d_full, ph_d);
+        __syncwarp();
+        ph_d ^= 1u;
+        fence_after_sync();
+        ws_group_sync(grp);                          // (A) reductions of the previous tile are complete
+        // ---- ubar = vbar * silu'(u) -> smem tile ; rbar = ubar . du (this thread's 32 channels)
+        float racc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = 32 * ch + 16 * c;
+          uint32_t vr[16], dr[16];
+          tmem_ld16(lane_addr + ACC + col0, vr);
+          tmem_ld16(lane_addr + DU + col0, dr);
+          tmem_ld_wait();
+          float* urow = sU + row * kTileLd + col0;
+          float ra = 0.0f, rb = 0.0f;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            float4 ub;
+            ub.x = __uint_as_float(vr[4 * j4 + 0]) * dsu[16 * c + 4 * j4 + 0];
+            ub.y = __uint_as_float(vr[4 * j4 + 1]) * dsu[16 * c + 4 * j4 + 1];
+            ub.z = __uint_as_float(vr[4 * j4 + 2]) * dsu[16 * c + 4 * j4 + 2];
+            ub.w = __uint_as_float(vr[4 * j4 + 3]) * dsu[16 * c + 4 * j4 + 3];
+            ra = fmaf(ub.x, __uint_as_float(dr[4 * j4 + 0]), ra);
+            rb = fmaf(ub.y, __uint_as_float(dr[4 * j4 + 1]), rb);
+            ra = fmaf(ub.z, __uint_as_float(dr[4 * j4 + 2]), ra);
+            rb = fmaf(ub.w, __uint_as_float(dr[4 * j4 + 3]), rb);
+            *reinterpret_cast<float4*>(urow + 4 * j4) = ub;
+          }
+          racc += ra + rb;
+        }
+        if (has_next) warp_arrive(u_ok, lane);       // ACC / DU drained
+        if (ch == 1) sPart[grp][row] = racc;
+        if (has_next && ch == 0) {
+          float o[32], od[32];
+          rbf_regs<true>(r_n, g.inv_cutoff, o, od);
+          st_split(lane_addr + XH, lane_addr + XL, o);
+          st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
+          tmem_st_wait();
+          warp_arrive(u_ok, lane);
+        }
+        ws_group_sync(grp);                          // (B) tile complete
+        if (ch == 0 && valid) {
+          const float rs = racc + sPart[grp][row];   // channels 0..31 + 32..63
+          int repl = tg / g.N;
+          size_t slot = ((size_t)atom0 + tg) * g.N + (sr - repl * g.N);
+          g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + rs : rs;
+        }
+        reduce_targets_global_256(sU, tk, gPb, gt);          // Pbar[tgt] += ubar
+        reduce_sources_table_256(sU, tk, tQb, ld, gt);       // Qbar[src] += ubar
+        pr = pr_n;
+        r = r_n;
+        pm = pm_n;
+        valid = valid_n;
+        pr_n = pr_nn;
+        r_n = r_nn;
+        pm_n = pm_nn;
+        tk = tkn;
+        parity ^= 1;
+      }
+      ws_group_sync(grp);
+      if (SMEM_TABLES) {
+        copy_rows_n(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt, kWsGroupThreads);
+        ws_group_sync(grp);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
+int launch_edge_fwd_ws(Ctx* c, int l, cudaStream_t st) {
+  EdgeTcArgs g = make_tc_args(c, l);
+  size_t smem = fwd_tc_smem(c);
+  uint32_t gb = (uint32_t)group_bytes(c, 1);
+  if (c->smem_tables) {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_ws_kernel<true><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+  } else {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_ws_kernel<false><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+  }
+  GNNIS_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, cudaStream_t st) {
+  EdgeTcArgs g = make_tc_args(c, l);
+  g.rbar_accumulate = rbar_accumulate;
+  size_t smem = bwd_tc_smem(c);
+  uint32_t gb = (uint32_t)group_bytes(c, 2);
+  if (c->smem_tables) {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_bwd_ws_kernel<true><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+  } else {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_bwd_ws_kernel<false><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+  }
+  GNNIS_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_umma_selftest(Ctx* c, const float* A, const float* B, float* D, int K, int N, cudaStream_t st) {
   size_t smem = 32768 + 1024;
   GNNIS_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
