@@ -990,61 +990,104 @@ __device__ __forceinline__ void zero_rows_n(float* __restrict__ dst, int ld_dst,
   }
 }
 
-// target-segment sums to global rows, 256 threads: 32 column pairs x 8 segment slots (see reduce_targets_global)
+// target-segment sums to global rows, 256 threads = 8 warps.  Warp w takes segments w, w+8, ...; its lanes are
+// 16 column quads x 2 row halves (first / second half of the segment), combined in fixed order through one shuffle.
 __device__ __forceinline__ void reduce_targets_global_256(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
                                                           float* __restrict__ out, int gt) {
-  const int cp = gt & 31, slot = gt >> 5;
+  const int lane = gt & 31, cq = lane & 15, half = lane >> 4, w = gt >> 5;
   const int nseg = tk->n_seg_t;
-  for (int s = slot; s < nseg; s += 8) {
+  for (int s = w; s < nseg; s += 8) {
     const int p0 = tk->seg_t[s], p1 = tk->seg_t[s + 1];
-    float2 run = make_float2(0.f, 0.f), run2 = make_float2(0.f, 0.f);
-    int p = p0;
+    const int mid = p0 + ((p1 - p0 + 1) >> 1);
+    const int a0 = half ? mid : p0, a1 = half ? p1 : mid;
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f), run2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = a0;
 #pragma unroll 2
-    for (; p + 1 < p1; p += 2) {
-      const float2 v = *reinterpret_cast<const float2*>(sX + p * kTileLd + 2 * cp);
-      const float2 w = *reinterpret_cast<const float2*>(sX + (p + 1) * kTileLd + 2 * cp);
+    for (; p + 1 < a1; p += 2) {   // two interleaved partial sums, fixed order
+      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
+      const float4 u = *reinterpret_cast<const float4*>(sX + (p + 1) * kTileLd + 4 * cq);
       run.x += v.x;
       run.y += v.y;
-      run2.x += w.x;
-      run2.y += w.y;
+      run.z += v.z;
+      run.w += v.w;
+      run2.x += u.x;
+      run2.y += u.y;
+      run2.z += u.z;
+      run2.w += u.w;
     }
-    if (p < p1) {
-      const float2 v = *reinterpret_cast<const float2*>(sX + p * kTileLd + 2 * cp);
+    if (p < a1) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
       run.x += v.x;
       run.y += v.y;
+      run.z += v.z;
+      run.w += v.w;
     }
     run.x += run2.x;
     run.y += run2.y;
-    float2* dst = reinterpret_cast<float2*>(out + (size_t)tk->tgt[p0] * 64 + 2 * cp);
-    if (s == 0 && tk->cont_prev) {
-      float2 t = *dst;
-      run.x += t.x;
-      run.y += t.y;
+    run.z += run2.z;
+    run.w += run2.w;
+    // first half + second half
+    const float ox = __shfl_xor_sync(0xffffffffu, run.x, 16), oy = __shfl_xor_sync(0xffffffffu, run.y, 16);
+    const float oz = __shfl_xor_sync(0xffffffffu, run.z, 16), ow = __shfl_xor_sync(0xffffffffu, run.w, 16);
+    if (half == 0) {
+      run.x += ox;
+      run.y += oy;
+      run.z += oz;
+      run.w += ow;
+      float4* dst = reinterpret_cast<float4*>(out + (size_t)tk->tgt[p0] * 64 + 4 * cq);
+      if (s == 0 && tk->cont_prev) {
+        float4 t = *dst;
+        run.x += t.x;
+        run.y += t.y;
+        run.z += t.z;
+        run.w += t.w;
+      }
+      *dst = run;
     }
-    *dst = run;
   }
 }
-// source-segment sums into table rows, 256 threads: 16 column quads x 16 segment slots
+// source-segment sums into table rows, 256 threads: 16 column quads x 16 segment slots; rows of a segment are
+// fetched four at a time (independent loads) and added in order
 __device__ __forceinline__ void reduce_sources_table_256(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
                                                          float* __restrict__ table, int ld, int gt) {
   const int cq = gt & 15, slot = gt >> 4;
   const int nseg = tk->n_seg_s;
   for (int s = slot; s < nseg; s += 16) {
     const int p0 = tk->seg_s[s], p1 = tk->seg_s[s + 1];
-    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = p0; p < p1; ++p) {
-      const float4 v = *reinterpret_cast<const float4*>(sX + (int)tk->perm[p] * kTileLd + 4 * cq);
-      run.x += v.x;
-      run.y += v.y;
-      run.z += v.z;
-      run.w += v.w;
-    }
-    float4* dst = reinterpret_cast<float4*>(table + (size_t)tk->src[tk->perm[p0]] * ld + 4 * cq);
+    const int row0 = tk->perm[p0];
+    float4* dst = reinterpret_cast<float4*>(table + (size_t)tk->src[row0] * ld + 4 * cq);
     float4 t = *dst;
-    t.x += run.x;
-    t.y += run.y;
-    t.z += run.z;
-    t.w += run.w;
+    for (int p = p0; p < p1; p += 4) {
+      const int r0 = tk->perm[p], r1 = tk->perm[min(p + 1, p1 - 1)], r2 = tk->perm[min(p + 2, p1 - 1)],
+                r3 = tk->perm[min(p + 3, p1 - 1)];
+      const float4 v0 = *reinterpret_cast<const float4*>(sX + r0 * kTileLd + 4 * cq);
+      const float4 v1 = *reinterpret_cast<const float4*>(sX + r1 * kTileLd + 4 * cq);
+      const float4 v2 = *reinterpret_cast<const float4*>(sX + r2 * kTileLd + 4 * cq);
+      const float4 v3 = *reinterpret_cast<const float4*>(sX + r3 * kTileLd + 4 * cq);
+      const bool b1 = p + 1 < p1, b2 = p + 2 < p1, b3 = p + 3 < p1;
+      t.x += v0.x;
+      t.y += v0.y;
+      t.z += v0.z;
+      t.w += v0.w;
+      if (b1) {
+        t.x += v1.x;
+        t.y += v1.y;
+        t.z += v1.z;
+        t.w += v1.w;
+      }
+      if (b2) {
+        t.x += v2.x;
+        t.y += v2.y;
+        t.z += v2.z;
+        t.w += v2.w;
+      }
+      if (b3) {
+        t.x += v3.x;
+        t.y += v3.y;
+        t.z += v3.z;
+        t.w += v3.w;
+      }
+    }
     *dst = t;
   }
 }
@@ -1588,6 +1631,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         __syncwarp();
         ph_d ^= 1u;
         fence_after_sync();
+        // slot of this edge in the dense pair-adjoint array; its previous value is fetched early (layers 2, 1 add)
+        size_t rslot = 0;
+        float rold = 0.0f;
+        if (ch == 0 && valid) {
+          rslot = ((size_t)atom0 + tg) * g.N + (sr - (tg / g.N) * g.N);
+          if (g.rbar_accumulate) rold = g.rbar[rslot];
+        }
         ws_group_sync(grp);                          // (A) reductions of the previous tile are complete
         // ---- ubar = vbar * silu'(u) -> smem tile ; rbar = ubar . du (this thread's 32 channels)
         float racc = 0.0f;
@@ -1626,12 +1676,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           warp_arrive(u_ok, lane);
         }
         ws_group_sync(grp);                          // (B) tile complete
-        if (ch == 0 && valid) {
-          const float rs = racc + sPart[grp][row];   // channels 0..31 + 32..63
-          int repl = tg / g.N;
-          size_t slot = ((size_t)atom0 + tg) * g.N + (sr - repl * g.N);
-          g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + rs : rs;
-        }
+        if (ch == 0 && valid) g.rbar[rslot] = rold + (racc + sPart[grp][row]);   // channels 0..31 + 32..63
         reduce_targets_global_256(sU, tk, gPb, gt);          // Pbar[tgt] += ubar
         reduce_sources_table_256(sU, tk, tQb, ld, gt);       // Qbar[src] += ubar
         pr = pr_n;
