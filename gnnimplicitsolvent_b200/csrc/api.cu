@@ -26,6 +26,8 @@ int launch_edge_bwd(Ctx*, int, int, cudaStream_t);
 int launch_node_pre1(Ctx*, cudaStream_t);
 int launch_node_fwd(Ctx*, int, cudaStream_t);
 int launch_node_bwd(Ctx*, int, cudaStream_t);
+int launch_node_fwd_tc(Ctx*, int, cudaStream_t);
+int launch_node_bwd_tc(Ctx*, int, cudaStream_t);
 int launch_node_pre1_bwd(Ctx*, cudaStream_t);
 int launch_gb_only_head(Ctx*, cudaStream_t);
 int launch_add_vec(Ctx*, int, const float*, float*, cudaStream_t);
@@ -102,6 +104,7 @@ static int ensure_workspace(Ctx* c) {
         dev_alloc(c, &c->o[l], n * (l == 2 ? 2 : 64)))
       return -1;
   }
+  if (dev_alloc(c, &c->gbar, n * 128)) return -1;
   if (dev_alloc(c, &c->abar, n * 64) || dev_alloc(c, &c->Pbar, n * 64) || dev_alloc(c, &c->Qbar, n * 64) ||
       dev_alloc(c, &c->rbar, n * (size_t)c->N))
     return -1;
@@ -149,6 +152,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
   // do not fit next to the staged weight operands
   const bool tc_ok = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && tc_path_fits(c);
   const bool tc_fwd = tc_ok && (c->tc_mask & 1), tc_bwd = tc_ok && (c->tc_mask & 2);
+  const bool node_tc = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && (c->tc_mask & 16);
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
   if (tm) tm->mark(kStNeighborBorn);
@@ -162,7 +166,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
       if (tm) tm->mark(kStEdgeFwd);
       if (tc_fwd ? ((c->tc_mask & 4) ? launch_edge_fwd_ws(c, l, st) : launch_edge_fwd_tc(c, l, st)) : launch_edge_fwd(c, l, st)) return -1;
       if (tm) tm->mark(kStNodeFwd);
-      if (launch_node_fwd(c, l, st)) return -1;
+      if ((node_tc ? launch_node_fwd_tc(c, l, st) : launch_node_fwd(c, l, st))) return -1;
     }
   } else {
     if (launch_gb_only_head(c, st)) return -1;
@@ -176,7 +180,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     } else {
       for (int l = 2; l >= 0; --l) {
         if (tm) tm->mark(kStNodeBwd);
-        if (launch_node_bwd(c, l, st)) return -1;
+        if ((node_tc ? launch_node_bwd_tc(c, l, st) : launch_node_bwd(c, l, st))) return -1;
         if (tm) tm->mark(kStEdgeBwd);
         if (tc_bwd ? ((c->tc_mask & 8) ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, st) : launch_edge_bwd_tc(c, l, l == 2 ? 0 : 1, st))
                  : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
@@ -245,7 +249,7 @@ int gnnis_destroy(gnnis_handle h) {
                  &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->abar, &c->Pbar, &c->Qbar, &c->rbar, &c->e_atom,
                  &c->sa_atom, &c->h_pos_dev, &c->h_e_dev, &c->h_f_dev, &c->bond_r0, &c->bond_k, &c->lb_S, &c->lb_Y,
                  &c->lb_rho, &c->lb_alpha, &c->lb_g, &c->lb_gprev, &c->lb_xprev, &c->lb_d, &c->lb_e, &c->lb_eprev,
-                 &c->lb_step, &c->lb_ftmp, &c->lb_etmp, &c->masses, &c->gamma_emb};
+                 &c->lb_step, &c->lb_ftmp, &c->lb_etmp, &c->masses, &c->gamma_emb, &c->gbar};
   for (float** p : f) dev_free(p);
   for (int l = 0; l < 3; ++l) {
     dev_free(&c->P[l]);

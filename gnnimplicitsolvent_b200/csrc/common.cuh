@@ -62,7 +62,8 @@ struct Ctx {
   std::string err;
   int64_t launches = 0;
   int num_sms = 148;
-  int tc_mask = 15;  // bit0 / bit1: forward / adjoint edge kernel on tcgen05; bit2 / bit3: warp-specialised variant
+  int tc_mask = 31;  // bit0 / bit1: forward / adjoint edge kernel on tcgen05; bit2 / bit3: warp-specialised variant;
+                     // bit4: node MLP kernels on tcgen05
   // model
   bool have_weights = false;
   int S = 0;  // num_solvents
@@ -94,6 +95,7 @@ struct Ctx {
   float *P[3] = {nullptr, nullptr, nullptr}, *Q[3] = {nullptr, nullptr, nullptr}, *a[3] = {nullptr, nullptr, nullptr};
   float *o[3] = {nullptr, nullptr, nullptr};
   float *abar = nullptr, *Pbar = nullptr, *Qbar = nullptr, *obar3 = nullptr;
+  float* gbar = nullptr;   // [n][128] adjoint of silu(p), scratch between the two tensor-core node adjoint kernels
   float *rbar = nullptr;
   float *e_atom = nullptr, *sa_atom = nullptr;
   int64_t* n_edges_dev = nullptr;
