@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __re
 constexpr uint32_t kFwdWeights = 49152, kBwdWeights = 81920;
 constexpr uint32_t kGrpX = 0;
 constexpr uint32_t kGrpKeys = kGrpX + kTileE * kTileLd * 4;
-constexpr uint32_t kGrpTab = kGrpKeys + 2 * (uint32_t)sizeof(TileKeys);
+constexpr uint32_t kGrpTab = kGrpKeys + 3 * (uint32_t)sizeof(TileKeys);   // ws kernels rotate three key buffers
 static_assert(sizeof(TileKeys) % 16 == 0, "TileKeys must keep the tables 16-byte aligned");
 
 static size_t group_bytes(const Ctx* c, int ntables) {
@@ -1202,7 +1202,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
     const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
     uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp];
     uint32_t ph_d = 0, ph_a = 0, cur = 0;
-    int parity = 0;
+    int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
       const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
@@ -1237,7 +1237,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
         pr_n = g.pair[e_begin + kTileE + row];
         if (ch == 0) r_n = g.r_e[e_begin + kTileE + row];
       }
-      TileKeys* tk = keys + parity;
+      TileKeys* tk = keys + kidx;
       if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
       prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
       warp_arrive(u_ok, lane);                       // accumulators are free
@@ -1257,7 +1257,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
           const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
           if (lane == 0) {
             tk->n_seg_t = ns;
-            tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
+            tk->cont_prev = (t0 > e_begin && keys[(kidx + 2) % 3].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
           }
         }
         mbar_wait(d_full, ph_d);
@@ -1292,7 +1292,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
         tmem_st_wait();
         warp_arrive(a_full, lane);
         // ---- look ahead: keys / radial basis of the next tile while w runs
-        TileKeys* tkn = keys + (parity ^ 1);
+        TileKeys* tkn = keys + (kidx + 1) % 3;
         bool valid_n = false;
         uint32_t pr_nn = 0u;
         float r_nn = 0.3f;
@@ -1315,6 +1315,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
           }
         }
         ph_a ^= 1u;
+        // ---- a[tgt] += z of the PREVIOUS tile while the tensor pipe works on w of this one
+        if (t0 > e_begin) reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);
         mbar_wait(d_full, ph_d);
         __syncwarp();
         ph_d ^= 1u;
@@ -1339,17 +1341,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
             *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
           }
         }
-        ws_group_sync(grp);                          // (B) tile complete
-        reduce_targets_global_256(sZ, tk, gA, gt);
+        ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
         pr = pr_n;
         r = r_n;
         valid = valid_n;
         pr_n = pr_nn;
         r_n = r_nn;
         tk = tkn;
-        parity ^= 1;
+        kidx = (kidx + 1) % 3;
         cur ^= 64u;
       }
+      reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);   // last tile of the unit
       ws_group_sync(grp);   // all rows of the unit written before its tables are replaced
     }
   }
@@ -1455,7 +1457,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
     uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp];
     uint32_t ph_d = 0;
-    int parity = 0;
+    int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
       const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
@@ -1505,7 +1507,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           pm_n = g.perm[e_begin + kTileE + row];
         }
       }
-      TileKeys* tk = keys + parity;
+      TileKeys* tk = keys + kidx;
       if (ch == 0) {
         tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
         tk->src[row] = valid ? (int)(pr & 0xFFFFu) : -1;
@@ -1534,12 +1536,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
           if (lane == 0) {
             tk->n_seg_t = ns;
-            tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
+            tk->cont_prev = (t0 > e_begin && keys[(kidx + 2) % 3].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
           }
         } else if (w8 == 5) {
           const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, min(kTileE, e_end - t0), lane);
           if (lane == 0) tk->n_seg_s = ns;
         }
+        // the reductions of the PREVIOUS tile run while the tensor pipe works on u, du (targets) and w (sources)
+        const TileKeys* tkp = keys + (kidx + 2) % 3;
+        if (t0 > e_begin) reduce_targets_global_256(sU, tkp, gPb, gt);          // Pbar[tgt] += ubar
         mbar_wait(d_full, ph_d);
         __syncwarp();
         ph_d ^= 1u;
@@ -1572,6 +1577,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         }
         tmem_st_wait();
         warp_arrive(a_full, lane);
+        if (t0 > e_begin) reduce_sources_table_256(sU, tkp, tQb, ld, gt);       // Qbar[src] += ubar
         mbar_wait(d_full, ph_d);
         __syncwarp();
         ph_d ^= 1u;
@@ -1604,7 +1610,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         tmem_st_wait();
         warp_arrive(a_full, lane);
         // ---- edge data of the following tiles while vbar runs
-        TileKeys* tkn = keys + (parity ^ 1);
+        TileKeys* tkn = keys + (kidx + 1) % 3;
         bool valid_n = false;
         uint32_t pr_nn = 0u;
         float r_nn = 0.3f;
@@ -1677,8 +1683,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         }
         ws_group_sync(grp);                          // (B) tile complete
         if (ch == 0 && valid) g.rbar[rslot] = rold + (racc + sPart[grp][row]);   // channels 0..31 + 32..63
-        reduce_targets_global_256(sU, tk, gPb, gt);          // Pbar[tgt] += ubar
-        reduce_sources_table_256(sU, tk, tQb, ld, gt);       // Qbar[src] += ubar
         pr = pr_n;
         r = r_n;
         pm = pm_n;
@@ -1687,8 +1691,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         r_n = r_nn;
         pm_n = pm_nn;
         tk = tkn;
-        parity ^= 1;
+        kidx = (kidx + 1) % 3;
       }
+      reduce_targets_global_256(sU, keys + (kidx + 2) % 3, gPb, gt);          // last tile of the unit
+      reduce_sources_table_256(sU, keys + (kidx + 2) % 3, tQb, ld, gt);
       ws_group_sync(grp);
       if (SMEM_TABLES) {
         copy_rows_n(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt, kWsGroupThreads);
