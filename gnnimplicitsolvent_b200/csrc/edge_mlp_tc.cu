@@ -75,6 +75,46 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 // sigmoid = 1 / (1 + 2^(-x log2 e)): one MUFU.EX2 + one MUFU.RCP (~2 ulp); the parity gates guard this choice
 __device__ __forceinline__ float sig_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float silu_fast(float x) { return x * sig_fast(x); }
+// Four sigmoids from four MUFU.EX2 and ONE MUFU.RCP: 1/d_i = d_j d_k d_l / (d_0 d_1 d_2 d_3) with d = 1 + e^-x.
+// x is clamped at -20 inside the exponential (d <= 2^29, so the product of four stays below 2^116);
+// sigmoid(-20) = 2e-9, i.e. silu and its derivative are reproduced to ~1e-7 absolute below the clamp.
+__device__ __forceinline__ void sig4_fast(float x0, float x1, float x2, float x3, float& s0, float& s1, float& s2,
+                                          float& s3) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;   // -log2(e), 20 log2(e)
+  const float d0 = 1.0f + ex2_ftz(fminf(kL * x0, kClamp)), d1 = 1.0f + ex2_ftz(fminf(kL * x1, kClamp));
+  const float d2 = 1.0f + ex2_ftz(fminf(kL * x2, kClamp)), d3 = 1.0f + ex2_ftz(fminf(kL * x3, kClamp));
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
+  s0 = r01 * d1;
+  s1 = r01 * d0;
+  s2 = r23 * d3;
+  s3 = r23 * d2;
+}
+__device__ __forceinline__ float4 silu4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(x0 * s0, x1 * s1, x2 * s2, x3 * s3);
+}
+__device__ __forceinline__ void silu_fd4_fast(float x0, float x1, float x2, float x3, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  f[0] = x0 * s0;
+  f[1] = x1 * s1;
+  f[2] = x2 * s2;
+  f[3] = x3 * s3;
+  d[0] = fmaf(f[0], 1.0f - s0, s0);
+  d[1] = fmaf(f[1], 1.0f - s1, s1);
+  d[2] = fmaf(f[2], 1.0f - s2, s2);
+  d[3] = fmaf(f[3], 1.0f - s3, s3);
+}
+__device__ __forceinline__ float4 silu_d4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(fmaf(s0, fmaf(-x0, s0, x0), s0), fmaf(s1, fmaf(-x1, s1, x1), s1), fmaf(s2, fmaf(-x2, s2, x2), s2),
+                     fmaf(s3, fmaf(-x3, s3, x3), s3));
+}
 __device__ __forceinline__ void silu_fd_fast(float x, float& f, float& d) {
   const float sg = sig_fast(x);
   f = x * sg;
@@ -1282,10 +1322,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
           float v[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            v[4 * j4 + 0] = silu_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x));
-            v[4 * j4 + 1] = silu_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y));
-            v[4 * j4 + 2] = silu_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z));
-            v[4 * j4 + 3] = silu_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
+            const float4 y = silu4_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x),
+                                        __uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y),
+                                        __uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z),
+                                        __uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
+            v[4 * j4 + 0] = y.x;
+            v[4 * j4 + 1] = y.y;
+            v[4 * j4 + 2] = y.z;
+            v[4 * j4 + 3] = y.w;
           }
           st_split16(lane_addr + VH + col0, lane_addr + VL + col0, v);
         }
@@ -1333,11 +1377,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = bb[j4];
-            float4 z;
-            z.x = silu_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x);
-            z.y = silu_fast(__uint_as_float(wr[4 * j4 + 1]) + b.y);
-            z.z = silu_fast(__uint_as_float(wr[4 * j4 + 2]) + b.z);
-            z.w = silu_fast(__uint_as_float(wr[4 * j4 + 3]) + b.w);
+            const float4 z = silu4_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x, __uint_as_float(wr[4 * j4 + 1]) + b.y,
+                                        __uint_as_float(wr[4 * j4 + 2]) + b.z, __uint_as_float(wr[4 * j4 + 3]) + b.w);
             *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
           }
         }
@@ -1568,10 +1609,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           float v[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            silu_fd_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x), v[4 * j4 + 0], dsu[16 * c + 4 * j4 + 0]);
-            silu_fd_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y), v[4 * j4 + 1], dsu[16 * c + 4 * j4 + 1]);
-            silu_fd_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z), v[4 * j4 + 2], dsu[16 * c + 4 * j4 + 2]);
-            silu_fd_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w), v[4 * j4 + 3], dsu[16 * c + 4 * j4 + 3]);
+            silu_fd4_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x),
+                          __uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y),
+                          __uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z),
+                          __uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w), &v[4 * j4], &dsu[16 * c + 4 * j4]);
           }
           st_split16(lane_addr + XH + col0, lane_addr + XL + col0, v);
         }
@@ -1600,10 +1641,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           float wb[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            wb[4 * j4 + 0] = a[j4].x * silu_d_fast(__uint_as_float(wr[4 * j4 + 0]) + b[j4].x);
-            wb[4 * j4 + 1] = a[j4].y * silu_d_fast(__uint_as_float(wr[4 * j4 + 1]) + b[j4].y);
-            wb[4 * j4 + 2] = a[j4].z * silu_d_fast(__uint_as_float(wr[4 * j4 + 2]) + b[j4].z);
-            wb[4 * j4 + 3] = a[j4].w * silu_d_fast(__uint_as_float(wr[4 * j4 + 3]) + b[j4].w);
+            const float4 sd = silu_d4_fast(__uint_as_float(wr[4 * j4 + 0]) + b[j4].x, __uint_as_float(wr[4 * j4 + 1]) + b[j4].y,
+                                           __uint_as_float(wr[4 * j4 + 2]) + b[j4].z, __uint_as_float(wr[4 * j4 + 3]) + b[j4].w);
+            wb[4 * j4 + 0] = a[j4].x * sd.x;
+            wb[4 * j4 + 1] = a[j4].y * sd.y;
+            wb[4 * j4 + 2] = a[j4].z * sd.z;
+            wb[4 * j4 + 3] = a[j4].w * sd.w;
           }
           st_split16(lane_addr + XH + col0, lane_addr + XL + col0, wb);
         }
