@@ -202,3 +202,32 @@ def test_cuda_core_path_vs_golden(name, weights):
     # tensor-core (3xTF32) and CUDA-core paths agree to fp32 rounding
     assert rel_rms(f2.cpu().numpy(), f.cpu().numpy()) < 2e-5
     np.testing.assert_allclose(e2.cpu().numpy(), e.cpu().numpy(), rtol=2e-6)
+
+
+def test_cuda_graph_capture(weights):
+    """gnnis_energy_force does not synchronise the host: it can be captured into a CUDA graph and replayed."""
+    c = load_case("mixed_n50")
+    eng = _engine(c, weights)
+    pos = torch.from_numpy(c["pos"]).cuda()
+    e_ref, f_ref = eng.energy_force(pos)
+    e = torch.empty_like(e_ref)
+    f = torch.empty_like(f_ref)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng.energy_force(pos, out_energy=e, out_force=f)      # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.energy_force(pos, out_energy=e, out_force=f)
+    e.zero_()
+    f.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(e, e_ref) and torch.equal(f, f_ref)
+    # new positions through the same graph
+    pos.add_(0.001)
+    graph.replay()
+    torch.cuda.synchronize()
+    e2, f2 = eng.energy_force(pos)
+    assert torch.equal(e, e2) and torch.equal(f, f2)
