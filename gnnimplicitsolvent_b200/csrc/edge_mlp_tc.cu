@@ -984,28 +984,47 @@ int launch_edge_bwd_tc(Ctx* c, int l, int rbar_accumulate, cudaStream_t st) {
 }
 
 // ================================================================================================================
-// Warp-specialised variant (default): 2 groups x 8 epilogue warps + 1 MMA-issuer warp per CTA.
+// 16-warp variant (default): 2 groups x 8 warps per CTA, no group-wide barrier on the MMA hand-off.
 //
 // A thread is (edge row, 32-column half): warps 0-3 of a group take channels 0..31, warps 4-7 channels 32..63 of
-// the same 128 rows, so 16 epilogue warps share the four schedulers of the SM instead of 8.  All tcgen05.mma are
-// issued by lane 0 of warp 16, which polls (mbarrier.test_wait) the two groups in turn; the epilogue warps hand
-// operands over with mbarrier arrivals and never block on the issue itself:
-//     u_ok   (12 arrivals) : rbf operand of the next tile written (4 warps) + accumulators drained (8 warps)
-//     a_full ( 8 arrivals) : A operand (v, wbar) written by all warps
-//     d_full ( tcgen05.commit ) : products of the last issue are in TMEM
+// the same 128 rows, so 16 warps share the four schedulers of the SM instead of 8.  Operands are handed to the
+// tensor pipe by arrival counters in shared memory: every warp arrives once its part of an A operand is in TMEM
+// (or once it has drained an accumulator), and the warp whose arrival completes the count issues the tcgen05.mma
+// batch itself (one elected lane, warp converged) -- nobody waits for a dedicated issuer or for the slowest warp
+// before carrying on with independent work:
+//     cnt_u  (12 arrivals) : rbf operand of the next tile written (4 warps) + accumulators drained (8 warps)
+//     cnt_a  ( 8 arrivals) : A operand (v, wbar) written by all warps
+//     d_full ( tcgen05.commit -> mbarrier ) : products of the last issue are in TMEM
 // Only two group-wide named barriers per tile remain, both around the shared-memory tile of the reduction.
 constexpr int kWsGroupThreads = 256;
-constexpr int kWsThreads = kGroups * kWsGroupThreads + 32;
+constexpr int kWsThreads = kGroups * kWsGroupThreads;
 
 struct WsBars {
-  uint64_t d_full[kGroups], a_full[kGroups], u_ok[kGroups];
+  uint64_t d_full[kGroups], a_full[kGroups];
+  int cnt_a[kGroups], cnt_u[kGroups];
 };
 
 __device__ __forceinline__ void ws_group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
-// one arrival per warp, after the warp's outstanding TMEM traffic has been waited for by the caller
-__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+// One arrival per warp, after the warp's outstanding TMEM traffic has been waited for by the caller.  Returns true
+// (warp-uniform) in the warp that completes the count; that warp then issues the MMAs that depended on it.
+__device__ __forceinline__ bool warp_arrive_last(int* cnt, int expected, int lane) {
   fence_before_sync();
   __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    // acq_rel at CTA scope orders the counter protocol; TMEM traffic is ordered by the tcgen05 fences around it
+    int old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+    if (old == expected - 1) {
+      asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(cnt)), "r"(0) : "memory");
+      last = 1;
+    }
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) fence_after_sync();
+  return last != 0;
+}
+__device__ __forceinline__ void warp_arrive_mbar(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void st_split16(uint32_t t_hi, uint32_t t_lo, const float (&x)[16]) {
@@ -1132,6 +1151,19 @@ __device__ __forceinline__ void reduce_sources_table_256(const float* __restrict
   }
 }
 
+// ---- variant with a dedicated MMA-issuer warp (17 warps -> 96 registers per thread; used for the forward kernel,
+// where the issue work would otherwise sit on the critical path of the slowest epilogue warp): lane-elected issue
+// by warp 16, which polls (mbarrier.test_wait) the two groups in turn:
+//     u_ok (12 arrivals), a_full (8 arrivals), d_full (tcgen05.commit)
+constexpr int kWsiThreads = kGroups * kWsGroupThreads + 32;
+struct WsiBars {
+  uint64_t d_full[kGroups], a_full[kGroups], u_ok[kGroups];
+};
+__device__ __forceinline__ void warp_arrive_i(uint64_t* bar, int lane) {
+  fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 // issuer-side walk over the units of one group (must visit exactly the tiles the epilogue warps visit)
 struct IssueState {
   int unit, t0, e_end, stage;
@@ -1155,11 +1187,11 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
   }
 }
 
-// ---------------------------------------------------------------------------------------------- forward (ws)
+// ---------------------------------------------------------------------------------------------- forward (ws, dedicated issuer warp)
 template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+__global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   extern __shared__ uint8_t smraw[];
-  __shared__ WsBars bars;
+  __shared__ WsiBars bars;
   __shared__ uint32_t tmem_slot;
   uint32_t base = smem_u32(smraw);
   uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
@@ -1280,13 +1312,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
       TileKeys* tk = keys + kidx;
       if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
       prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
-      warp_arrive(u_ok, lane);                       // accumulators are free
+      warp_arrive_i(u_ok, lane);                       // accumulators are free
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<false>(r, g.inv_cutoff, o, od);
         st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
         tmem_st_wait();
-        warp_arrive(u_ok, lane);
+        warp_arrive_i(u_ok, lane);
       }
       ws_group_sync(grp);                            // tables + keys of the first tile visible
 
@@ -1334,7 +1366,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
           st_split16(lane_addr + VH + col0, lane_addr + VL + col0, v);
         }
         tmem_st_wait();
-        warp_arrive(a_full, lane);
+        warp_arrive_i(a_full, lane);
         // ---- look ahead: keys / radial basis of the next tile while w runs
         TileKeys* tkn = keys + (kidx + 1) % 3;
         bool valid_n = false;
@@ -1355,7 +1387,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
             __syncwarp();
             st_split(lane_addr + cur, lane_addr + cur + 32, o);
             tmem_st_wait();
-            warp_arrive(u_ok, lane);
+            warp_arrive_i(u_ok, lane);
           }
         }
         ph_a ^= 1u;
@@ -1369,7 +1401,228 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g
         uint32_t wr[32];
         tmem_ld32(lane_addr + (cur ^ 64u) + 32 * ch, wr);
         tmem_ld_wait();
-        if (has_next) warp_arrive(u_ok, lane);
+        if (has_next) warp_arrive_i(u_ok, lane);
+        ws_group_sync(grp);                          // (A) the reduction of the previous tile is complete
+        {
+          const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * ch);
+          float* zrow = sZ + row * kTileLd + 32 * ch;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = bb[j4];
+            const float4 z = silu4_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x, __uint_as_float(wr[4 * j4 + 1]) + b.y,
+                                        __uint_as_float(wr[4 * j4 + 2]) + b.z, __uint_as_float(wr[4 * j4 + 3]) + b.w);
+            *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
+          }
+        }
+        ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
+        pr = pr_n;
+        r = r_n;
+        valid = valid_n;
+        pr_n = pr_nn;
+        r_n = r_nn;
+        tk = tkn;
+        kidx = (kidx + 1) % 3;
+        cur ^= 64u;
+      }
+      reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);   // last tile of the unit
+      ws_group_sync(grp);   // all rows of the unit written before its tables are replaced
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- forward (ws)
+template <bool SMEM_TABLES>
+__global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+  extern __shared__ uint8_t smraw[];
+  __shared__ WsBars bars;
+  __shared__ uint32_t tmem_slot;
+  uint32_t base = smem_u32(smraw);
+  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
+  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
+  float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) {
+      mbar_init(&bars.d_full[i], 1);
+      mbar_init(&bars.a_full[i], 8);
+      bars.cnt_a[i] = 0;
+      bars.cnt_u[i] = 0;
+    }
+  }
+  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);
+  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);
+  if (tid < 64) sb2[tid] = g.b2[tid];
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  constexpr uint32_t VH = 128, VL = 192;
+  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+
+  {
+    const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
+    uint8_t* gsm = sm + kFwdWeights + 256 + (size_t)grp * grp_bytes;
+    float* sZ = reinterpret_cast<float*>(gsm + kGrpX);
+    TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
+    float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
+    const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
+    const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
+    uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp];
+    int *cnt_a = &bars.cnt_a[grp], *cnt_u = &bars.cnt_u[grp];
+    const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
+    // u of the tile whose accumulator is B[c]: A = rbf in B[c ^ 64]
+    auto issue_u = [&](uint32_t c) {
+      if (elect_one()) {
+        issue_gemm_3xtf32<0, 3>(tm + c, tm + (c ^ 64u), tm + (c ^ 64u) + 32, aWrH, aWrL, 64, idesc64, 0u);
+        mma_commit(d_full);
+      }
+      __syncwarp();
+    };
+    auto issue_w = [&](uint32_t c) {
+      if (elect_one()) {
+        issue_gemm_3xtf32<0, 8>(tm + (c ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
+        mma_commit(d_full);
+      }
+      __syncwarp();
+    };
+    uint32_t ph_d = 0, ph_a = 0, cur = 0;
+    int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
+
+    for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
+      const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
+      const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
+      const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
+      const float* gP = g.P + (size_t)atom0 * 64;
+      float* gA = g.a_out + (size_t)atom0 * 64;
+      const float* tQ;
+      int ld;
+      if (SMEM_TABLES) {
+        ld = kTabLd;
+        copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
+        tQ = sTab;
+      } else {
+        ld = 64;
+        tQ = g.Q + (size_t)atom0 * 64;
+      }
+      zero_rows_n(gA, 64, natoms, gt, kWsGroupThreads);
+      if (e_begin >= e_end) {
+        ws_group_sync(grp);
+        continue;
+      }
+      // ---- prologue: keys + radial basis of the first tile; edge data of the second tile in flight
+      uint32_t pr = 0u, pr_n = 0u;
+      float r = 0.3f, r_n = 0.3f;
+      bool valid = e_begin + row < e_end;
+      if (valid) {
+        pr = g.pair[e_begin + row];
+        if (ch == 0) r = g.r_e[e_begin + row];
+      }
+      if (e_begin + kTileE + row < e_end) {
+        pr_n = g.pair[e_begin + kTileE + row];
+        if (ch == 0) r_n = g.r_e[e_begin + kTileE + row];
+      }
+      TileKeys* tk = keys + kidx;
+      if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
+      prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
+      if (warp_arrive_last(cnt_u, 12, lane)) issue_u(cur);     // accumulators are free
+      if (ch == 0) {
+        float o[32], od[32];
+        rbf_regs<false>(r, g.inv_cutoff, o, od);
+        st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
+        tmem_st_wait();
+        if (warp_arrive_last(cnt_u, 12, lane)) issue_u(cur);
+      }
+      ws_group_sync(grp);                            // tables + keys of the first tile visible
+
+      for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
+        const bool has_next = t0 + kTileE < e_end;
+        const int tgc = valid ? (int)(pr >> 16) : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
+        if (w8 == 4) {
+          const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
+          if (lane == 0) {
+            tk->n_seg_t = ns;
+            tk->cont_prev = (t0 > e_begin && keys[(kidx + 2) % 3].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
+          }
+        }
+        mbar_wait(d_full, ph_d);
+        __syncwarp();
+        ph_d ^= 1u;
+        fence_after_sync();
+        // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM (this thread's 32 channels, two chunks of 16)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = 32 * ch + 16 * c;
+          uint32_t ur[16];
+          tmem_ld16(lane_addr + cur + col0, ur);
+          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + col0);
+          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
+          float4 p[4], q[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            p[j4] = __ldg(pp + j4);
+            q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+          }
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 y = silu4_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x),
+                                        __uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y),
+                                        __uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z),
+                                        __uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
+            v[4 * j4 + 0] = y.x;
+            v[4 * j4 + 1] = y.y;
+            v[4 * j4 + 2] = y.z;
+            v[4 * j4 + 3] = y.w;
+          }
+          st_split16(lane_addr + VH + col0, lane_addr + VL + col0, v);
+        }
+        tmem_st_wait();
+        {
+          const bool last = warp_arrive_last(cnt_a, 8, lane);
+          warp_arrive_mbar(a_full, lane);          // lets the rbf writers below know that u has been read by everyone
+          if (last) issue_w(cur);
+        }
+        // ---- look ahead: keys / radial basis of the next tile while w runs
+        TileKeys* tkn = keys + (kidx + 1) % 3;
+        bool valid_n = false;
+        uint32_t pr_nn = 0u;
+        float r_nn = 0.3f;
+        if (has_next) {
+          valid_n = t0 + kTileE + row < e_end;
+          if (ch == 0) tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
+          prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
+          if (t0 + 2 * kTileE + row < e_end) {
+            pr_nn = g.pair[t0 + 2 * kTileE + row];
+            if (ch == 0) r_nn = g.r_e[t0 + 2 * kTileE + row];
+          }
+          if (ch == 0) {
+            float o[32], od[32];
+            rbf_regs<false>(r_n, g.inv_cutoff, o, od);
+            mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
+            __syncwarp();
+            st_split(lane_addr + cur, lane_addr + cur + 32, o);
+            tmem_st_wait();
+            if (warp_arrive_last(cnt_u, 12, lane)) issue_u(cur ^ 64u);
+          }
+        }
+        ph_a ^= 1u;
+        // ---- a[tgt] += z of the PREVIOUS tile while the tensor pipe works on w of this one
+        if (t0 > e_begin) reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);
+        mbar_wait(d_full, ph_d);
+        __syncwarp();
+        ph_d ^= 1u;
+        fence_after_sync();
+        // ---- w -> registers; the accumulator may then be overwritten by u of the next tile
+        uint32_t wr[32];
+        tmem_ld32(lane_addr + (cur ^ 64u) + 32 * ch, wr);
+        tmem_ld_wait();
+        if (has_next && warp_arrive_last(cnt_u, 12, lane)) issue_u(cur ^ 64u);
         ws_group_sync(grp);                          // (A) the reduction of the previous tile is complete
         {
           const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * ch);
@@ -1420,7 +1673,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     for (int i = 0; i < kGroups; ++i) {
       mbar_init(&bars.d_full[i], 1);
       mbar_init(&bars.a_full[i], 8);
-      mbar_init(&bars.u_ok[i], 12);
+      bars.cnt_a[i] = 0;
+      bars.cnt_u[i] = 0;
     }
   }
   stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);
@@ -1434,61 +1688,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
   constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
   constexpr uint32_t idesc64 = idesc_tf32(128, 64);
 
-  if (warp == 2 * 8) {
-    {
-      const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
-      const uint32_t aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
-      IssueState st[kGroups];
-      for (int i = 0; i < kGroups; ++i) {
-        st[i] = IssueState{(int)blockIdx.x * kGroups + i, 0, 0, 0, 0u, 0u, 0u, false};
-        issue_next_unit(st[i], g);
-      }
-      while (!(st[0].done && st[1].done)) {
-#pragma unroll
-        for (int i = 0; i < kGroups; ++i) {
-          IssueState& x = st[i];
-          if (x.done) continue;
-          const uint32_t tm = tmem_slot + (uint32_t)i * 256u;
-          if (x.stage == 0) {          // u = rbf . Wr^T ; du = drbf . Wr^T
-            if (!mbar_test(&bars.u_ok[i], x.ph_u)) continue;
-            x.ph_u ^= 1u;
-            fence_after_sync();
-            if (elect_one()) {
-              issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
-              issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
-              mma_commit(&bars.d_full[i]);
-            }
-            __syncwarp();
-            x.stage = 1;
-          } else {
-            if (!mbar_test(&bars.a_full[i], x.ph_a)) continue;
-            x.ph_a ^= 1u;
-            fence_after_sync();
-            if (x.stage == 1) {        // w = v . W2^T
-              if (elect_one()) {
-                issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2H, aW2L, 64, idesc64, 0u);
-                mma_commit(&bars.d_full[i]);
-              }
-              __syncwarp();
-              x.stage = 2;
-            } else {                   // vbar = wbar . W2
-              if (elect_one()) {
-                issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2tH, aW2tL, 64, idesc64, 0u);
-                mma_commit(&bars.d_full[i]);
-              }
-              __syncwarp();
-              x.stage = 0;
-              x.t0 += kTileE;
-              if (x.t0 >= x.e_end) {
-                x.unit += gridDim.x * kGroups;
-                issue_next_unit(x, g);
-              }
-            }
-          }
-        }
-      }
-    }
-  } else {
+  {
     const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
     uint8_t* gsm = sm + kBwdWeights + 256 + (size_t)grp * grp_bytes;
     float* sU = reinterpret_cast<float*>(gsm + kGrpX);
@@ -1496,7 +1696,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
     const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
     const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-    uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp];
+    uint64_t* d_full = &bars.d_full[grp];
+    int *cnt_a = &bars.cnt_a[grp], *cnt_u = &bars.cnt_u[grp];
+    const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
+    const uint32_t aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
+    auto issue_u_du = [&]() {      // u = rbf . Wr^T ; du = drbf . Wr^T
+      if (elect_one()) {
+        issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
+        issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
+        mma_commit(d_full);
+      }
+      __syncwarp();
+    };
+    auto issue_x = [&](uint32_t bH, uint32_t bL) {   // ACC = X . B^T  (w with W2, vbar with W2^T)
+      if (elect_one()) {
+        issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, bH, bL, 64, idesc64, 0u);
+        mma_commit(d_full);
+      }
+      __syncwarp();
+    };
     uint32_t ph_d = 0;
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
@@ -1559,14 +1777,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         prefetch_l1(gP + t_);
         prefetch_l1(gAb + t_);
       }
-      warp_arrive(u_ok, lane);
+      if (warp_arrive_last(cnt_u, 12, lane)) issue_u_du();
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<true>(r, g.inv_cutoff, o, od);
         st_split(lane_addr + XH, lane_addr + XL, o);
         st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
         tmem_st_wait();
-        warp_arrive(u_ok, lane);
+        if (warp_arrive_last(cnt_u, 12, lane)) issue_u_du();
       }
       ws_group_sync(grp);
 
@@ -1617,7 +1835,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           st_split16(lane_addr + XH + col0, lane_addr + XL + col0, v);
         }
         tmem_st_wait();
-        warp_arrive(a_full, lane);
+        if (warp_arrive_last(cnt_a, 8, lane)) issue_x(aW2H, aW2L);              // w = v . W2^T
         if (t0 > e_begin) reduce_sources_table_256(sU, tkp, tQb, ld, gt);       // Qbar[src] += ubar
         mbar_wait(d_full, ph_d);
         __syncwarp();
@@ -1651,7 +1869,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           st_split16(lane_addr + XH + col0, lane_addr + XL + col0, wb);
         }
         tmem_st_wait();
-        warp_arrive(a_full, lane);
+        if (warp_arrive_last(cnt_a, 8, lane)) issue_x(aW2tH, aW2tL);            // vbar = wbar . W2
         // ---- edge data of the following tiles while vbar runs
         TileKeys* tkn = keys + (kidx + 1) % 3;
         bool valid_n = false;
@@ -1714,7 +1932,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           }
           racc += ra + rb;
         }
-        if (has_next) warp_arrive(u_ok, lane);       // ACC / DU drained
+        if (has_next && warp_arrive_last(cnt_u, 12, lane)) issue_u_du();   // ACC / DU drained
         if (ch == 1) sPart[grp][row] = racc;
         if (has_next && ch == 0) {
           float o[32], od[32];
@@ -1722,7 +1940,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           st_split(lane_addr + XH, lane_addr + XL, o);
           st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
           tmem_st_wait();
-          warp_arrive(u_ok, lane);
+          if (warp_arrive_last(cnt_u, 12, lane)) issue_u_du();
         }
         ws_group_sync(grp);                          // (B) tile complete
         if (ch == 0 && valid) g.rbar[rslot] = rold + (racc + sPart[grp][row]);   // channels 0..31 + 32..63
@@ -1755,11 +1973,21 @@ int launch_edge_fwd_ws(Ctx* c, int l, cudaStream_t st) {
   size_t smem = fwd_tc_smem(c);
   uint32_t gb = (uint32_t)group_bytes(c, 1);
   if (c->smem_tables) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_ws_kernel<true><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+    if (c->tc_mask & 32) {
+      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      edge_fwd_ws_kernel<true><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+    } else {
+      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      edge_fwd_wsi_kernel<true><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
+    }
   } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_ws_kernel<false><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+    if (c->tc_mask & 32) {
+      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      edge_fwd_ws_kernel<false><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
+    } else {
+      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      edge_fwd_wsi_kernel<false><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
+    }
   }
   GNNIS_LAUNCH_CHECK();
   return 0;
