@@ -1894,6 +1894,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
             }
           }
         }
+        // radial operands of the next tile are computed now (registers), while vbar runs, and stored after epi3
+        float o_n[32], od_n[32];
+        if (has_next && ch == 0) {
+          rbf_regs<true>(r_n, g.inv_cutoff, o_n, od_n);
+#pragma unroll
+          for (int k = 0; k < kRbf; ++k) asm volatile("" : "+f"(o_n[k]), "+f"(od_n[k]));   // keep the work above the wait
+        }
         mbar_wait(d_full, ph_d);
         __syncwarp();
         ph_d ^= 1u;
@@ -1935,10 +1942,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         if (has_next && warp_arrive_last(cnt_u, 12, lane)) issue_u_du();   // ACC / DU drained
         if (ch == 1) sPart[grp][row] = racc;
         if (has_next && ch == 0) {
-          float o[32], od[32];
-          rbf_regs<true>(r_n, g.inv_cutoff, o, od);
-          st_split(lane_addr + XH, lane_addr + XL, o);
-          st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
+          st_split(lane_addr + XH, lane_addr + XL, o_n);
+          st_split(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
           tmem_st_wait();
           if (warp_arrive_last(cnt_u, 12, lane)) issue_u_du();
         }
