@@ -16,8 +16,6 @@ int launch_born_adjoint(Ctx*, const float*, int, float*, cudaStream_t);
 int launch_reduce_energy(Ctx*, const float*, float*, cudaStream_t);
 int launch_edge_fwd(Ctx*, int, cudaStream_t);
 int launch_tile_perm(Ctx*, cudaStream_t);
-int launch_edge_fwd_tc(Ctx*, int, cudaStream_t);
-int launch_edge_bwd_tc(Ctx*, int, int, cudaStream_t);
 int launch_edge_fwd_ws(Ctx*, int, cudaStream_t);
 int launch_edge_bwd_ws(Ctx*, int, int, cudaStream_t);
 int launch_umma_selftest(Ctx*, const float*, const float*, float*, int, int, cudaStream_t);
@@ -152,7 +150,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
   // do not fit next to the staged weight operands
   const bool tc_ok = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && tc_path_fits(c);
   const bool tc_fwd = tc_ok && (c->tc_mask & 1), tc_bwd = tc_ok && (c->tc_mask & 2);
-  const bool node_tc = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && (c->tc_mask & 16);
+  const bool node_tc = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && (c->tc_mask & 4);
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
   if (tm) tm->mark(kStNeighborBorn);
@@ -164,7 +162,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     if (launch_node_pre1(c, st)) return -1;
     for (int l = 0; l < 3; ++l) {
       if (tm) tm->mark(kStEdgeFwd);
-      if (tc_fwd ? ((c->tc_mask & 4) ? launch_edge_fwd_ws(c, l, st) : launch_edge_fwd_tc(c, l, st)) : launch_edge_fwd(c, l, st)) return -1;
+      if (tc_fwd ? launch_edge_fwd_ws(c, l, st) : launch_edge_fwd(c, l, st)) return -1;
       if (tm) tm->mark(kStNodeFwd);
       if ((node_tc ? launch_node_fwd_tc(c, l, st) : launch_node_fwd(c, l, st))) return -1;
     }
@@ -182,8 +180,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
         if (tm) tm->mark(kStNodeBwd);
         if ((node_tc ? launch_node_bwd_tc(c, l, st) : launch_node_bwd(c, l, st))) return -1;
         if (tm) tm->mark(kStEdgeBwd);
-        if (tc_bwd ? ((c->tc_mask & 8) ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, st) : launch_edge_bwd_tc(c, l, l == 2 ? 0 : 1, st))
-                 : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
+        if (tc_bwd ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
       }
       if (tm) tm->mark(kStNodeBwd);
       if (launch_node_pre1_bwd(c, st)) return -1;
@@ -234,7 +231,7 @@ int gnnis_create(gnnis_handle* out, int device) {
     delete c;
     return -1;
   }
-  if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 fwd, bit1 bwd on tensor cores
+  if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;
 }

@@ -62,8 +62,7 @@ struct Ctx {
   std::string err;
   int64_t launches = 0;
   int num_sms = 148;
-  int tc_mask = 31;  // bit0 / bit1: forward / adjoint edge kernel on tcgen05; bit2 / bit3: warp-specialised variant;
-                     // bit4: node MLP kernels on tcgen05
+  int tc_mask = 7;   // tcgen05 kernels in use: bit0 edge forward, bit1 edge adjoint, bit2 node MLPs (else fp32 CUDA cores)
   // model
   bool have_weights = false;
   int S = 0;  // num_solvents

@@ -7,11 +7,12 @@
 //     wbar = abar[i] * silu'(w);  vbar = wbar W2;  ubar = vbar * silu'(u)
 //     Pbar[i] += ubar;  Qbar[j] += ubar;  rbar_e = sum_c ubar_c (d rbf/dr Wr^T)_c
 //
-// Work decomposition: one persistent CTA per SM made of TWO independent 128-thread groups.  Each group owns its
+// Work decomposition: one persistent CTA per SM made of TWO independent groups of 8 warps.  Each group owns its
 // own units (a unit = G replicas whose tables fit in shared memory), its own 128-edge tile, its own 256 TMEM
-// columns, its own mbarrier and named barrier -- the groups never synchronise with each other, so while one
-// group waits for its tcgen05.mma the other one runs its SiLU epilogue (MUFU) and vice versa.  Inside a group a
-// thread is one edge row (= one TMEM lane) and walks the 64 channels in two halves of 32 columns.
+// columns, its own mbarriers / arrival counters and named barrier -- the groups never synchronise with each other,
+// so while one group waits for its tcgen05.mma the other one runs its SiLU epilogue and vice versa.  Inside a group
+// a thread is (edge row = TMEM lane, 32-column half): warps 0-3 take channels 0..31, warps 4-7 channels 32..63, and
+// each walks its channels in two chunks of 16 columns (tcgen05.ld/st.32x32b.x16).
 //
 // Every dense contraction of a tile is tcgen05.mma.kind::tf32 with the accumulator in TMEM and the A operand
 // written back to TMEM by the previous epilogue (tcgen05.st), i.e. A never touches shared memory:
@@ -27,9 +28,10 @@
 //
 // Reductions are deterministic (no atomics).  Rows of a tile with equal target are contiguous (CSR order), rows
 // with equal source are contiguous in the precomputed source-sorted permutation of the tile; one warp builds the
-// list of segment starts while the first MMA runs, then every segment is summed by exactly 16 threads (one per
-// column quad) in row order.  Target sums go straight to global memory (a row is complete unless it straddles a
-// tile boundary: then the next tile adds to it), source sums into a shared-memory table of the unit.
+// list of segment starts while the first MMA runs, then every segment is summed in a fixed order by a fixed set of
+// threads.  Target sums go straight to global memory (a row is complete unless it straddles a tile boundary: then
+// the next tile adds to it), source sums into a shared-memory table of the unit.  The reductions of tile t run
+// while the tensor pipe works on tile t+1.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -38,9 +40,7 @@ namespace gnnis {
 using namespace umma;
 
 constexpr int kTabLd = 68;        // padded row of the shared-memory node tables (bank spread for row-per-lane gathers)
-constexpr int kGroupThreads = 128;
 constexpr int kGroups = 2;
-constexpr int kSlots = 8;         // segments summed concurrently (x 16 column quads = 128 threads)
 
 struct EdgeTcArgs {
   int n_units, G, N, R;
@@ -60,8 +60,6 @@ struct EdgeTcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
-__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
-
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -115,16 +113,6 @@ __device__ __forceinline__ float4 silu_d4_fast(float x0, float x1, float x2, flo
   return make_float4(fmaf(s0, fmaf(-x0, s0, x0), s0), fmaf(s1, fmaf(-x1, s1, x1), s1), fmaf(s2, fmaf(-x2, s2, x2), s2),
                      fmaf(s3, fmaf(-x3, s3, x3), s3));
 }
-__device__ __forceinline__ void silu_fd_fast(float x, float& f, float& d) {
-  const float sg = sig_fast(x);
-  f = x * sg;
-  d = fmaf(f, 1.0f - sg, sg);              // sg (1 + x (1 - sg))
-}
-__device__ __forceinline__ float silu_d_fast(float x) {
-  const float sg = sig_fast(x);
-  return fmaf(sg, fmaf(-x, sg, x), sg);    // sg + sg x (1 - sg)
-}
-
 // stage a K-major B operand [rows][kdim] (element (n,k) = src[n*ld_n + k*ld_k], zero outside n_valid x k_valid)
 // as hi / lo TF32 parts in the SW128 layout
 __device__ __forceinline__ void stage_b_operand(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int rows,
@@ -201,22 +189,6 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
   tmem_st32(t_lo, l);
 }
 
-// group-wide row copies / zero fill of [nrows][64] blocks (16-byte vectors)
-__device__ __forceinline__ void copy_rows_grp(float* __restrict__ dst, int ld_dst, const float* __restrict__ src,
-                                              int ld_src, int nrows, int gt) {
-  for (int t = gt; t < nrows * 16; t += kGroupThreads) {
-    int r = t >> 4, c4 = t & 15;
-    *reinterpret_cast<float4*>(dst + (size_t)r * ld_dst + c4 * 4) =
-        *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c4 * 4);
-  }
-}
-__device__ __forceinline__ void zero_rows_grp(float* __restrict__ dst, int ld_dst, int nrows, int gt) {
-  for (int t = gt; t < nrows * 16; t += kGroupThreads) {
-    int r = t >> 4, c4 = t & 15;
-    *reinterpret_cast<float4*>(dst + (size_t)r * ld_dst + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
 // Per-tile keys (double-buffered by tile parity so that the reduction of tile t may overlap the set-up of t+1)
 struct TileKeys {
   int tgt[kTileE];        // unit-local target of row e (-1 past the end of the unit)
@@ -244,79 +216,6 @@ __device__ __forceinline__ int build_segments(const int* __restrict__ key, const
   }
   if (lane == 0) seg[base] = (uint8_t)n_valid;   // <= 128
   return base;
-}
-
-// Target-segment sums straight to global rows out[key][64]: segment s is summed by the 16 threads of slot s % 8.
-// A segment is stored (first touch of its row) unless it continues the last row of the previous tile (cont_prev,
-// segment 0 only), in which case it is added.  Rows without edges keep the zero written at the start of the unit.
-__device__ __forceinline__ void reduce_targets_global(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
-                                                      float* __restrict__ out, int gt) {
-  const int cq = gt & 15, slot = gt >> 4;
-  const int nseg = tk->n_seg_t;
-  for (int s = slot; s < nseg; s += kSlots) {
-    const int p0 = tk->seg_t[s], p1 = tk->seg_t[s + 1];
-    float4 run = make_float4(0.f, 0.f, 0.f, 0.f), run2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int p = p0;
-#pragma unroll 2
-    for (; p + 1 < p1; p += 2) {   // two interleaved partial sums, fixed order
-      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
-      const float4 w = *reinterpret_cast<const float4*>(sX + (p + 1) * kTileLd + 4 * cq);
-      run.x += v.x;
-      run.y += v.y;
-      run.z += v.z;
-      run.w += v.w;
-      run2.x += w.x;
-      run2.y += w.y;
-      run2.z += w.z;
-      run2.w += w.w;
-    }
-    if (p < p1) {
-      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
-      run.x += v.x;
-      run.y += v.y;
-      run.z += v.z;
-      run.w += v.w;
-    }
-    run.x += run2.x;
-    run.y += run2.y;
-    run.z += run2.z;
-    run.w += run2.w;
-    float4* dst = reinterpret_cast<float4*>(out + (size_t)tk->tgt[p0] * 64 + 4 * cq);
-    if (s == 0 && tk->cont_prev) {
-      float4 t = *dst;
-      run.x += t.x;
-      run.y += t.y;
-      run.z += t.z;
-      run.w += t.w;
-    }
-    *dst = run;
-  }
-}
-
-// Source-segment sums into table rows (shared memory or global): every distinct source of the tile is one segment,
-// so no two threads touch the same entry.
-__device__ __forceinline__ void reduce_sources_table(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
-                                                     float* __restrict__ table, int ld, int gt) {
-  const int cq = gt & 15, slot = gt >> 4;
-  const int nseg = tk->n_seg_s;
-  for (int s = slot; s < nseg; s += kSlots) {
-    const int p0 = tk->seg_s[s], p1 = tk->seg_s[s + 1];
-    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = p0; p < p1; ++p) {
-      const float4 v = *reinterpret_cast<const float4*>(sX + (int)tk->perm[p] * kTileLd + 4 * cq);
-      run.x += v.x;
-      run.y += v.y;
-      run.z += v.z;
-      run.w += v.w;
-    }
-    float4* dst = reinterpret_cast<float4*>(table + (size_t)tk->src[tk->perm[p0]] * ld + 4 * cq);
-    float4 t = *dst;
-    t.x += run.x;
-    t.y += run.y;
-    t.z += run.z;
-    t.w += run.w;
-    *dst = t;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------- self test
@@ -392,532 +291,6 @@ static size_t group_bytes(const Ctx* c, int ntables) {
 static size_t fwd_tc_smem(const Ctx* c) { return kFwdWeights + 256 + kGroups * group_bytes(c, 1) + 1024; }
 static size_t bwd_tc_smem(const Ctx* c) { return kBwdWeights + 256 + kGroups * group_bytes(c, 2) + 1024; }
 
-// ---------------------------------------------------------------------------------------------- forward
-// TMEM columns of a group: B0 64 | B1 64 | V hi 64 | V lo 64.  Tile t has u in B[t & 1]; w goes to the other buffer
-// (so the first K half of w may be issued while the second half of u is still being read); once u has been read
-// its buffer receives the radial basis (hi 32 | lo 32) of tile t+1, whose u lands in the buffer w has left.
-// Per tile t:  wait u(t) -> v half 0 -> issue w k[0,32) -> v half 1 -> issue w k[32,64) -> rbf(t+1) ->
-//              wait w(t) -> load w to registers -> issue u(t+1) -> z = silu(w + b2) -> segmented sums of tile t.
-// so the tensor pipe works on the second half of w while the first half of the next epilogue is computed, and u of
-// the next tile is produced under the second epilogue and the reduction.
-template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_fwd_tc_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
-  extern __shared__ uint8_t smraw[];
-  __shared__ uint64_t bars[kGroups];
-  __shared__ uint32_t tmem_slot;
-  uint32_t base = smem_u32(smraw);
-  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
-  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
-  float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = tid >> 7, gt = tid & 127, wq = warp & 3, row = gt;
-  uint8_t* gsm = sm + kFwdWeights + 256 + (size_t)grp * grp_bytes;
-  float* sZ = reinterpret_cast<float*>(gsm + kGrpX);
-  TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
-  float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
-
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-  }
-  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);     // B[n = c][k] = Wr[c][k]
-  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);         // B[n = c][k] = W2[c][k]
-  if (tid < 64) sb2[tid] = g.b2[tid];
-  fence_proxy_async_smem();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;            // this group's 256 columns
-  const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-  constexpr uint32_t VH = 128, VL = 192;
-  uint32_t cur = 0;   // buffer (column offset 0 or 64) holding u of the current tile
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
-  const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
-  uint64_t* bar = &bars[grp];
-  uint32_t phase = 0;
-  int parity = 0;
-
-  for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
-    const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
-    const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
-    const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
-    const float* gP = g.P + (size_t)atom0 * 64;
-    float* gA = g.a_out + (size_t)atom0 * 64;
-    const float* tQ;
-    int ld;
-    if (SMEM_TABLES) {
-      ld = kTabLd;
-      copy_rows_grp(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt);
-      tQ = sTab;
-    } else {
-      ld = 64;
-      tQ = g.Q + (size_t)atom0 * 64;
-    }
-    zero_rows_grp(gA, 64, natoms, gt);
-    if (e_begin >= e_end) {   // no edges in this unit
-      group_sync(grp);
-      continue;
-    }
-    // ---- prologue: keys, radial basis and u of the first tile; edge data of the second tile in flight
-    uint32_t pr = 0u, pr_n = 0u;
-    float r = 0.3f, r_n = 0.3f;
-    bool valid = e_begin + row < e_end;
-    if (valid) {
-      pr = g.pair[e_begin + row];
-      r = g.r_e[e_begin + row];
-    }
-    if (e_begin + kTileE + row < e_end) {
-      pr_n = g.pair[e_begin + kTileE + row];
-      r_n = g.r_e[e_begin + kTileE + row];
-    }
-    TileKeys* tk = keys + parity;
-    tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
-    prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64);
-    prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32);
-    {
-      float o[32], od[32];
-      rbf_regs<false>(r, g.inv_cutoff, o, od);
-      st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
-      tmem_st_wait();
-    }
-    fence_before_sync();
-    group_sync(grp);
-    if (gt == 0) {
-      fence_after_sync();
-      issue_gemm_3xtf32<0, 3>(tm + cur, tm + (cur ^ 64u), tm + (cur ^ 64u) + 32, aWrH, aWrL, 64, idesc64, 0u);
-      mma_commit(bar);
-    }
-
-    for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-      const bool has_next = t0 + kTileE < e_end;
-      const int tgc = valid ? (int)(pr >> 16) : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
-      if (wq == 1) {
-        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
-        if (lane == 0) {
-          tk->n_seg_t = ns;
-          tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
-        }
-      }
-      mbar_wait(bar, phase);
-      __syncwarp();
-      phase ^= 1;
-      fence_after_sync();
-      // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM, w issued in two K halves
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t ur[32];
-        tmem_ld32(lane_addr + cur + 32 * h, ur);
-        const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + 32 * h);
-        const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + 32 * h);
-        float4 p[8], q[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          p[j4] = __ldg(pp + j4);
-          q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
-        }
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          v[4 * j4 + 0] = silu_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x));
-          v[4 * j4 + 1] = silu_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y));
-          v[4 * j4 + 2] = silu_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z));
-          v[4 * j4 + 3] = silu_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
-        }
-        st_split(lane_addr + VH + 32 * h, lane_addr + VL + 32 * h, v);
-        tmem_st_wait();
-        fence_before_sync();
-        group_sync(grp);
-        if (gt == 0) {
-          fence_after_sync();
-          if (h == 0) {
-            issue_gemm_3xtf32<0, 4>(tm + (cur ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
-          } else {
-            issue_gemm_3xtf32<4, 8>(tm + (cur ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 1u);
-            mma_commit(bar);
-          }
-        }
-      }
-      // ---- look ahead: keys and radial basis of the next tile while w runs
-      TileKeys* tkn = keys + (parity ^ 1);
-      bool valid_n = false;
-      uint32_t pr_nn = 0u;
-      float r_nn = 0.3f;
-      if (has_next) {
-        valid_n = t0 + kTileE + row < e_end;
-        tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
-        const float* pn = gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64;
-        prefetch_l1(pn);
-        prefetch_l1(pn + 32);
-        if (t0 + 2 * kTileE + row < e_end) {
-          pr_nn = g.pair[t0 + 2 * kTileE + row];
-          r_nn = g.r_e[t0 + 2 * kTileE + row];
-        }
-        float o[32], od[32];
-        rbf_regs<false>(r_n, g.inv_cutoff, o, od);
-        st_split(lane_addr + cur, lane_addr + cur + 32, o);   // u of this tile has been consumed
-      }
-      mbar_wait(bar, phase);
-      __syncwarp();
-      phase ^= 1;
-      fence_after_sync();
-      // ---- w -> registers, then u of the next tile may overwrite the accumulator
-      uint32_t wr[64];
-      tmem_ld32(lane_addr + (cur ^ 64u), *reinterpret_cast<uint32_t(*)[32]>(&wr[0]));
-      tmem_ld32(lane_addr + (cur ^ 64u) + 32, *reinterpret_cast<uint32_t(*)[32]>(&wr[32]));
-      tmem_ld_wait();
-      if (has_next) {
-        tmem_st_wait();
-        fence_before_sync();
-        group_sync(grp);
-        if (gt == 0) {
-          fence_after_sync();
-          issue_gemm_3xtf32<0, 3>(tm + (cur ^ 64u), tm + cur, tm + cur + 32, aWrH, aWrL, 64, idesc64, 0u);
-          mma_commit(bar);
-        }
-      }
-      // ---- z = silu(w + b2) -> smem tile
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * h);
-        float4 b[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) b[j4] = bb[j4];
-        float4 z[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          z[j4].x = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 0]) + b[j4].x);
-          z[j4].y = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 1]) + b[j4].y);
-          z[j4].z = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 2]) + b[j4].z);
-          z[j4].w = silu_fast(__uint_as_float(wr[32 * h + 4 * j4 + 3]) + b[j4].w);
-        }
-        float* zrow = sZ + row * kTileLd + 32 * h;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(zrow + 4 * j4) = z[j4];
-      }
-      group_sync(grp);
-      // ---- a[tgt] += z
-      reduce_targets_global(sZ, tk, gA, gt);
-      // no barrier here: the next tile uses the other TileKeys buffer and rewrites sZ only after two more barriers
-      pr = pr_n;
-      r = r_n;
-      valid = valid_n;
-      pr_n = pr_nn;
-      r_n = r_nn;
-      tk = tkn;
-      parity ^= 1;
-      cur ^= 64u;
-    }
-    group_sync(grp);   // all rows of the unit written before its tables are replaced
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_slot, 512);
-}
-
-// ---------------------------------------------------------------------------------------------- adjoint
-// TMEM columns of a group: ACC (u, then w, then vbar) 64 | DU (d u / d r) 64 | X hi 64 | X lo 64, where X holds the
-// A operands in turn: rbf | drbf (32 + 32 columns), v, wbar.
-// Per tile t:  wait u, du -> v -> issue w -> wait w -> wbar -> issue vbar -> wait vbar ->
-//              ubar = vbar silu'(u), rbar = ubar . du -> rbf, drbf (t+1) -> issue u, du (t+1) -> segmented sums of t.
-template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(kGroups * kGroupThreads, 1) edge_bwd_tc_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
-  extern __shared__ uint8_t smraw[];
-  __shared__ uint64_t bars[kGroups];
-  __shared__ uint32_t tmem_slot;
-  uint32_t base = smem_u32(smraw);
-  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
-  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
-  uint8_t *sW2tH = sm + 49152, *sW2tL = sm + 65536;
-  float* sb2 = reinterpret_cast<float*>(sm + kBwdWeights);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = tid >> 7, gt = tid & 127, wq = warp & 3, row = gt;
-  uint8_t* gsm = sm + kBwdWeights + 256 + (size_t)grp * grp_bytes;
-  float* sU = reinterpret_cast<float*>(gsm + kGrpX);
-  TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
-  float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
-
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-  }
-  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);      // u, du : B[n = c ][k    ] = Wr[c][k]
-  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);          // w     : B[n = c ][k    ] = W2[c][k]
-  stage_b_operand(sW2tH, sW2tL, g.W2_t, 64, 64, 64, 64, 64, 1);      // vbar  : B[n = k'][k = c] = W2[c][k'] = W2_t[k'][c]
-  if (tid < 64) sb2[tid] = g.b2[tid];
-  fence_proxy_async_smem();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
-  const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-  constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
-  const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
-  const uint32_t aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
-  uint64_t* bar = &bars[grp];
-  uint32_t phase = 0;
-  int parity = 0;
-
-  for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
-    const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
-    const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
-    const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
-    const float* gP = g.P + (size_t)atom0 * 64;
-    const float* gAb = g.abar + (size_t)atom0 * 64;
-    float* gPb = g.Pbar + (size_t)atom0 * 64;
-    const float* tQ;
-    float* tQb;
-    int ld;
-    if (SMEM_TABLES) {
-      ld = kTabLd;
-      tQb = sTab + g.unit_atoms * kTabLd;
-      copy_rows_grp(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt);
-      tQ = sTab;
-    } else {
-      ld = 64;
-      tQ = g.Q + (size_t)atom0 * 64;
-      tQb = g.Qbar + (size_t)atom0 * 64;
-    }
-    zero_rows_grp(gPb, 64, natoms, gt);
-    zero_rows_grp(tQb, ld, natoms, gt);
-    if (e_begin >= e_end) {
-      group_sync(grp);
-      if (SMEM_TABLES) {
-        copy_rows_grp(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt);
-        group_sync(grp);
-      }
-      continue;
-    }
-    // ---- prologue: keys, rbf / drbf and u / du of the first tile; edge data of the second tile in flight
-    uint32_t pr = 0u, pr_n = 0u;
-    float r = 0.3f, r_n = 0.3f;
-    uint8_t pm = (uint8_t)row, pm_n = (uint8_t)row;
-    bool valid = e_begin + row < e_end;
-    if (valid) {
-      pr = g.pair[e_begin + row];
-      r = g.r_e[e_begin + row];
-      pm = g.perm[e_begin + row];
-    }
-    if (e_begin + kTileE + row < e_end) {
-      pr_n = g.pair[e_begin + kTileE + row];
-      r_n = g.r_e[e_begin + kTileE + row];
-      pm_n = g.perm[e_begin + kTileE + row];
-    }
-    TileKeys* tk = keys + parity;
-    tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
-    tk->src[row] = valid ? (int)(pr & 0xFFFFu) : -1;
-    tk->perm[row] = pm;
-    {
-      const size_t t_ = (size_t)(valid ? (pr >> 16) : 0u) * 64;
-      prefetch_l1(gP + t_);
-      prefetch_l1(gP + t_ + 32);
-      prefetch_l1(gAb + t_);
-      prefetch_l1(gAb + t_ + 32);
-      float o[32], od[32];
-      rbf_regs<true>(r, g.inv_cutoff, o, od);
-      st_split(lane_addr + XH, lane_addr + XL, o);
-      st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
-      tmem_st_wait();
-    }
-    fence_before_sync();
-    group_sync(grp);
-    if (gt == 0) {
-      fence_after_sync();
-      issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
-      issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
-      mma_commit(bar);
-    }
-
-    for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-      const bool has_next = t0 + kTileE < e_end;
-      const int tg = valid ? (int)(pr >> 16) : -1, tgc = valid ? tg : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
-      if (wq == 1) {
-        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
-        if (lane == 0) {
-          tk->n_seg_t = ns;
-          tk->cont_prev = (t0 > e_begin && keys[parity ^ 1].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
-        }
-      } else if (wq == 2) {
-        const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, min(kTileE, e_end - t0), lane);
-        if (lane == 0) tk->n_seg_s = ns;
-      }
-      mbar_wait(bar, phase);
-      __syncwarp();
-      phase ^= 1;
-      fence_after_sync();
-      // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM ; keep silu'(u); w issued in two K halves
-      float dsu[64];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t ur[32];
-        tmem_ld32(lane_addr + ACC + 32 * h, ur);
-        const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + 32 * h);
-        const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + 32 * h);
-        float4 p[8], q[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          p[j4] = __ldg(pp + j4);
-          q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
-        }
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x), v[4 * j4 + 0], dsu[32 * h + 4 * j4 + 0]);
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y), v[4 * j4 + 1], dsu[32 * h + 4 * j4 + 1]);
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z), v[4 * j4 + 2], dsu[32 * h + 4 * j4 + 2]);
-          silu_fd_fast(__uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w), v[4 * j4 + 3], dsu[32 * h + 4 * j4 + 3]);
-        }
-        st_split(lane_addr + XH + 32 * h, lane_addr + XL + 32 * h, v);
-      }
-      tmem_st_wait();
-      fence_before_sync();
-      group_sync(grp);
-      if (gt == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2H, aW2L, 64, idesc64, 0u);
-        mma_commit(bar);
-      }
-      mbar_wait(bar, phase);
-      __syncwarp();
-      phase ^= 1;
-      fence_after_sync();
-      // ---- wbar = abar[tgt] * silu'(w + b2) -> TMEM ; vbar issued in two K halves
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t wr[32];
-        tmem_ld32(lane_addr + ACC + 32 * h, wr);
-        const float4* ab = reinterpret_cast<const float4*>(gAb + (size_t)tgc * 64 + 32 * h);
-        const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * h);
-        float4 a[8], b[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          a[j4] = __ldg(ab + j4);
-          b[j4] = bb[j4];
-        }
-        tmem_ld_wait();
-        float wb[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          wb[4 * j4 + 0] = a[j4].x * silu_d_fast(__uint_as_float(wr[4 * j4 + 0]) + b[j4].x);
-          wb[4 * j4 + 1] = a[j4].y * silu_d_fast(__uint_as_float(wr[4 * j4 + 1]) + b[j4].y);
-          wb[4 * j4 + 2] = a[j4].z * silu_d_fast(__uint_as_float(wr[4 * j4 + 2]) + b[j4].z);
-          wb[4 * j4 + 3] = a[j4].w * silu_d_fast(__uint_as_float(wr[4 * j4 + 3]) + b[j4].w);
-        }
-        st_split(lane_addr + XH + 32 * h, lane_addr + XL + 32 * h, wb);
-      }
-      tmem_st_wait();
-      fence_before_sync();
-      group_sync(grp);
-      if (gt == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, aW2tH, aW2tL, 64, idesc64, 0u);
-        mma_commit(bar);
-      }
-      // edge data of the tile after next (registers), while vbar runs
-      TileKeys* tkn = keys + (parity ^ 1);
-      bool valid_n = false;
-      uint32_t pr_nn = 0u;
-      float r_nn = 0.3f;
-      uint8_t pm_nn = (uint8_t)row;
-      if (has_next) {
-        valid_n = t0 + kTileE + row < e_end;
-        tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
-        tkn->src[row] = valid_n ? (int)(pr_n & 0xFFFFu) : -1;
-        tkn->perm[row] = valid_n ? pm_n : (uint8_t)row;
-        const size_t t_ = (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64;
-        prefetch_l1(gP + t_);
-        prefetch_l1(gP + t_ + 32);
-        prefetch_l1(gAb + t_);
-        prefetch_l1(gAb + t_ + 32);
-        if (t0 + 2 * kTileE + row < e_end) {
-          pr_nn = g.pair[t0 + 2 * kTileE + row];
-          r_nn = g.r_e[t0 + 2 * kTileE + row];
-          pm_nn = g.perm[t0 + 2 * kTileE + row];
-        }
-      }
-      mbar_wait(bar, phase);
-      __syncwarp();
-      phase ^= 1;
-      fence_after_sync();
-      // ---- ubar = vbar * silu'(u) -> smem tile ; rbar = ubar . du
-      float racc = 0.0f;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t vr[32], dr[32];
-        tmem_ld32(lane_addr + ACC + 32 * h, vr);
-        tmem_ld32(lane_addr + DU + 32 * h, dr);
-        tmem_ld_wait();
-        float4 ub[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          ub[j4].x = __uint_as_float(vr[4 * j4 + 0]) * dsu[32 * h + 4 * j4 + 0];
-          ub[j4].y = __uint_as_float(vr[4 * j4 + 1]) * dsu[32 * h + 4 * j4 + 1];
-          ub[j4].z = __uint_as_float(vr[4 * j4 + 2]) * dsu[32 * h + 4 * j4 + 2];
-          ub[j4].w = __uint_as_float(vr[4 * j4 + 3]) * dsu[32 * h + 4 * j4 + 3];
-        }
-        float ra = 0.0f, rb = 0.0f;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          ra = fmaf(ub[j4].x, __uint_as_float(dr[4 * j4 + 0]), ra);
-          rb = fmaf(ub[j4].y, __uint_as_float(dr[4 * j4 + 1]), rb);
-          ra = fmaf(ub[j4].z, __uint_as_float(dr[4 * j4 + 2]), ra);
-          rb = fmaf(ub[j4].w, __uint_as_float(dr[4 * j4 + 3]), rb);
-        }
-        racc += ra + rb;
-        float* urow = sU + row * kTileLd + 32 * h;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(urow + 4 * j4) = ub[j4];
-      }
-      if (valid) {
-        int repl = tg / g.N;
-        size_t slot = ((size_t)atom0 + tg) * g.N + (sr - repl * g.N);
-        g.rbar[slot] = g.rbar_accumulate ? g.rbar[slot] + racc : racc;
-      }
-      // ---- rbf / drbf of the next tile, u / du issued under the reductions of this one
-      if (has_next) {
-        float o[32], od[32];
-        rbf_regs<true>(r_n, g.inv_cutoff, o, od);
-        st_split(lane_addr + XH, lane_addr + XL, o);
-        st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
-        tmem_st_wait();
-      }
-      fence_before_sync();
-      group_sync(grp);
-      if (has_next && gt == 0) {
-        fence_after_sync();
-        issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
-        issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
-        mma_commit(bar);
-      }
-      reduce_targets_global(sU, tk, gPb, gt);            // Pbar[tgt] += ubar
-      reduce_sources_table(sU, tk, tQb, ld, gt);         // Qbar[src] += ubar
-      pr = pr_n;
-      r = r_n;
-      pm = pm_n;
-      valid = valid_n;
-      pr_n = pr_nn;
-      r_n = r_nn;
-      pm_n = pm_nn;
-      tk = tkn;
-      parity ^= 1;
-    }
-    group_sync(grp);
-    if (SMEM_TABLES) {
-      copy_rows_grp(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt);
-      group_sync(grp);
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_slot, 512);
-}
-
 // ---------------------------------------------------------------------------------------------- launchers
 static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   EdgeTcArgs g{};
@@ -950,37 +323,6 @@ bool tc_path_fits(const Ctx* c) { return fwd_tc_smem(c) <= 227 * 1024 && bwd_tc_
 static int tc_grid(const Ctx* c) {
   int want = (c->n_units + kGroups - 1) / kGroups;
   return want < c->num_sms ? want : c->num_sms;
-}
-
-int launch_edge_fwd_tc(Ctx* c, int l, cudaStream_t st) {
-  EdgeTcArgs g = make_tc_args(c, l);
-  size_t smem = fwd_tc_smem(c);
-  uint32_t gb = (uint32_t)group_bytes(c, 1);
-  if (c->smem_tables) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_tc_kernel<true><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
-  } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_tc_kernel<false><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
-  }
-  GNNIS_LAUNCH_CHECK();
-  return 0;
-}
-
-int launch_edge_bwd_tc(Ctx* c, int l, int rbar_accumulate, cudaStream_t st) {
-  EdgeTcArgs g = make_tc_args(c, l);
-  g.rbar_accumulate = rbar_accumulate;
-  size_t smem = bwd_tc_smem(c);
-  uint32_t gb = (uint32_t)group_bytes(c, 2);
-  if (c->smem_tables) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_tc_kernel<true><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
-  } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_tc_kernel<false><<<tc_grid(c), kGroups * kGroupThreads, smem, st>>>(g, gb);
-  }
-  GNNIS_LAUNCH_CHECK();
-  return 0;
 }
 
 // ================================================================================================================
@@ -1433,227 +775,6 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
-// ---------------------------------------------------------------------------------------------- forward (ws)
-template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(kWsThreads, 1) edge_fwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
-  extern __shared__ uint8_t smraw[];
-  __shared__ WsBars bars;
-  __shared__ uint32_t tmem_slot;
-  uint32_t base = smem_u32(smraw);
-  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
-  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
-  float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) {
-    for (int i = 0; i < kGroups; ++i) {
-      mbar_init(&bars.d_full[i], 1);
-      mbar_init(&bars.a_full[i], 8);
-      bars.cnt_a[i] = 0;
-      bars.cnt_u[i] = 0;
-    }
-  }
-  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);
-  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);
-  if (tid < 64) sb2[tid] = g.b2[tid];
-  fence_proxy_async_smem();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  constexpr uint32_t VH = 128, VL = 192;
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
-
-  {
-    const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
-    uint8_t* gsm = sm + kFwdWeights + 256 + (size_t)grp * grp_bytes;
-    float* sZ = reinterpret_cast<float*>(gsm + kGrpX);
-    TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
-    float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
-    const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
-    const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-    uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp];
-    int *cnt_a = &bars.cnt_a[grp], *cnt_u = &bars.cnt_u[grp];
-    const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
-    // u of the tile whose accumulator is B[c]: A = rbf in B[c ^ 64]
-    auto issue_u = [&](uint32_t c) {
-      if (elect_one()) {
-        issue_gemm_3xtf32<0, 3>(tm + c, tm + (c ^ 64u), tm + (c ^ 64u) + 32, aWrH, aWrL, 64, idesc64, 0u);
-        mma_commit(d_full);
-      }
-      __syncwarp();
-    };
-    auto issue_w = [&](uint32_t c) {
-      if (elect_one()) {
-        issue_gemm_3xtf32<0, 8>(tm + (c ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
-        mma_commit(d_full);
-      }
-      __syncwarp();
-    };
-    uint32_t ph_d = 0, ph_a = 0, cur = 0;
-    int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
-
-    for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
-      const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
-      const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
-      const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
-      const float* gP = g.P + (size_t)atom0 * 64;
-      float* gA = g.a_out + (size_t)atom0 * 64;
-      const float* tQ;
-      int ld;
-      if (SMEM_TABLES) {
-        ld = kTabLd;
-        copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
-        tQ = sTab;
-      } else {
-        ld = 64;
-        tQ = g.Q + (size_t)atom0 * 64;
-      }
-      zero_rows_n(gA, 64, natoms, gt, kWsGroupThreads);
-      if (e_begin >= e_end) {
-        ws_group_sync(grp);
-        continue;
-      }
-      // ---- prologue: keys + radial basis of the first tile; edge data of the second tile in flight
-      uint32_t pr = 0u, pr_n = 0u;
-      float r = 0.3f, r_n = 0.3f;
-      bool valid = e_begin + row < e_end;
-      if (valid) {
-        pr = g.pair[e_begin + row];
-        if (ch == 0) r = g.r_e[e_begin + row];
-      }
-      if (e_begin + kTileE + row < e_end) {
-        pr_n = g.pair[e_begin + kTileE + row];
-        if (ch == 0) r_n = g.r_e[e_begin + kTileE + row];
-      }
-      TileKeys* tk = keys + kidx;
-      if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
-      prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
-      if (warp_arrive_last(cnt_u, 12, lane)) issue_u(cur);     // accumulators are free
-      if (ch == 0) {
-        float o[32], od[32];
-        rbf_regs<false>(r, g.inv_cutoff, o, od);
-        st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
-        tmem_st_wait();
-        if (warp_arrive_last(cnt_u, 12, lane)) issue_u(cur);
-      }
-      ws_group_sync(grp);                            // tables + keys of the first tile visible
-
-      for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-        const bool has_next = t0 + kTileE < e_end;
-        const int tgc = valid ? (int)(pr >> 16) : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
-        if (w8 == 4) {
-          const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
-          if (lane == 0) {
-            tk->n_seg_t = ns;
-            tk->cont_prev = (t0 > e_begin && keys[(kidx + 2) % 3].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
-          }
-        }
-        mbar_wait(d_full, ph_d);
-        __syncwarp();
-        ph_d ^= 1u;
-        fence_after_sync();
-        // ---- v = silu(u + P[tgt] + Q[src]) -> TMEM (this thread's 32 channels, two chunks of 16)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = 32 * ch + 16 * c;
-          uint32_t ur[16];
-          tmem_ld16(lane_addr + cur + col0, ur);
-          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + col0);
-          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
-          float4 p[4], q[4];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            p[j4] = __ldg(pp + j4);
-            q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
-          }
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 y = silu4_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x),
-                                        __uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y),
-                                        __uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z),
-                                        __uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
-            v[4 * j4 + 0] = y.x;
-            v[4 * j4 + 1] = y.y;
-            v[4 * j4 + 2] = y.z;
-            v[4 * j4 + 3] = y.w;
-          }
-          st_split16(lane_addr + VH + col0, lane_addr + VL + col0, v);
-        }
-        tmem_st_wait();
-        {
-          const bool last = warp_arrive_last(cnt_a, 8, lane);
-          warp_arrive_mbar(a_full, lane);          // lets the rbf writers below know that u has been read by everyone
-          if (last) issue_w(cur);
-        }
-        // ---- look ahead: keys / radial basis of the next tile while w runs
-        TileKeys* tkn = keys + (kidx + 1) % 3;
-        bool valid_n = false;
-        uint32_t pr_nn = 0u;
-        float r_nn = 0.3f;
-        if (has_next) {
-          valid_n = t0 + kTileE + row < e_end;
-          if (ch == 0) tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
-          prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
-          if (t0 + 2 * kTileE + row < e_end) {
-            pr_nn = g.pair[t0 + 2 * kTileE + row];
-            if (ch == 0) r_nn = g.r_e[t0 + 2 * kTileE + row];
-          }
-          if (ch == 0) {
-            float o[32], od[32];
-            rbf_regs<false>(r_n, g.inv_cutoff, o, od);
-            mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
-            __syncwarp();
-            st_split(lane_addr + cur, lane_addr + cur + 32, o);
-            tmem_st_wait();
-            if (warp_arrive_last(cnt_u, 12, lane)) issue_u(cur ^ 64u);
-          }
-        }
-        ph_a ^= 1u;
-        // ---- a[tgt] += z of the PREVIOUS tile while the tensor pipe works on w of this one
-        if (t0 > e_begin) reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);
-        mbar_wait(d_full, ph_d);
-        __syncwarp();
-        ph_d ^= 1u;
-        fence_after_sync();
-        // ---- w -> registers; the accumulator may then be overwritten by u of the next tile
-        uint32_t wr[32];
-        tmem_ld32(lane_addr + (cur ^ 64u) + 32 * ch, wr);
-        tmem_ld_wait();
-        if (has_next && warp_arrive_last(cnt_u, 12, lane)) issue_u(cur ^ 64u);
-        ws_group_sync(grp);                          // (A) the reduction of the previous tile is complete
-        {
-          const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * ch);
-          float* zrow = sZ + row * kTileLd + 32 * ch;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = bb[j4];
-            const float4 z = silu4_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x, __uint_as_float(wr[4 * j4 + 1]) + b.y,
-                                        __uint_as_float(wr[4 * j4 + 2]) + b.z, __uint_as_float(wr[4 * j4 + 3]) + b.w);
-            *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
-          }
-        }
-        ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
-        pr = pr_n;
-        r = r_n;
-        valid = valid_n;
-        pr_n = pr_nn;
-        r_n = r_nn;
-        tk = tkn;
-        kidx = (kidx + 1) % 3;
-        cur ^= 64u;
-      }
-      reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);   // last tile of the unit
-      ws_group_sync(grp);   // all rows of the unit written before its tables are replaced
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_slot, 512);
-}
-
 // ---------------------------------------------------------------------------------------------- adjoint (ws)
 template <bool SMEM_TABLES>
 __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
@@ -1978,21 +1099,11 @@ int launch_edge_fwd_ws(Ctx* c, int l, cudaStream_t st) {
   size_t smem = fwd_tc_smem(c);
   uint32_t gb = (uint32_t)group_bytes(c, 1);
   if (c->smem_tables) {
-    if (c->tc_mask & 32) {
-      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      edge_fwd_ws_kernel<true><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
-    } else {
-      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      edge_fwd_wsi_kernel<true><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
-    }
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_wsi_kernel<true><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
   } else {
-    if (c->tc_mask & 32) {
-      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      edge_fwd_ws_kernel<false><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
-    } else {
-      GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      edge_fwd_wsi_kernel<false><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
-    }
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_wsi_kernel<false><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
   }
   GNNIS_LAUNCH_CHECK();
   return 0;

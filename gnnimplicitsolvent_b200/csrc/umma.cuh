@@ -94,15 +94,6 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// MN-major operand, 128-byte swizzle (cute::UMMA canonical ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 4 fp32):
-// for one k, 32 consecutive n are contiguous (128 B); 8 k-rows form a 1024-B atom (SBO = 1024 B between k-groups);
-// 32-wide n panels are `lbo_bytes` apart.  A matrix staged K-major with sw128_offset(n', k', rows) is, byte for
-// byte, the MN-major operand with (n, k) = (k', n') and LBO = rows * 128.  `addr` = panel base + 1024 * (k / 8).
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
-         (1ull << 46) | (2ull << 61);
-}
-constexpr uint32_t kIdescBMajorMN = 1u << 16;   // instruction-descriptor bit: B operand is MN-major
 // kind::tf32, fp32 accumulate, A and B K-major, M x N tile
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
