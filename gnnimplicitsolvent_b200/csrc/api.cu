@@ -25,6 +25,8 @@ int launch_node_pre1(Ctx*, cudaStream_t);
 int launch_node_fwd(Ctx*, int, cudaStream_t);
 int launch_node_bwd(Ctx*, int, cudaStream_t);
 int launch_node_fwd_tc(Ctx*, int, cudaStream_t);
+int build_edge_images(Ctx*, cudaStream_t);
+int build_node_images(Ctx*, cudaStream_t);
 int launch_node_bwd_tc(Ctx*, int, cudaStream_t);
 int launch_node_pre1_bwd(Ctx*, cudaStream_t);
 int launch_gb_only_head(Ctx*, cudaStream_t);
@@ -242,6 +244,7 @@ int gnnis_destroy(gnnis_handle h) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   dev_free(&c->wblob);
+  dev_free(&c->img);
   float** f[] = {&c->q, &c->rho, &c->s, &c->alpha, &c->beta, &c->gamma, &c->d0, &c->m0, &c->pref, &c->r_e, &c->born,
                  &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->abar, &c->Pbar, &c->Qbar, &c->rbar, &c->e_atom,
                  &c->sa_atom, &c->h_pos_dev, &c->h_e_dev, &c->h_f_dev, &c->bond_r0, &c->bond_k, &c->lb_S, &c->lb_Y,
@@ -370,6 +373,21 @@ int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w) {
     L.W2 = c->wblob + o.W2;
     L.W3a = c->wblob + o.W3a;
     L.W4 = c->wblob + o.W4;
+  }
+  // tensor-core operand images (zero-filled: the padded K columns of Wr stay zero)
+  {
+    const size_t per_layer = 81920 + 196608 + 131072 + 131072;
+    if (dev_alloc(c, &c->img, 3 * per_layer)) return -1;
+    GNNIS_CUDA_OK(cudaMemset(c->img, 0, 3 * per_layer));
+    for (int l = 0; l < 3; ++l) {
+      uint8_t* base = c->img + (size_t)l * per_layer;
+      c->img_edge[l] = base;
+      c->img_nf[l] = base + 81920;
+      c->img_nba[l] = base + 81920 + 196608;
+      c->img_nbb[l] = base + 81920 + 196608 + 131072;
+    }
+    if (build_edge_images(c, 0) || build_node_images(c, 0)) return -1;
+    GNNIS_CUDA_OK(cudaDeviceSynchronize());
   }
   // gamma table is a view into the blob; keep a separate pointer that destroy() must not free twice
   c->gamma_emb = nullptr;

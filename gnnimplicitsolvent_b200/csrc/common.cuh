@@ -70,6 +70,13 @@ struct Ctx {
   float* gamma_emb = nullptr;  // [S]
   float fraction = 0.1f, scaling = 2.0f, cutoff = 0.6f;
   float* wblob = nullptr;  // one allocation backing all weight matrices
+  // tensor-core operand images: the exact shared-memory bytes (hi | lo TF32 parts, K-major 128B swizzle) of the B
+  // operands of every tcgen05 kernel, built once when the weights are loaded; kernels copy them with 16-byte loads
+  uint8_t* img = nullptr;
+  uint8_t *img_edge[3] = {nullptr, nullptr, nullptr};   // 80 KB: Wr | W2 | W2^T        (forward uses the first 48 KB)
+  uint8_t *img_nf[3] = {nullptr, nullptr, nullptr};     // 192 KB: W3a | W4 | [Wi;Wj]    (last layer: first 64 KB)
+  uint8_t *img_nba[3] = {nullptr, nullptr, nullptr};    // 128 KB: [Wi;Wj]^T | W4^T      (layers 1, 2)
+  uint8_t *img_nbb[3] = {nullptr, nullptr, nullptr};    // 128 KB: W3a | W3a^T
   // system
   int N = 0, U = 0;
   float *q = nullptr, *rho = nullptr, *s = nullptr, *alpha = nullptr, *beta = nullptr, *gamma = nullptr;

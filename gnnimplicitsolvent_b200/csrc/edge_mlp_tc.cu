@@ -48,8 +48,8 @@ struct EdgeTcArgs {
   const uint32_t* pair;
   const float* r_e;
   float inv_cutoff;
-  const float *Wr, *W2, *b2;   // torch layout [64][20], [64][64]
-  const float* W2_t;           // [64][64] transposed
+  const uint8_t* img;          // operand image: WrH 8K | WrL 8K | W2H 16K | W2L 16K | W2tH 16K | W2tL 16K
+  const float* b2;
   const float *P, *Q;
   float* a_out;
   const float* abar;
@@ -145,6 +145,31 @@ __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi
       acc = 1;
     }
   }
+}
+// the same staging into a GLOBAL image (built once per weight load): block (n0.., k0..) of an operand with rows_total
+// rows, element (n0 + n, k0 + k) = src[n * ld_n + k]
+__global__ void build_operand_image_kernel(uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                                           const float* __restrict__ src, int rows_total, int n0, int nrows, int k0,
+                                           int kcount, int ld_n) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nrows * kcount; t += gridDim.x * blockDim.x) {
+    int n = t / kcount, k = t - n * kcount;
+    uint32_t h, l;
+    split_tf32(src[(size_t)n * ld_n + k], h, l);
+    uint32_t off = sw128_offset(n0 + n, k0 + k, rows_total);
+    *reinterpret_cast<uint32_t*>(hi + off) = h;
+    *reinterpret_cast<uint32_t*>(lo + off) = l;
+  }
+}
+int launch_build_operand(Ctx* c, uint8_t* hi, uint8_t* lo, const float* src, int rows_total, int n0, int nrows, int k0,
+                         int kcount, int ld_n, cudaStream_t st) {
+  build_operand_image_kernel<<<32, 256, 0, st>>>(hi, lo, src, rows_total, n0, nrows, k0, kcount, ld_n);
+  GNNIS_LAUNCH_CHECK();
+  return 0;
+}
+// block-wide copy of a prebuilt operand image into shared memory (16-byte vectors)
+__device__ __forceinline__ void copy_image(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int bytes) {
+  for (int t = threadIdx.x * 16; t < bytes; t += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(dst + t) = __ldg(reinterpret_cast<const uint4*>(src + t));
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -302,9 +327,7 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   g.pair = c->pair;
   g.r_e = c->r_e;
   g.inv_cutoff = (float)(1.0 / (double)c->cutoff);
-  g.Wr = c->L[l].Wr;
-  g.W2 = c->L[l].W2;
-  g.W2_t = c->L[l].W2_t;
+  g.img = c->img_edge[l];
   g.b2 = c->L[l].b2;
   g.P = c->P[l];
   g.Q = c->Q[l];
@@ -316,6 +339,17 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   g.perm = c->perm;
   g.unit_atoms = c->G * c->N;
   return g;
+}
+
+int build_edge_images(Ctx* c, cudaStream_t st) {
+  for (int l = 0; l < 3; ++l) {
+    uint8_t* im = c->img_edge[l];
+    if (launch_build_operand(c, im, im + 8192, c->L[l].Wr, 64, 0, 64, 0, kRbf, kRbf, st) ||
+        launch_build_operand(c, im + 16384, im + 32768, c->L[l].W2, 64, 0, 64, 0, 64, 64, st) ||
+        launch_build_operand(c, im + 49152, im + 65536, c->L[l].W2_t, 64, 0, 64, 0, 64, 64, st))
+      return -1;
+  }
+  return 0;
 }
 
 bool tc_path_fits(const Ctx* c) { return fwd_tc_smem(c) <= 227 * 1024 && bwd_tc_smem(c) <= 227 * 1024; }
@@ -549,8 +583,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       mbar_init(&bars.u_ok[i], 12);
     }
   }
-  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);
-  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);
+  copy_image(sm, g.img, kFwdWeights);   // B[n = c][k] = Wr[c][k] and W2[c][k], hi | lo
   if (tid < 64) sb2[tid] = g.b2[tid];
   fence_proxy_async_smem();
   fence_before_sync();
@@ -798,9 +831,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       bars.cnt_u[i] = 0;
     }
   }
-  stage_b_operand(sWrH, sWrL, g.Wr, 64, 32, 64, kRbf, kRbf, 1);
-  stage_b_operand(sW2H, sW2L, g.W2, 64, 64, 64, 64, 64, 1);
-  stage_b_operand(sW2tH, sW2tL, g.W2_t, 64, 64, 64, 64, 64, 1);
+  copy_image(sm, g.img, kBwdWeights);   // Wr, W2 as above and B[n = k'][k = c] = W2[c][k'] for vbar
   if (tid < 64) sb2[tid] = g.b2[tid];
   fence_proxy_async_smem();
   fence_before_sync();

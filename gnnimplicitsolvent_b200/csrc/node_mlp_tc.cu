@@ -18,14 +18,16 @@ namespace gnnis {
 
 using namespace umma;
 
+int launch_build_operand(Ctx*, uint8_t*, uint8_t*, const float*, int, int, int, int, int, int, cudaStream_t);
+
 constexpr int kNtThreads = 256;
 constexpr int kNtRows = 128;
 
 struct NodeTcArgs {
   int n, N;
   const int* solvent_id;
-  const float *a, *W3a, *W3a_t, *sbias, *W4, *W4_t, *b4;
-  const float *Wi_next, *Wj_next, *Wi_t_next, *Wj_t_next, *b1_next;
+  const float *a, *sbias, *W4, *b4, *b1_next;
+  const uint8_t* img;   // operand image of this kernel (see Ctx::img_*)
   float *o, *P_next, *Q_next;
   // head
   const float *born, *rho, *gamma_emb;
@@ -53,18 +55,9 @@ __device__ __forceinline__ float nt_silu_d(float x) {
   return fmaf(sg, fmaf(-x, sg, x), sg);
 }
 
-// stage the block (n0.., k0..) of a K-major SW128 operand with `rows_total` rows: element (n0+n, k0+k) = src[n*ld_n + k]
-__device__ __forceinline__ void nt_stage(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int rows_total, int n0,
-                                         int nrows, int k0, int kcount, int ld_n) {
-  for (int t = threadIdx.x; t < nrows * kcount; t += blockDim.x) {
-    int n = t / kcount, k = t - n * kcount;
-    float v = src[(size_t)n * ld_n + k];
-    uint32_t h, l;
-    split_tf32(v, h, l);
-    uint32_t off = sw128_offset(n0 + n, k0 + k, rows_total);
-    *reinterpret_cast<uint32_t*>(hi + off) = h;
-    *reinterpret_cast<uint32_t*>(lo + off) = l;
-  }
+__device__ __forceinline__ void nt_copy_image(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int bytes) {
+  for (int t = threadIdx.x * 16; t < bytes; t += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(dst + t) = __ldg(reinterpret_cast<const uint4*>(src + t));
 }
 
 // D[128 x N] = A[128 x 8 KSTEPS] * B^T (3xTF32), A in TMEM, B K-major SW128 with b_rows rows
@@ -162,12 +155,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
   uint8_t *sWpH = sm + 131072, *sWpL = sm + 163840;
   float* sHead = reinterpret_cast<float*>(sm + (LAST ? 65536 : 196608));   // [128][2] partial head sums
-  nt_stage(sW3H, sW3L, g.W3a, 128, 0, 128, 0, 64, 64);
-  if (!LAST) {
-    nt_stage(sW4H, sW4L, g.W4, 64, 0, 64, 0, 128, 128);
-    nt_stage(sWpH, sWpL, g.Wi_next, 128, 0, 64, 0, 64, 64);
-    nt_stage(sWpH, sWpL, g.Wj_next, 128, 64, 64, 0, 64, 64);
-  }
+  nt_copy_image(sm, g.img, LAST ? 65536 : 196608);
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aW3H = smem_u32(sW3H), aW3L = smem_u32(sW3L), aW4H = smem_u32(sW4H), aW4L = smem_u32(sW4L);
@@ -279,9 +267,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
 __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sWpH = sm, *sWpL = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
-  nt_stage(sWpH, sWpL, g.Wi_t_next, 64, 0, 64, 0, 64, 64);     // B[n = c_in][k = c_out] = Wi[c_out][c_in]
-  nt_stage(sWpH, sWpL, g.Wj_t_next, 64, 0, 64, 64, 64, 64);
-  nt_stage(sW4H, sW4L, g.W4_t, 128, 0, 128, 0, 64, 64);        // B[n = m][k = c] = W4[c][m]
+  nt_copy_image(sm, g.img, 131072);   // B[n = c_in][k = c_out] = Wi|Wj[c_out][c_in] ; B[n = m][k = c] = W4[c][m]
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aWpH = smem_u32(sWpH), aWpL = smem_u32(sWpL), aW4H = smem_u32(sW4H), aW4L = smem_u32(sW4L);
@@ -342,8 +328,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
   NT_PROLOGUE();
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sWtH = sm + 65536, *sWtL = sm + 98304;
   float* sHead = reinterpret_cast<float*>(sm + 131072);   // [128][2] (cbar, sbar)
-  nt_stage(sW3H, sW3L, g.W3a, 128, 0, 128, 0, 64, 64);
-  nt_stage(sWtH, sWtL, g.W3a_t, 64, 0, 64, 0, 128, 128);      // B[n = k_in][k = m] = W3a[m][k_in]
+  nt_copy_image(sm, g.img, 131072);   // B[n = m][k] = W3a[m][k] ; B[n = k_in][k = m] = W3a[m][k_in]
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aW3H = smem_u32(sW3H), aW3L = smem_u32(sW3L), aWtH = smem_u32(sWtH), aWtL = smem_u32(sWtL);
@@ -432,19 +417,12 @@ static NodeTcArgs nt_args(Ctx* c, int l) {
   g.solvent_id = c->solvent_id;
   g.a = c->a[l];
   g.o = c->o[l];
-  g.W3a = c->L[l].W3a;
-  g.W3a_t = c->L[l].W3a_t;
   g.sbias = c->L[l].sbias;
   g.W4 = c->L[l].W4;
-  g.W4_t = c->L[l].W4_t;
   g.b4 = c->L[l].b4;
   if (l < 2) {
     g.P_next = c->P[l + 1];
     g.Q_next = c->Q[l + 1];
-    g.Wi_next = c->L[l + 1].Wi;
-    g.Wj_next = c->L[l + 1].Wj;
-    g.Wi_t_next = c->L[l + 1].Wi_t;
-    g.Wj_t_next = c->L[l + 1].Wj_t;
     g.b1_next = c->L[l + 1].b1;
   }
   g.born = c->born;
@@ -468,8 +446,33 @@ static int nt_grid(const Ctx* c) {
   return ntiles < c->num_sms ? ntiles : c->num_sms;
 }
 
+int build_node_images(Ctx* c, cudaStream_t st) {
+  for (int l = 0; l < 3; ++l) {
+    const LayerW& L = c->L[l];
+    uint8_t* f = c->img_nf[l];
+    if (launch_build_operand(c, f, f + 32768, L.W3a, 128, 0, 128, 0, 64, 64, st)) return -1;
+    if (l < 2) {
+      const LayerW& Ln = c->L[l + 1];
+      uint8_t* a = c->img_nba[l];
+      if (launch_build_operand(c, f + 65536, f + 98304, L.W4, 64, 0, 64, 0, 128, 128, st) ||
+          launch_build_operand(c, f + 131072, f + 163840, Ln.Wi, 128, 0, 64, 0, 64, 64, st) ||
+          launch_build_operand(c, f + 131072, f + 163840, Ln.Wj, 128, 64, 64, 0, 64, 64, st) ||
+          launch_build_operand(c, a, a + 32768, Ln.Wi_t, 64, 0, 64, 0, 64, 64, st) ||
+          launch_build_operand(c, a, a + 32768, Ln.Wj_t, 64, 0, 64, 64, 64, 64, st) ||
+          launch_build_operand(c, a + 65536, a + 98304, L.W4_t, 128, 0, 128, 0, 64, 64, st))
+        return -1;
+    }
+    uint8_t* b = c->img_nbb[l];
+    if (launch_build_operand(c, b, b + 32768, L.W3a, 128, 0, 128, 0, 64, 64, st) ||
+        launch_build_operand(c, b + 65536, b + 98304, L.W3a_t, 64, 0, 64, 0, 128, 128, st))
+      return -1;
+  }
+  return 0;
+}
+
 int launch_node_fwd_tc(Ctx* c, int l, cudaStream_t st) {
   NodeTcArgs g = nt_args(c, l);
+  g.img = c->img_nf[l];
   if (l == 2) {
     size_t smem = 65536 + 1024 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -486,11 +489,13 @@ int launch_node_fwd_tc(Ctx* c, int l, cudaStream_t st) {
 int launch_node_bwd_tc(Ctx* c, int l, cudaStream_t st) {
   NodeTcArgs g = nt_args(c, l);
   if (l < 2) {
+    g.img = c->img_nba[l];
     size_t smem = 131072 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_bwd_a_tc_kernel<<<nt_grid(c), kNtThreads, smem, st>>>(g);
     GNNIS_LAUNCH_CHECK();
   }
+  g.img = c->img_nbb[l];
   size_t smem = 131072 + 1024 + 1024;
   if (l == 2) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_b_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
