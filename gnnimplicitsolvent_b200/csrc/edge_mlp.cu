@@ -557,9 +557,69 @@ static EdgeArgs make_args(Ctx* c, int l) {
   return g;
 }
 
+// Same permutation by a counting sort over the (<= 128) unit-local source indices: warps take their rows in
+// order, __match_any_sync groups equal sources inside a warp, so the rank inside a bin follows the edge order.
+__global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, int G, int N, int R,
+                                                                 const int* __restrict__ row_ptr,
+                                                                 const uint32_t* __restrict__ pair,
+                                                                 uint8_t* __restrict__ perm) {
+  __shared__ int bins[128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int rep0 = unit * G, rep1 = min(R, rep0 + G);
+    const int atom0 = rep0 * N, natoms = (rep1 - rep0) * N;
+    const int e_begin = row_ptr[atom0], e_end = row_ptr[atom0 + natoms];
+    for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
+      const int e = t0 + tid;
+      const bool valid = e < e_end;
+      const int key = valid ? (int)(pair[e] & 0xFFFFu) : 0;
+      bins[tid] = 0;
+      __syncthreads();
+      int in_bin = 0;   // rows of this tile with the same source that come before this one
+      for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+          const unsigned act = __ballot_sync(0xffffffffu, valid);
+          if (valid) {
+            const unsigned peers = __match_any_sync(act, key);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) {
+              base = bins[key];
+              bins[key] = base + __popc(peers);
+            }
+            base = __shfl_sync(peers, base, leader);
+            in_bin = base + __popc(peers & ((1u << lane) - 1u));
+          }
+        }
+        __syncthreads();
+      }
+      // exclusive scan of the 128 bin counts (warp 0: 4 bins per lane)
+      if (warp == 0) {
+        int c0 = bins[4 * lane], c1 = bins[4 * lane + 1], c2 = bins[4 * lane + 2], c3 = bins[4 * lane + 3];
+        int tot = c0 + c1 + c2 + c3, inc = tot;
+        for (int off = 1; off < 32; off <<= 1) {
+          int v = __shfl_up_sync(0xffffffffu, inc, off);
+          if (lane >= off) inc += v;
+        }
+        int ex = inc - tot;
+        bins[4 * lane] = ex;
+        bins[4 * lane + 1] = ex + c0;
+        bins[4 * lane + 2] = ex + c0 + c1;
+        bins[4 * lane + 3] = ex + c0 + c1 + c2;
+      }
+      __syncthreads();
+      if (valid) perm[t0 + bins[key] + in_bin] = (uint8_t)tid;
+      __syncthreads();
+    }
+  }
+}
+
 int launch_tile_perm(Ctx* c, cudaStream_t st) {
   int grid = c->n_units < 8 * c->num_sms ? c->n_units : 8 * c->num_sms;
-  tile_perm_kernel<<<grid, kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
+  if (c->G * c->N <= 128)
+    tile_perm_count_kernel<<<grid, kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
+  else
+    tile_perm_kernel<<<grid, kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
   GNNIS_LAUNCH_CHECK();
   return 0;
 }
