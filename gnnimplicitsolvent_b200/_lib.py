@@ -24,6 +24,18 @@ class GnnisWeights(C.Structure):
     ]
 
 
+class GnnisForcefield(C.Structure):
+    _fields_ = [
+        ("n_bonds", C.c_int32), ("bond_idx", c_int32_p), ("bond_r0", c_float_p), ("bond_k", c_float_p),
+        ("n_angles", C.c_int32), ("angle_idx", c_int32_p), ("angle_theta0", c_float_p), ("angle_k", c_float_p),
+        ("n_torsions", C.c_int32), ("torsion_idx", c_int32_p), ("torsion_periodicity", c_int32_p),
+        ("torsion_phase", c_float_p), ("torsion_k", c_float_p),
+        ("charge", c_float_p), ("sigma", c_float_p), ("epsilon", c_float_p),
+        ("n_exceptions", C.c_int32), ("exception_idx", c_int32_p), ("exception_chargeprod", c_float_p),
+        ("exception_sigma", c_float_p), ("exception_epsilon", c_float_p),
+    ]
+
+
 # every symbol include/gnnis.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gnnis_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -40,6 +52,7 @@ SIGNATURES = {
     "gnnis_get_atom_energies": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnis_get_born_radii": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnis_last_edge_count": (C.c_int, [C.c_void_p, c_int64_p, C.c_void_p]),
+    "gnnis_set_forcefield": (C.c_int, [C.c_void_p, C.POINTER(GnnisForcefield)]),
     "gnnis_set_bonds": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p, c_float_p, c_float_p]),
     "gnnis_minimize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int32_p, C.c_float, C.c_int32,
                                  C.c_int32, C.c_uint32, C.c_void_p]),
@@ -55,6 +68,7 @@ SIGNATURES = {
 
 FLAG_DELTA, FLAG_NO_FORCES, FLAG_GB_ONLY, FLAG_MLP_BF16, FLAG_MLP_CUDA_CORES = 0x1, 0x2, 0x4, 0x8, 0x10
 FLAG_DATA_PREDICATE = 0x20
+FLAG_VACUUM_ONLY = 0x40
 
 _lib = None
 

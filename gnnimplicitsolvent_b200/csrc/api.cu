@@ -32,6 +32,7 @@ int launch_node_pre1_bwd(Ctx*, cudaStream_t);
 int launch_gb_only_head(Ctx*, cudaStream_t);
 int launch_add_vec(Ctx*, int, const float*, float*, cudaStream_t);
 int launch_bond_forces(Ctx*, const float*, float*, float*, cudaStream_t);
+int launch_mm_forces(Ctx*, const float*, float*, float*, int, cudaStream_t);
 
 static std::string g_create_err;
 
@@ -137,6 +138,20 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
                       StageTimer* tm) {
   const bool gb_only = flags & GNNIS_FLAG_GB_ONLY;
   const bool want_grad = !(flags & GNNIS_FLAG_NO_FORCES);
+  if (flags & GNNIS_FLAG_VACUUM_ONLY) {
+    if (c->N <= 0 || c->R <= 0 || !c->have_ff) {
+      c->err = "GNNIS_FLAG_VACUUM_ONLY needs gnnis_set_system, gnnis_set_replicas and gnnis_set_forcefield";
+      return -1;
+    }
+    if (want_grad && !force) {
+      c->err = "force_dev is NULL but GNNIS_FLAG_NO_FORCES is not set";
+      return -1;
+    }
+    GNNIS_CUDA_OK(cudaSetDevice(c->device));
+    if (launch_mm_forces(c, pos, e_rep, want_grad ? force : nullptr, 0, st)) return -1;
+    if (c->n_bonds > 0 && launch_bond_forces(c, pos, e_rep, want_grad ? force : nullptr, st)) return -1;
+    return 0;
+  }
   const int delta = (flags & GNNIS_FLAG_DELTA) ? 1 : 0;
   const int predicate = (flags & GNNIS_FLAG_DATA_PREDICATE) ? 1 : 0;
   if (check_ready(c, !gb_only)) return -1;
@@ -190,8 +205,10 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     if (tm) tm->mark(kStBornAdjoint);
     if (launch_born_adjoint(c, pos, gb_only ? 0 : 1, force, st)) return -1;
     if (c->n_bonds > 0 && launch_bond_forces(c, pos, e_rep, force, st)) return -1;
-  } else if (c->n_bonds > 0) {
-    if (launch_bond_forces(c, pos, e_rep, nullptr, st)) return -1;
+    if (c->have_ff && launch_mm_forces(c, pos, e_rep, force, 1, st)) return -1;
+  } else {
+    if (c->n_bonds > 0 && launch_bond_forces(c, pos, e_rep, nullptr, st)) return -1;
+    if (c->have_ff && launch_mm_forces(c, pos, e_rep, nullptr, 1, st)) return -1;
   }
   if (tm) tm->mark(-1);
   return 0;
@@ -257,6 +274,19 @@ int gnnis_destroy(gnnis_handle h) {
     dev_free(&c->a[l]);
     dev_free(&c->o[l]);
   }
+  cudaFree(c->ff_excl);
+  cudaFree(c->ff_bond);
+  cudaFree(c->ff_angle);
+  cudaFree(c->ff_tors);
+  cudaFree(c->ff_exc);
+  cudaFree(c->ff_bond_p);
+  cudaFree(c->ff_angle_p);
+  cudaFree(c->ff_tors_p);
+  cudaFree(c->ff_exc_p);
+  float** fff[] = {&c->ff_charge, &c->ff_sigma, &c->ff_epsilon};
+  for (float** p : fff) dev_free(p);
+  dev_free(&c->ff_term_ptr);
+  dev_free(&c->ff_term_ref);
   int** ip[] = {&c->radidx, &c->solvent_id, &c->deg, &c->row_ptr, &c->blk_sum, &c->col, &c->bond_idx, &c->lb_state,
                 &c->lb_count, &c->lb_active};
   for (int** p : ip) dev_free(p);

@@ -112,6 +112,14 @@ struct Ctx {
   int n_bonds = 0;
   int* bond_idx = nullptr;
   float *bond_r0 = nullptr, *bond_k = nullptr;
+  // vacuum force field (forcefield.cu)
+  bool have_ff = false;
+  float *ff_charge = nullptr, *ff_sigma = nullptr, *ff_epsilon = nullptr;
+  uint32_t* ff_excl = nullptr;
+  int *ff_term_ptr = nullptr, *ff_term_ref = nullptr;
+  int4 *ff_bond = nullptr, *ff_angle = nullptr, *ff_tors = nullptr, *ff_exc = nullptr;
+  float2 *ff_bond_p = nullptr, *ff_angle_p = nullptr;
+  float4 *ff_tors_p = nullptr, *ff_exc_p = nullptr;
   // dynamics workspace
   size_t dyn_atoms = 0;
   int dyn_hist = 0;

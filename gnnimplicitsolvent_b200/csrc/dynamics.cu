@@ -138,7 +138,17 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
     }
     accept = true;
   } else {
-    accept = finite && (et <= a.e[r] + 1e-4f * step * a.gd[r]);
+    // Armijo decrease, or -- when the energy difference is below the fp32 resolution of the summed energy -- the
+    // approximate Wolfe conditions of Hager & Zhang: energy not higher than the noise allows and the directional
+    // derivative reduced, sigma phi'(0) <= phi'(step) <= (2 delta - 1) phi'(0)
+    float gtd = 0.f;
+    for (int t = threadIdx.x; t < D; t += kLbThreads) gtd += -ft[t] * d[t];
+    gtd = block_sum(gtd, red);
+    const float e0 = a.e[r], gd0 = a.gd[r];
+    const float noise = 2e-6f * fabsf(e0) + 1e-3f;
+    const bool armijo = et <= e0 + 1e-4f * step * gd0;
+    const bool approx_wolfe = et <= e0 + noise && gtd >= 0.9f * gd0 && gtd <= -0.9998f * gd0;
+    accept = finite && (armijo || approx_wolfe);
   }
 
   if (accept) {

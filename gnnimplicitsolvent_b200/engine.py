@@ -121,6 +121,51 @@ class Engine:
         self.n_rep = int(n_rep)
         self._host = None
 
+    def set_forcefield(self, ff: Optional[dict]):
+        """Vacuum MM terms: dict with `bonds` (idx [B,2], r0, k), `angles` (idx [A,3], theta0, k),
+        `torsions` (idx [T,4], periodicity, phase, k), `charge`, `sigma`, `epsilon` [N] and `exceptions`
+        (idx [X,2], chargeprod, sigma, epsilon) -- the parameters of an OpenMM System's HarmonicBond / HarmonicAngle /
+        PeriodicTorsion / NonbondedForce.  None removes the force field."""
+        if ff is None:
+            self._check(self.lib.gnnis_set_forcefield(self._h, None))
+            return
+        s = _lib.GnnisForcefield()
+        keep = []
+
+        def ints(a, w):
+            a = np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1, w))
+            keep.append(a)
+            return a, a.ctypes.data_as(_lib.c_int32_p)
+
+        def flt(a):
+            a = _f32(a).reshape(-1)
+            keep.append(a)
+            return _fp(a)
+
+        b = ff.get("bonds", {"idx": np.zeros((0, 2)), "r0": [], "k": []})
+        a = ff.get("angles", {"idx": np.zeros((0, 3)), "theta0": [], "k": []})
+        t = ff.get("torsions", {"idx": np.zeros((0, 4)), "periodicity": [], "phase": [], "k": []})
+        x = ff.get("exceptions", {"idx": np.zeros((0, 2)), "chargeprod": [], "sigma": [], "epsilon": []})
+        bi, s.bond_idx = ints(b["idx"], 2)
+        s.n_bonds, s.bond_r0, s.bond_k = bi.shape[0], flt(b["r0"]), flt(b["k"])
+        ai, s.angle_idx = ints(a["idx"], 3)
+        s.n_angles, s.angle_theta0, s.angle_k = ai.shape[0], flt(a["theta0"]), flt(a["k"])
+        ti, s.torsion_idx = ints(t["idx"], 4)
+        per = np.ascontiguousarray(np.asarray(t["periodicity"], dtype=np.int32).reshape(-1))
+        keep.append(per)
+        s.n_torsions, s.torsion_periodicity = ti.shape[0], per.ctypes.data_as(_lib.c_int32_p)
+        s.torsion_phase, s.torsion_k = flt(t["phase"]), flt(t["k"])
+        for name in ("charge", "sigma", "epsilon"):
+            arr = _f32(ff[name]).reshape(-1)
+            if arr.size != self.n_atoms:
+                raise ValueError(f"forcefield['{name}'] needs one value per atom")
+            keep.append(arr)
+            setattr(s, name, _fp(arr))
+        xi, s.exception_idx = ints(x["idx"], 2)
+        s.n_exceptions = xi.shape[0]
+        s.exception_chargeprod, s.exception_sigma, s.exception_epsilon = flt(x["chargeprod"]), flt(x["sigma"]), flt(x["epsilon"])
+        self._check(self.lib.gnnis_set_forcefield(self._h, C.byref(s)))
+
     def set_bonds(self, idx, r0, k):
         idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int32).reshape(-1, 2))
         r0, k = _f32(r0).reshape(-1), _f32(k).reshape(-1)
@@ -128,7 +173,7 @@ class Engine:
 
     # ------------------------------------------------------------------ hot path
     def energy_force(self, positions: torch.Tensor, *, delta=False, forces=True, gb_only=False, cuda_cores=False,
-                     data_predicate=False, out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
+                     data_predicate=False, vacuum_only=False, out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
         """positions [R,N,3] (or [R*N,3]) fp32 on the engine's device -> (E[R], F[R,N,3] or None)."""
         p = self._pos(positions)
         e = out_energy if out_energy is not None else torch.empty(self.n_rep, dtype=torch.float32, device=self.device)
@@ -137,7 +182,7 @@ class Engine:
             f = out_force if out_force is not None else torch.empty_like(p)
         flags = ((_lib.FLAG_DELTA if delta else 0) | (0 if forces else _lib.FLAG_NO_FORCES)
                  | (_lib.FLAG_GB_ONLY if gb_only else 0) | (_lib.FLAG_MLP_CUDA_CORES if cuda_cores else 0)
-                 | (_lib.FLAG_DATA_PREDICATE if data_predicate else 0))
+                 | (_lib.FLAG_DATA_PREDICATE if data_predicate else 0) | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0))
         self._check(self.lib.gnnis_energy_force(self._h, p.data_ptr(), e.data_ptr(), f.data_ptr() if forces else None,
                                                 flags, self._stream()))
         return e, f

@@ -166,3 +166,85 @@ SOLVENT_DIELECTRICS = [
     35.6, 29.6, 4.5, 20.18, 2.03, 13.26, 7.52, 6.20, 43.3, 37.27, 6.10, 32.55, 10.3, 2.024, 46.53, 2.24,
     7.30, 26.74, 9.22, 2.104, 29.7, 25.9, 2.56,
 ]  # Simulation/solvents.yml:2-40, indexed by solvent_id 0..38
+
+
+# GAFF-like Lennard-Jones parameters (sigma nm, epsilon kJ/mol) per element of the synthetic molecules
+LJ = {"H": (0.2650, 0.0657), "HN": (0.1069, 0.0657), "C": (0.3400, 0.4577), "N": (0.3250, 0.7113),
+      "O": (0.2960, 0.8786), "S": (0.3564, 1.0460)}
+
+
+def synth_forcefield(mol, coulomb14=1.0 / 1.2, lj14=0.5):
+    """A complete vacuum force field for a `synth_molecule`, in the layout of an OpenMM System built by OpenFF
+    (HarmonicBondForce, HarmonicAngleForce, PeriodicTorsionForce, NonbondedForce with 1-2 / 1-3 exclusions and scaled
+    1-4 exceptions; reference: Simulation/Simulator.py:2036-2143 for how the non-bonded part is re-expressed).
+    Equilibrium values are the base geometry's; force constants are typical small-molecule values."""
+    pos, elements, bonds = mol["pos"], mol["elements"], [tuple(b) for b in mol["bonds"]]
+    n = len(elements)
+    nbrs = {i: [] for i in range(n)}
+    for i, j in bonds:
+        nbrs[i].append(j)
+        nbrs[j].append(i)
+    dist = lambda a, b: float(np.linalg.norm(pos[a] - pos[b]))
+    b_idx = np.array(bonds, dtype=np.int32).reshape(-1, 2)
+    b_r0 = np.array([dist(i, j) for i, j in bonds], dtype=np.float32)
+    b_k = np.array([3.0e5 if elements[i].startswith("H") or elements[j].startswith("H") else 2.5e5 for i, j in bonds],
+                   dtype=np.float32)
+    a_idx, a_t0 = [], []
+    for j in range(n):
+        nb = sorted(nbrs[j])
+        for x in range(len(nb)):
+            for y in range(x + 1, len(nb)):
+                i, k = nb[x], nb[y]
+                u, v = pos[i] - pos[j], pos[k] - pos[j]
+                c = float(np.dot(u, v) / (np.linalg.norm(u) * np.linalg.norm(v)))
+                a_idx.append((i, j, k))
+                a_t0.append(np.arccos(np.clip(c, -1.0, 1.0)))
+    t_idx, t_n, t_ph, t_k = [], [], [], []
+    for (j, k) in bonds:
+        for i in sorted(nbrs[j]):
+            if i == k:
+                continue
+            for l in sorted(nbrs[k]):
+                if l == j or l == i:
+                    continue
+                t_idx.append((i, j, k, l))
+                if len(t_idx) % 3 == 0:
+                    t_n.append(2), t_ph.append(np.pi), t_k.append(2.0)
+                else:
+                    t_n.append(3), t_ph.append(0.0), t_k.append(0.6)
+    # topological distances for the exception list
+    sep = np.full((n, n), 99, dtype=np.int64)
+    for s in range(n):
+        sep[s, s] = 0
+        frontier = [s]
+        d = 0
+        while frontier and d < 3:
+            d += 1
+            nxt = []
+            for u in frontier:
+                for v in nbrs[u]:
+                    if sep[s, v] > d:
+                        sep[s, v] = d
+                        nxt.append(v)
+            frontier = nxt
+    q = np.asarray(mol["params"][:, 0], dtype=np.float64)
+    sig = np.array([LJ[e][0] for e in elements])
+    eps = np.array([LJ[e][1] for e in elements])
+    x_idx, x_qq, x_s, x_e = [], [], [], []
+    for i in range(n):
+        for j in range(i + 1, n):
+            if sep[i, j] in (1, 2):
+                x_idx.append((i, j)), x_qq.append(0.0), x_s.append(0.5 * (sig[i] + sig[j])), x_e.append(0.0)
+            elif sep[i, j] == 3:
+                x_idx.append((i, j)), x_qq.append(coulomb14 * q[i] * q[j])
+                x_s.append(0.5 * (sig[i] + sig[j])), x_e.append(lj14 * np.sqrt(eps[i] * eps[j]))
+    f32 = lambda a: np.asarray(a, dtype=np.float32)
+    return {
+        "bonds": {"idx": b_idx, "r0": b_r0, "k": b_k},
+        "angles": {"idx": np.array(a_idx, dtype=np.int32).reshape(-1, 3), "theta0": f32(a_t0), "k": f32([400.0] * len(a_idx))},
+        "torsions": {"idx": np.array(t_idx, dtype=np.int32).reshape(-1, 4), "periodicity": np.array(t_n, dtype=np.int32),
+                     "phase": f32(t_ph), "k": f32(t_k)},
+        "charge": f32(q), "sigma": f32(sig), "epsilon": f32(eps),
+        "exceptions": {"idx": np.array(x_idx, dtype=np.int32).reshape(-1, 2), "chargeprod": f32(x_qq), "sigma": f32(x_s),
+                       "epsilon": f32(x_e)},
+    }

@@ -31,6 +31,8 @@ typedef struct gnnis_ctx* gnnis_handle;
 #define GNNIS_FLAG_MLP_BF16 0x8u   /* reserved: bf16-operand edge MLP (not built; returns -3)             */
 #define GNNIS_FLAG_DATA_PREDICATE 0x20u /* GNN graph by torch_cluster.radius_graph semantics, sum((x_i-x_j)^2) < r^2
                                       (data path, GNN_Models.py:345-357), instead of eps-distance r < cutoff */
+#define GNNIS_FLAG_VACUUM_ONLY 0x40u  /* only the vacuum force field of gnnis_set_forcefield (no GB, no GNN): the
+                                      reference's vacuum "_ref_system" simulation                          */
 #define GNNIS_FLAG_MLP_CUDA_CORES 0x10u /* force the fp32 CUDA-core edge kernels instead of the default
                                       tcgen05 tensor-core kernels (3xTF32, fp32-accurate)                 */
 
@@ -100,6 +102,37 @@ int gnnis_get_atom_energies(gnnis_handle h, float* e_atom_dev, float* sa_atom_de
 int gnnis_get_born_radii(gnnis_handle h, float* born_dev, float* born_scaled_dev, void* stream);
 /* number of GNN edges found by the LAST evaluation (synchronises the stream) */
 int gnnis_last_edge_count(gnnis_handle h, int64_t* n_edges_host, void* stream);
+
+/* Vacuum molecular-mechanics terms added to every evaluation: what OpenMM evaluates next to the
+ * GNN in the reference's replicated system (Simulation/Simulator.py:1597-1634, 2036-2143).  All arrays are host
+ * pointers, per MOLECULE (every replica uses the same terms); units nm, kJ/mol, rad, e.
+ *   bonds      0.5 k (r - r0)^2                       HarmonicBondForce
+ *   angles     0.5 k (theta - theta0)^2               HarmonicAngleForce (theta at the middle atom)
+ *   torsions   k (1 + cos(n phi - phase))             PeriodicTorsionForce (phi: IUPAC dihedral of i-j-k-l)
+ *   charge, sigma, epsilon [N]                        NonbondedForce particles -> Custom_electrostatic
+ *                                                     (q_i q_j 138.935456 / r) + Custom_lennard_jones
+ *                                                     (Lorentz-Berthelot), all non-excepted pairs, no cutoff
+ *   exceptions (i, j, chargeprod, sigma, epsilon)     NonbondedForce exceptions: the pair is removed from the two
+ *                                                     sums and gets 4 eps ((s/r)^12 - (s/r)^6) + chargeprod 138.935456 / r
+ *                                                     (Custom_exception_force_with_scale; zero parameters = plain exclusion)
+ * Pass NULL to remove the force field again. */
+typedef struct gnnis_forcefield {
+  int32_t n_bonds;
+  const int32_t* bond_idx;        /* [n_bonds][2] */
+  const float *bond_r0, *bond_k;
+  int32_t n_angles;
+  const int32_t* angle_idx;       /* [n_angles][3] */
+  const float *angle_theta0, *angle_k;
+  int32_t n_torsions;
+  const int32_t* torsion_idx;     /* [n_torsions][4] */
+  const int32_t* torsion_periodicity;
+  const float *torsion_phase, *torsion_k;
+  const float *charge, *sigma, *epsilon;   /* [n_atoms] */
+  int32_t n_exceptions;
+  const int32_t* exception_idx;   /* [n_exceptions][2] */
+  const float *exception_chargeprod, *exception_sigma, *exception_epsilon;
+} gnnis_forcefield;
+int gnnis_set_forcefield(gnnis_handle h, const gnnis_forcefield* ff);
 
 /* Batched per-replica L-BFGS (replaces simulation.minimizeEnergy(tolerance, maxIterations) driven by
  * OpenMM's LocalEnergyMinimizer, helper_functions.py:614-624; semantics differ by design: one optimiser
