@@ -46,3 +46,49 @@ def neck_tables(unique_radii=DEFAULT_UNIQUE_RADII):
                              + whi[i] * wlo[j] * t[hi[i], lo[j]] + whi[i] * whi[j] * t[hi[i], hi[j]])
         out[key] = res.reshape(-1).astype(np.float32)
     return out["d0"], out["m0"], n
+
+
+# GBn2 per-element standard parameters: (radius nm, screen, alpha, beta, gamma).  Restated from OpenMM 8.0.0
+# `openmm.app.internal.customgbforces` (GBSAGBn2Force.getStandardParameters: mbondi3 radii for small molecules =
+# mbondi2, hydrogens bonded to nitrogen 0.13 nm), which the reference calls at MachineLearning/GNN_Trainer.py:854-857.
+# UNPINNED: OpenMM is absent here; verify where it is installed before relying on elements beyond H, C, N, O, S.
+GBN2_ELEMENT = {
+    "H": (0.12, 1.425952, 0.788440, 0.798699, 0.437334),
+    "C": (0.17, 1.058554, 0.733756, 0.506378, 0.205844),
+    "N": (0.155, 0.733599, 0.503364, 0.316828, 0.192915),
+    "O": (0.15, 1.061039, 0.867814, 0.876635, 0.387882),
+    "F": (0.15, 0.5, 1.0, 0.8, 4.851),
+    "Si": (0.21, 0.5, 1.0, 0.8, 4.851),
+    "P": (0.185, 0.5, 1.0, 0.8, 4.851),
+    "S": (0.18, -0.703469, 0.867814, 0.876635, 0.387882),
+    "Cl": (0.17, 0.5, 1.0, 0.8, 4.851),
+}
+
+
+def gbneck2_parameters(elements, bonds, charges, unique_radii=DEFAULT_UNIQUE_RADII):
+    """The [N,7] parameter table of the run models, `[q, rho, s, alpha, beta, gamma, radindex]`, from element symbols,
+    the bond list (for the H-on-N radius) and partial charges -- what Trainer.get_gbneck2_param_small_molecules
+    (MachineLearning/GNN_Trainer.py:829-869) extracts from an OpenMM system:
+        rho = radius - 0.0195141 (:865-866), s = screen * rho (:867),
+        radindex = position of the RAW radius in `unique_radii` in the order GIVEN (:861-864) -- for the default list
+        that is the unsorted order of GNN_Models.py:38, the quirk the shipped weights were used with.
+    Returns (params float64 [N,7], unique_radii)."""
+    n = len(elements)
+    nbr_n = [False] * n
+    for i, j in bonds:
+        if elements[j] == "N":
+            nbr_n[i] = True
+        if elements[i] == "N":
+            nbr_n[j] = True
+    out = np.zeros((n, 7), dtype=np.float64)
+    lookup = {float("%.4f" % r): k for k, r in enumerate(unique_radii)}
+    for i, el in enumerate(elements):
+        radius, screen, a, b, g = GBN2_ELEMENT[el]
+        if el == "H" and nbr_n[i]:
+            radius = 0.13
+        key = float("%.4f" % radius)
+        if key not in lookup:
+            raise KeyError(f"radius {radius} of element {el} is not in unique_radii")
+        rho = radius - OFFSET
+        out[i] = [charges[i], rho, screen * rho, a, b, g, lookup[key]]
+    return out, list(unique_radii)

@@ -155,3 +155,16 @@ def test_data_model_vs_oracle(weights):
     e1, _ = model_nb(data)
     assert e1.shape == (1, 1)
     assert abs(float(e1) - float(o["energy_total"])) <= E_RTOL * abs(float(o["energy_total"]))
+
+
+def test_gbneck2_parameter_table_layout():
+    """N2: [q, rho, s, alpha, beta, gamma, radindex] with rho = r - 0.0195141, s = screen * rho and the UNSORTED
+    radindex of the default unique-radii list (GNN_Trainer.py:861-867; carbon 0.17 -> index 7)."""
+    from gnnimplicitsolvent_b200 import gbneck, synth
+    mol = synth.synth_molecule(21, seed=3)
+    els = ["H" if e == "HN" else e for e in mol["elements"]]
+    p, radii = gbneck.gbneck2_parameters(els, mol["bonds"], mol["params"][:, 0])
+    np.testing.assert_allclose(p, mol["params"], rtol=0, atol=1e-12)        # the synthetic generator follows the same rules
+    c = els.index("C")
+    assert p[c, 6] == 7 and abs(p[c, 1] - (0.17 - 0.0195141)) < 1e-12 and abs(p[c, 2] - 1.058554 * p[c, 1]) < 1e-12
+    assert radii == gbneck.DEFAULT_UNIQUE_RADII
