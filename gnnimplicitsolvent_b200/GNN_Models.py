@@ -78,10 +78,9 @@ class _Interaction(torch.nn.Module):
 class GNN3_Multisolvent_embedding(torch.nn.Module):
     """Data-path model (GNN_Models.py:326-498): forward(data) -> (energy [1,1] or [B,1], forces [n,3]).
 
-    `data` needs `.pos [n,3]`, `.atom_features [n,7]`, `.batch [n]`, `.solvent_model_tensor [n]`,
-    `.solvent_dielectric [n]`.  Graphs of one call must be conformers of ONE molecule (equal atom count and
-    identical atom_features per graph): the engine keeps one parameter table per handle.  Ragged batches
-    (a13 in SURVEY.md §8) are not built yet and raise NotImplementedError."""
+    `data` needs `.pos [n,3]`, `.atom_features [n,7]`, `.batch [n]` (sorted), `.solvent_model_tensor [n]`,
+    `.solvent_dielectric [n]`.  Ragged batches of different molecules (a13 in SURVEY.md §8) are evaluated molecule
+    by molecule: graphs sharing atom count and atom_features form one batched engine call."""
 
     _gb_only = False
     _data_predicate = True     # torch_cluster.radius_graph semantics for the GNN graph (GNN_Models.py:345-357)
@@ -126,6 +125,7 @@ class GNN3_Multisolvent_embedding(torch.nn.Module):
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._weights_dirty = True
+        self.__dict__["_weights_version"] = self.__dict__.get("_weights_version", 0) + 1
         return out
 
     def _engine_ready(self, parameters=None) -> Engine:
@@ -162,31 +162,68 @@ class GNN3_Multisolvent_embedding(torch.nn.Module):
 
     # ------------------------------------------------------------------ data path
     def forward(self, data):
+        """Ragged PyG-style batches are supported by grouping the graphs by molecule (identical atom count and
+        atom_features): each group is one batched evaluation on an engine cached for that molecule."""
         pos = data.pos
         n = pos.shape[0]
         batch = getattr(data, "batch", None)
         if batch is None:
             batch = torch.zeros(n, dtype=torch.int64)
-        b = batch.detach().cpu().numpy()
-        n_graphs = int(b.max()) + 1 if n else 0
-        if n_graphs < 1 or n % n_graphs != 0 or not np.array_equal(b, np.repeat(np.arange(n_graphs), n // n_graphs)):
-            raise NotImplementedError("data batches must be R contiguous graphs of equal size (ragged batches: SURVEY a13)")
-        N = n // n_graphs
-        feats = data.atom_features.detach().cpu().to(torch.float32).reshape(n_graphs, N, 7)
-        if not bool((feats == feats[:1]).all()):
-            raise NotImplementedError("all graphs of one call must share atom_features (one molecule per engine handle)")
-        sid = data.solvent_model_tensor.detach().cpu().reshape(n_graphs, N)[:, 0].tolist()
-        die = data.solvent_dielectric.detach().cpu().to(torch.float32).reshape(n_graphs, N)[:, 0].tolist()
-        eng = self._engine_ready(feats[0])
-        self._set_replica_config(n_graphs, sid, die)
-        eng = self._engine_ready(feats[0])
-        e_rep, f = eng.energy_force(pos, gb_only=self._gb_only, data_predicate=self._data_predicate)
-        forces = f.reshape(n, 3)
+        b = batch.detach().cpu().numpy().astype(np.int64)
+        if n == 0 or np.any(np.diff(b) < 0):
+            raise ValueError("data.batch must be non-empty and sorted (PyG batches are)")
+        n_graphs = int(b.max()) + 1
+        counts = np.bincount(b, minlength=n_graphs)
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        feats = data.atom_features.detach().cpu().to(torch.float32).numpy()
+        sid = data.solvent_model_tensor.detach().cpu().numpy()
+        die = data.solvent_dielectric.detach().cpu().to(torch.float32).numpy()
+        groups = {}
+        for gi in range(n_graphs):
+            lo, hi = int(starts[gi]), int(starts[gi + 1])
+            if hi == lo:
+                raise ValueError(f"graph {gi} of the batch is empty")
+            groups.setdefault(feats[lo:hi].tobytes(), []).append(gi)
+        dev = self._device if self._device.type == "cuda" else torch.device("cuda", torch.cuda.current_device()) \
+            if torch.cuda.is_available() else None
+        if dev is None:
+            raise GnnisError("no CUDA device: the gnnis hot path has no CPU fallback")
+        e_graph = torch.empty(n_graphs, dtype=torch.float32, device=dev)
+        forces = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        pos_dev = pos.detach().to(dev, torch.float32)
+        for key, members in groups.items():
+            lo0 = int(starts[members[0]])
+            N = int(counts[members[0]])
+            eng = self._data_engine(key, feats[lo0:lo0 + N], dev)
+            idx = torch.as_tensor(np.concatenate([np.arange(starts[g], starts[g + 1]) for g in members]), device=dev)
+            R = len(members)
+            eng.set_replicas(R, [int(sid[starts[g]]) for g in members], [float(die[starts[g]]) for g in members])
+            e_rep, f = eng.energy_force(pos_dev.index_select(0, idx).reshape(R, N, 3), gb_only=self._gb_only,
+                                        data_predicate=self._data_predicate)
+            e_graph[torch.as_tensor(members, device=dev)] = e_rep
+            forces.index_copy_(0, idx, f.reshape(R * N, 3))
         if self._nobatch:
-            energy = e_rep.sum().reshape(1, 1)
+            energy = e_graph.sum().reshape(1, 1)
         else:
-            energy = e_rep.reshape(n_graphs, 1)
+            energy = e_graph.reshape(n_graphs, 1)
         return energy, forces
+
+    def _data_engine(self, key, params, dev) -> Engine:
+        """One engine per distinct molecule of the data path (small LRU keyed by the atom_features bytes)."""
+        cache = self.__dict__.setdefault("_data_engines", {})
+        sd = None if self._gb_only else {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 16:
+                cache.pop(next(iter(cache))).close()
+            ent = Engine(params, sd, device=dev, unique_radii=self._unique_radii, fraction=self._fraction,
+                         scaling_factor=self._scaling_factor, cutoff=self._gnn_radius)
+            cache[key] = ent
+            ent._weights_version = self.__dict__.get("_weights_version", 0)
+        elif ent._weights_version != self.__dict__.get("_weights_version", 0) and sd is not None:
+            ent.load_state_dict(sd)
+            ent._weights_version = self.__dict__.get("_weights_version", 0)
+        return ent
 
     # ------------------------------------------------------------------ native batched call
     def energy_force(self, positions: torch.Tensor, delta: bool = False):

@@ -168,3 +168,33 @@ def test_gbneck2_parameter_table_layout():
     c = els.index("C")
     assert p[c, 6] == 7 and abs(p[c, 1] - (0.17 - 0.0195141)) < 1e-12 and abs(p[c, 2] - 1.058554 * p[c, 1]) < 1e-12
     assert radii == gbneck.DEFAULT_UNIQUE_RADII
+
+
+@pytest.mark.gpu
+def test_data_model_ragged_batch(weights):
+    """A PyG-style batch mixing two different molecules (13 and 21 atoms, interleaved graphs, mixed solvents)."""
+    from types import SimpleNamespace
+    from gnnimplicitsolvent_b200 import GNN_Models as M
+    from oracle import gnn_oracle as O
+    ca, cb = load_case("c1_n13_dmso"), load_case("mixed_n21")
+    order = [("a", 0), ("b", 0), ("b", 1), ("a", 1), ("b", 2)]
+    pos, feats, batch, sid, die, ref_e, ref_f = [], [], [], [], [], [], []
+    oa = O.evaluate(ca["params"], ca["pos"][:2], ca["solvent_ids"][:2], ca["dielectrics"][:2], weights, predicate="data")
+    ob = O.evaluate(cb["params"], cb["pos"][:3], cb["solvent_ids"][:3], cb["dielectrics"][:3], weights, predicate="data")
+    for g, (which, k) in enumerate(order):
+        c, o = (ca, oa) if which == "a" else (cb, ob)
+        N = c["pos"].shape[1]
+        pos.append(c["pos"][k]), feats.append(np.asarray(c["params"], dtype=np.float32))
+        batch += [g] * N
+        sid += [int(c["solvent_ids"][k])] * N
+        die += [float(c["dielectrics"][k])] * N
+        ref_e.append(float(o["energy_rep"][k])), ref_f.append(o["forces"][k].numpy())
+    data = SimpleNamespace(pos=torch.from_numpy(np.concatenate(pos)).cuda(), atom_features=torch.from_numpy(np.concatenate(feats)),
+                           batch=torch.tensor(batch), solvent_model_tensor=torch.tensor(sid),
+                           solvent_dielectric=torch.tensor(die, dtype=torch.float32))
+    model = M.GNN3_Multisolvent_embedding(parameters=None, device="cuda", num_solvents=42, no_batch=False)
+    model.load_state_dict(weights)
+    energy, forces = model(data)
+    assert energy.shape == (5, 1) and forces.shape == (len(batch), 3)
+    np.testing.assert_allclose(energy.cpu().numpy().ravel(), np.array(ref_e), rtol=E_RTOL)
+    assert rel_rms(forces.cpu().numpy(), np.concatenate(ref_f)) < F_RRMS
