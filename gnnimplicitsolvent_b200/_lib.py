@@ -53,6 +53,7 @@ SIGNATURES = {
     "gnnis_get_born_radii": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnis_last_edge_count": (C.c_int, [C.c_void_p, c_int64_p, C.c_void_p]),
     "gnnis_set_forcefield": (C.c_int, [C.c_void_p, C.POINTER(GnnisForcefield)]),
+    "gnnis_set_constraints": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p, c_float_p, C.c_float]),
     "gnnis_set_bonds": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p, c_float_p, c_float_p]),
     "gnnis_minimize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int32_p, C.c_float, C.c_int32,
                                  C.c_int32, C.c_uint32, C.c_void_p]),

@@ -274,6 +274,11 @@ int gnnis_destroy(gnnis_handle h) {
     dev_free(&c->a[l]);
     dev_free(&c->o[l]);
   }
+  cudaFree(c->cl_atom_ptr);
+  cudaFree(c->cl_atoms);
+  cudaFree(c->cl_con_ptr);
+  cudaFree(c->cl_con);
+  cudaFree(c->cl_con_d);
   cudaFree(c->ff_excl);
   cudaFree(c->ff_bond);
   cudaFree(c->ff_angle);

@@ -128,6 +128,12 @@ struct Ctx {
   float *lb_step = nullptr, *lb_ftmp = nullptr, *lb_etmp = nullptr;
   int *lb_state = nullptr, *lb_count = nullptr, *lb_active = nullptr;
   float* masses = nullptr;
+  // distance constraints of the integrator (clusters of constrained atoms)
+  int n_clusters = 0;
+  float con_tol = 1e-5f;
+  int *cl_atom_ptr = nullptr, *cl_atoms = nullptr, *cl_con_ptr = nullptr;
+  int2* cl_con = nullptr;
+  float* cl_con_d = nullptr;
 };
 
 #define GNNIS_CUDA_OK(call)                                                                   \

@@ -8,6 +8,8 @@
 //   LangevinMiddleIntegrator(300 K, 1/ps, 2 fs) + simulation.step  helper_functions.py:787-789, Simulator.py:402
 #include <vector>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace gnnis {
@@ -374,6 +376,112 @@ __global__ void langevin_middle_kernel(int n, int N, const float* __restrict__ i
   }
 }
 
+// The same step with holonomic distance constraints (the reference's default `constraints=HBonds`,
+// helper_functions.py:937-946; OpenMM LangevinMiddleIntegrator):
+//   v += dt F/m ; RATTLE(v) ; x += dt/2 v ; v = a v + noise ; x += dt/2 v ; SHAKE(x) ; v += (x_constrained - x) / dt
+// One thread per (replica, cluster): a cluster is a connected set of constrained atoms (a heavy atom and its
+// hydrogens, at most kMaxClusterAtoms atoms / constraints); unconstrained atoms are clusters of one.
+constexpr int kMaxClusterAtoms = 8;
+struct ClusterArgs {
+  int n_clusters, N;
+  const int* atom_ptr;   // [n_clusters + 1] -> cluster_atom
+  const int* atoms;      // atom indices of a cluster
+  const int* con_ptr;    // [n_clusters + 1] -> constraints
+  const int2* con;       // (local a, local b) inside the cluster
+  const float* con_d;    // target distance
+  float tol;
+};
+
+__global__ void langevin_middle_constrained_kernel(int R, ClusterArgs c, const float* __restrict__ inv_mass,
+                                                   const float* __restrict__ force, float* __restrict__ pos,
+                                                   float* __restrict__ vel, float dt, float a_fric, float kT,
+                                                   uint64_t seed, uint64_t step) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * c.n_clusters) return;
+  const int rep = t / c.n_clusters, cl = t - rep * c.n_clusters;
+  const int a0 = c.atom_ptr[cl], na = c.atom_ptr[cl + 1] - a0;
+  const int k0 = c.con_ptr[cl], nk = c.con_ptr[cl + 1] - k0;
+  float x0[kMaxClusterAtoms][3], x[kMaxClusterAtoms][3], v[kMaxClusterAtoms][3], im[kMaxClusterAtoms];
+  size_t gi[kMaxClusterAtoms];
+  for (int l = 0; l < na; ++l) {
+    const int a = c.atoms[a0 + l];
+    gi[l] = ((size_t)rep * c.N + a) * 3;
+    im[l] = inv_mass[a];
+    for (int k = 0; k < 3; ++k) {
+      x0[l][k] = pos[gi[l] + k];
+      v[l][k] = vel[gi[l] + k] + dt * force[gi[l] + k] * im[l];
+    }
+  }
+  // RATTLE: remove the velocity components along the constraints
+  for (int it = 0; it < 50; ++it) {
+    bool done = true;
+    for (int q = 0; q < nk; ++q) {
+      const int2 ab = c.con[k0 + q];
+      float rx = x0[ab.x][0] - x0[ab.y][0], ry = x0[ab.x][1] - x0[ab.y][1], rz = x0[ab.x][2] - x0[ab.y][2];
+      float rv = rx * (v[ab.x][0] - v[ab.y][0]) + ry * (v[ab.x][1] - v[ab.y][1]) + rz * (v[ab.x][2] - v[ab.y][2]);
+      float r2 = rx * rx + ry * ry + rz * rz;
+      if (fabsf(rv) * dt > c.tol * r2) {
+        done = false;
+        float gmm = -rv / (r2 * (im[ab.x] + im[ab.y]));
+        v[ab.x][0] += gmm * rx * im[ab.x];
+        v[ab.x][1] += gmm * ry * im[ab.x];
+        v[ab.x][2] += gmm * rz * im[ab.x];
+        v[ab.y][0] -= gmm * rx * im[ab.y];
+        v[ab.y][1] -= gmm * ry * im[ab.y];
+        v[ab.y][2] -= gmm * rz * im[ab.y];
+      }
+    }
+    if (done) break;
+  }
+  // half drift, Ornstein-Uhlenbeck refresh, half drift
+  for (int l = 0; l < na; ++l) {
+    const int a = c.atoms[a0 + l];
+    uint32_t rnd[4];
+    philox4x32((uint32_t)(rep * c.N + a), (uint32_t)(step & 0xFFFFFFFFu), (uint32_t)(step >> 32), 0x4C616E67u,
+               (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32), rnd);
+    float r1 = sqrtf(-2.0f * logf(u01(rnd[0]))), t1 = 6.283185307179586f * u01(rnd[1]);
+    float r2 = sqrtf(-2.0f * logf(u01(rnd[2]))), t2 = 6.283185307179586f * u01(rnd[3]);
+    const float xi[3] = {r1 * cosf(t1), r1 * sinf(t1), r2 * cosf(t2)};
+    const float sig = sqrtf(kT * (1.0f - a_fric * a_fric) * im[l]);
+    for (int k = 0; k < 3; ++k) {
+      float xx = x0[l][k] + 0.5f * dt * v[l][k];
+      v[l][k] = a_fric * v[l][k] + sig * xi[k];
+      x[l][k] = xx + 0.5f * dt * v[l][k];
+    }
+  }
+  // SHAKE along the old bond vectors, then the velocity correction of the middle scheme
+  float xu[kMaxClusterAtoms][3];
+  for (int l = 0; l < na; ++l)
+    for (int k = 0; k < 3; ++k) xu[l][k] = x[l][k];
+  for (int it = 0; it < 100; ++it) {
+    bool done = true;
+    for (int q = 0; q < nk; ++q) {
+      const int2 ab = c.con[k0 + q];
+      const float d = c.con_d[k0 + q];
+      float rx = x[ab.x][0] - x[ab.y][0], ry = x[ab.x][1] - x[ab.y][1], rz = x[ab.x][2] - x[ab.y][2];
+      float diff = d * d - (rx * rx + ry * ry + rz * rz);
+      if (fabsf(diff) > 2.0f * c.tol * d * d) {
+        done = false;
+        float ox = x0[ab.x][0] - x0[ab.y][0], oy = x0[ab.x][1] - x0[ab.y][1], oz = x0[ab.x][2] - x0[ab.y][2];
+        float gmm = diff / (2.0f * (rx * ox + ry * oy + rz * oz) * (im[ab.x] + im[ab.y]));
+        x[ab.x][0] += gmm * ox * im[ab.x];
+        x[ab.x][1] += gmm * oy * im[ab.x];
+        x[ab.x][2] += gmm * oz * im[ab.x];
+        x[ab.y][0] -= gmm * ox * im[ab.y];
+        x[ab.y][1] -= gmm * oy * im[ab.y];
+        x[ab.y][2] -= gmm * oz * im[ab.y];
+      }
+    }
+    if (done) break;
+  }
+  const float idt = 1.0f / dt;
+  for (int l = 0; l < na; ++l)
+    for (int k = 0; k < 3; ++k) {
+      pos[gi[l] + k] = x[l][k];
+      vel[gi[l] + k] = v[l][k] + (x[l][k] - xu[l][k]) * idt;
+    }
+}
+
 }  // namespace gnnis
 
 using namespace gnnis;
@@ -412,6 +520,80 @@ int gnnis_set_bonds(gnnis_handle h, int32_t n_bonds, const int32_t* idx, const f
   GNNIS_CUDA_OK(cudaMemcpy(c->bond_r0, r0, n_bonds * sizeof(float), cudaMemcpyHostToDevice));
   GNNIS_CUDA_OK(cudaMemcpy(c->bond_k, k, n_bonds * sizeof(float), cudaMemcpyHostToDevice));
   c->n_bonds = n_bonds;
+  return 0;
+}
+
+int gnnis_set_constraints(gnnis_handle h, int32_t n_con, const int32_t* idx, const float* dist, float tolerance) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (c->N <= 0) {
+    c->err = "gnnis_set_constraints: call gnnis_set_system first";
+    return -1;
+  }
+  if (n_con <= 0) {
+    c->n_clusters = 0;
+    return 0;
+  }
+  const int N = c->N;
+  std::vector<int> parent(N);
+  for (int i = 0; i < N; ++i) parent[i] = i;
+  auto find = [&](int a) {
+    while (parent[a] != a) a = parent[a] = parent[parent[a]];
+    return a;
+  };
+  for (int q = 0; q < n_con; ++q) {
+    int a = idx[2 * q], b = idx[2 * q + 1];
+    if (a < 0 || a >= N || b < 0 || b >= N || a == b || !(dist[q] > 0.f)) {
+      c->err = "gnnis_set_constraints: bad constraint";
+      return -1;
+    }
+    parent[find(a)] = find(b);
+  }
+  std::vector<int> root_to_cluster(N, -1), atom_ptr(1, 0), atoms, local(N, -1);
+  std::vector<std::vector<int>> members;
+  for (int i = 0; i < N; ++i) {
+    int r = find(i);
+    if (root_to_cluster[r] < 0) {
+      root_to_cluster[r] = (int)members.size();
+      members.emplace_back();
+    }
+    members[root_to_cluster[r]].push_back(i);
+  }
+  for (auto& m : members) {
+    if ((int)m.size() > kMaxClusterAtoms) {
+      c->err = "gnnis_set_constraints: a constraint cluster has more than 8 atoms (only X-H style clusters are supported)";
+      return -1;
+    }
+    for (size_t l = 0; l < m.size(); ++l) {
+      local[m[l]] = (int)l;
+      atoms.push_back(m[l]);
+    }
+    atom_ptr.push_back((int)atoms.size());
+  }
+  std::vector<std::vector<int>> con_of(members.size());
+  for (int q = 0; q < n_con; ++q) con_of[root_to_cluster[find(idx[2 * q])]].push_back(q);
+  std::vector<int> con_ptr(1, 0);
+  std::vector<int2> con;
+  std::vector<float> con_d;
+  for (auto& lst : con_of) {
+    for (int q : lst) {
+      con.push_back(make_int2(local[idx[2 * q]], local[idx[2 * q + 1]]));
+      con_d.push_back(dist[q]);
+    }
+    con_ptr.push_back((int)con.size());
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  if (dyn_alloc(c, &c->cl_atom_ptr, atom_ptr.size()) || dyn_alloc(c, &c->cl_atoms, atoms.size()) ||
+      dyn_alloc(c, &c->cl_con_ptr, con_ptr.size()) || dyn_alloc(c, &c->cl_con, con.size()) ||
+      dyn_alloc(c, &c->cl_con_d, con_d.size()))
+    return -1;
+  GNNIS_CUDA_OK(cudaMemcpy(c->cl_atom_ptr, atom_ptr.data(), atom_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  GNNIS_CUDA_OK(cudaMemcpy(c->cl_atoms, atoms.data(), atoms.size() * sizeof(int), cudaMemcpyHostToDevice));
+  GNNIS_CUDA_OK(cudaMemcpy(c->cl_con_ptr, con_ptr.data(), con_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  GNNIS_CUDA_OK(cudaMemcpy(c->cl_con, con.data(), con.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  GNNIS_CUDA_OK(cudaMemcpy(c->cl_con_d, con_d.data(), con_d.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->n_clusters = (int)members.size();
+  c->con_tol = tolerance > 0.f ? tolerance : 1e-5f;
   return 0;
 }
 
@@ -525,8 +707,15 @@ int gnnis_langevin(gnnis_handle h, float* pos_dev, float* vel_dev, const float* 
   for (int s = 0; s < n_steps; ++s) {
     int rc = energy_force_impl(c, pos_dev, c->h_e_dev, c->h_f_dev, eflags, st, nullptr);
     if (rc) return rc;
-    langevin_middle_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, c->N, c->masses, c->h_f_dev, pos_dev, vel_dev, dt, a_fric, kT,
-                                                           seed, first_step + (uint64_t)s);
+    if (c->n_clusters > 0) {
+      ClusterArgs ca{c->n_clusters, c->N, c->cl_atom_ptr, c->cl_atoms, c->cl_con_ptr, c->cl_con, c->cl_con_d, c->con_tol};
+      const int nt = c->R * c->n_clusters;
+      langevin_middle_constrained_kernel<<<(nt + 127) / 128, 128, 0, st>>>(c->R, ca, c->masses, c->h_f_dev, pos_dev, vel_dev,
+                                                                          dt, a_fric, kT, seed, first_step + (uint64_t)s);
+    } else {
+      langevin_middle_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, c->N, c->masses, c->h_f_dev, pos_dev, vel_dev, dt, a_fric, kT,
+                                                             seed, first_step + (uint64_t)s);
+    }
     GNNIS_LAUNCH_CHECK();
   }
   return 0;

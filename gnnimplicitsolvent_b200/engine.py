@@ -166,6 +166,13 @@ class Engine:
         s.exception_chargeprod, s.exception_sigma, s.exception_epsilon = flt(x["chargeprod"]), flt(x["sigma"]), flt(x["epsilon"])
         self._check(self.lib.gnnis_set_forcefield(self._h, C.byref(s)))
 
+    def set_constraints(self, idx, dist, tolerance: float = 1e-5):
+        """Distance constraints for `langevin` (e.g. all X-H bonds at their force-field length = OpenMM's HBonds)."""
+        idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int32).reshape(-1, 2))
+        dist = _f32(dist).reshape(-1)
+        self._check(self.lib.gnnis_set_constraints(self._h, idx.shape[0], idx.ctypes.data_as(_lib.c_int32_p), _fp(dist),
+                                                   float(tolerance)))
+
     def set_bonds(self, idx, r0, k):
         idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int32).reshape(-1, 2))
         r0, k = _f32(r0).reshape(-1), _f32(k).reshape(-1)

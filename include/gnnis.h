@@ -153,6 +153,14 @@ int gnnis_langevin(gnnis_handle h, float* pos_dev, float* vel_dev, const float* 
                    float temperature, float friction, float dt, int32_t n_steps, uint64_t seed,
                    uint64_t first_step, uint32_t flags, void* stream);
 
+/* Distance constraints of the integrator (the reference's default `constraints=HBonds`, helper_functions.py:937-946):
+ * idx_host [n][2] atom pairs, dist_host [n] nm; connected constraints form clusters of at most 8 atoms (a heavy atom
+ * and its hydrogens).  gnnis_langevin then runs RATTLE on the velocities and SHAKE on the positions of every cluster
+ * (relative tolerance, OpenMM default 1e-5).  n = 0 removes them.  The minimiser ignores constraints, as the
+ * reference's entropy path does (constraints=None). */
+int gnnis_set_constraints(gnnis_handle h, int32_t n_constraints, const int32_t* idx_host, const float* dist_host,
+                          float tolerance);
+
 /* Building-block check of the tensor-core path: D[128][n] = A[128][k] * B[n][k]^T (row-major device buffers)
  * through TMEM-resident A, 128B-swizzled shared-memory B, 3xTF32 tcgen05.mma.  k, n in {32, 64}. */
 int gnnis_umma_selftest(gnnis_handle h, const float* a_dev, const float* b_dev, float* d_dev, int32_t k, int32_t n,
