@@ -266,7 +266,7 @@ int gnnis_destroy(gnnis_handle h) {
                  &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->abar, &c->Pbar, &c->Qbar, &c->rbar, &c->e_atom,
                  &c->sa_atom, &c->h_pos_dev, &c->h_e_dev, &c->h_f_dev, &c->bond_r0, &c->bond_k, &c->lb_S, &c->lb_Y,
                  &c->lb_rho, &c->lb_alpha, &c->lb_g, &c->lb_gprev, &c->lb_xprev, &c->lb_d, &c->lb_e, &c->lb_eprev,
-                 &c->lb_step, &c->lb_ftmp, &c->lb_etmp, &c->masses, &c->gamma_emb, &c->gbar};
+                 &c->lb_step, &c->lb_ftmp, &c->lb_etmp, &c->masses, &c->gamma_emb, &c->gbar, &c->lb_eref};
   for (float** p : f) dev_free(p);
   for (int l = 0; l < 3; ++l) {
     dev_free(&c->P[l]);
@@ -293,7 +293,7 @@ int gnnis_destroy(gnnis_handle h) {
   dev_free(&c->ff_term_ptr);
   dev_free(&c->ff_term_ref);
   int** ip[] = {&c->radidx, &c->solvent_id, &c->deg, &c->row_ptr, &c->blk_sum, &c->col, &c->bond_idx, &c->lb_state,
-                &c->lb_count, &c->lb_active};
+                &c->lb_count, &c->lb_active, &c->lb_stall};
   for (int** p : ip) dev_free(p);
   dev_free(&c->pair);
   dev_free(&c->perm);

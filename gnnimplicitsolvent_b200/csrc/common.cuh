@@ -125,8 +125,8 @@ struct Ctx {
   int dyn_hist = 0;
   float *lb_S = nullptr, *lb_Y = nullptr, *lb_rho = nullptr, *lb_alpha = nullptr;
   float *lb_g = nullptr, *lb_gprev = nullptr, *lb_xprev = nullptr, *lb_d = nullptr, *lb_e = nullptr, *lb_eprev = nullptr;
-  float *lb_step = nullptr, *lb_ftmp = nullptr, *lb_etmp = nullptr;
-  int *lb_state = nullptr, *lb_count = nullptr, *lb_active = nullptr;
+  float *lb_step = nullptr, *lb_ftmp = nullptr, *lb_etmp = nullptr, *lb_eref = nullptr;
+  int *lb_state = nullptr, *lb_count = nullptr, *lb_active = nullptr, *lb_stall = nullptr;
   float* masses = nullptr;
   // distance constraints of the integrator (clusters of constrained atoms)
   int n_clusters = 0;

@@ -96,8 +96,8 @@ struct LbArgs {
   float* xt;       // [R][D] trial positions
   const float* ft; // [R][D] forces at the trial positions
   const float* et; // [R]    energies at the trial positions
-  float *g, *d, *S, *Y, *rho, *alpha, *e, *step, *gd;
-  int *state, *hist, *status, *n_active;
+  float *g, *d, *S, *Y, *rho, *alpha, *e, *step, *gd, *eref;
+  int *state, *hist, *status, *n_active, *stall;
   float grad_tol, max_disp;
 };
 
@@ -185,6 +185,38 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
     gg = block_sum(gg, red);
     __syncthreads();
     float grms = sqrtf(gg / D);
+    // stagnation: the energy surface is discontinuous at graph-cutoff crossings, so a replica can keep accepting
+    // steps that gain nothing; 20 accepted steps without a gain above the fp32 resolution end it
+    bool stalled = false;
+    if (state == LB_INIT) {
+      if (threadIdx.x == 0) {
+        a.eref[r] = et;
+        a.stall[r] = 0;
+      }
+    } else {
+      const float eref = a.eref[r];
+      const int st = a.stall[r];
+      if (et < eref - (1e-6f * fabsf(eref) + 1e-3f)) {
+        if (threadIdx.x == 0) {
+          a.eref[r] = et;
+          a.stall[r] = 0;
+        }
+      } else {
+        stalled = st + 1 >= 20;
+        if (threadIdx.x == 0) a.stall[r] = st + 1;
+      }
+    }
+    __syncthreads();
+    if (stalled && grms >= a.grad_tol) {
+      if (threadIdx.x == 0) {
+        a.e[r] = et;
+        a.state[r] = LB_DONE;
+        a.status[r] = grms < 20.f * a.grad_tol ? 0 : 1;
+        a.hist[r] = (head << 16) | cnt;
+        atomicSub(a.n_active, 1);
+      }
+      return;
+    }
     if (grms < a.grad_tol) {
       if (threadIdx.x == 0) {
         a.e[r] = et;
@@ -622,7 +654,8 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
         dyn_alloc(c, &c->lb_g, n3) || dyn_alloc(c, &c->lb_d, n3) || dyn_alloc(c, &c->lb_xprev, n3) ||
         dyn_alloc(c, &c->lb_ftmp, n3) || dyn_alloc(c, &c->lb_etmp, (size_t)R) || dyn_alloc(c, &c->lb_e, (size_t)R) ||
         dyn_alloc(c, &c->lb_step, (size_t)R) || dyn_alloc(c, &c->lb_eprev, (size_t)R) ||
-        dyn_alloc(c, &c->lb_state, (size_t)R) || dyn_alloc(c, &c->lb_count, (size_t)R) || dyn_alloc(c, &c->lb_active, 1))
+        dyn_alloc(c, &c->lb_state, (size_t)R) || dyn_alloc(c, &c->lb_count, (size_t)R) || dyn_alloc(c, &c->lb_active, 1) ||
+        dyn_alloc(c, &c->lb_eref, (size_t)R) || dyn_alloc(c, &c->lb_stall, (size_t)R))
       return -1;
     c->dyn_atoms = n3;
     c->dyn_hist = history;
@@ -643,6 +676,8 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
   a.e = c->lb_e;
   a.step = c->lb_step;
   a.gd = c->lb_eprev;
+  a.eref = c->lb_eref;
+  a.stall = c->lb_stall;
   a.state = c->lb_state;
   a.hist = c->lb_count;
   a.status = status_dev;

@@ -169,7 +169,7 @@ SOLVENT_DIELECTRICS = [
 
 
 # GAFF-like Lennard-Jones parameters (sigma nm, epsilon kJ/mol) per element of the synthetic molecules
-LJ = {"H": (0.2650, 0.0657), "HN": (0.1069, 0.0657), "C": (0.3400, 0.4577), "N": (0.3250, 0.7113),
+LJ = {"H": (0.2650, 0.0657), "HN": (0.2650, 0.0657), "C": (0.3400, 0.4577), "N": (0.3250, 0.7113),
       "O": (0.2960, 0.8786), "S": (0.3564, 1.0460)}
 
 
@@ -198,7 +198,8 @@ def synth_forcefield(mol, coulomb14=1.0 / 1.2, lj14=0.5):
                 u, v = pos[i] - pos[j], pos[k] - pos[j]
                 c = float(np.dot(u, v) / (np.linalg.norm(u) * np.linalg.norm(v)))
                 a_idx.append((i, j, k))
-                a_t0.append(np.arccos(np.clip(c, -1.0, 1.0)))
+                # a harmonic angle is singular at 180 deg unless theta0 = 180 deg: keep equilibrium angles well away
+                a_t0.append(min(np.arccos(np.clip(c, -1.0, 1.0)), np.deg2rad(150.0)))
     t_idx, t_n, t_ph, t_k = [], [], [], []
     for (j, k) in bonds:
         for i in sorted(nbrs[j]):

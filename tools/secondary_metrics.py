@@ -1,5 +1,5 @@
-"""Secondary metrics of SURVEY.md 8(d): batched minimisation throughput (C2) and Langevin ns/day (C4-like).
-GNN potential + an elastic-network stand-in for the vacuum force field (SURVEY.md N1 is not built yet)."""
+"""Secondary metrics of SURVEY.md 8(d): batched minimisation throughput (C2) and Langevin ns/day (C4-like) on the
+full Hamiltonian: GNN implicit solvent + synthetic vacuum force field (synth.synth_forcefield), HBonds constraints."""
 import json
 import os
 import sys
@@ -17,10 +17,7 @@ from gnnimplicitsolvent_b200.engine import Engine  # noqa: E402
 def system(N, R, seed, sigma):
     mol = synth.synth_molecule(N, seed=seed)
     pos = synth.conformers(mol["pos"], R, sigma, seed=seed + 1)
-    iu = np.triu_indices(N, 1)
-    bonds = np.stack(iu, axis=1).astype(np.int32)
-    r0 = np.linalg.norm(mol["pos"][bonds[:, 0]] - mol["pos"][bonds[:, 1]], axis=1).astype(np.float32)
-    return mol, pos, bonds, r0, np.full(len(bonds), 2.0e4, dtype=np.float32)
+    return mol, pos, synth.synth_forcefield(mol)
 
 
 z = np.load(os.path.join(ROOT, "tests", "golden", "gnn_weights.npz"))
@@ -28,10 +25,10 @@ sd = {k: torch.from_numpy(z[k]) for k in z.files}
 out = {}
 
 # C2: N = 50, R = 4096, water: L-BFGS to gradient RMS < 10 kJ/mol/nm
-mol, pos, bonds, r0, k = system(50, 4096, 50, 0.03)
+mol, pos, ff = system(50, 4096, 50, 0.02)
 eng = Engine(mol["params"], sd)
 eng.set_replicas(4096, [0] * 4096, [78.5] * 4096)
-eng.set_bonds(bonds, r0, k)
+eng.set_forcefield(ff)
 p0 = torch.from_numpy(pos).cuda()
 eng.minimize(p0[:], grad_tol=10.0, max_iter=3)      # warm-up
 torch.cuda.synchronize()
@@ -44,25 +41,29 @@ out["minimize_c2"] = {"replicas": 4096, "atoms": 50, "rounds": rounds, "seconds"
                       "ms_per_round": 1e3 * dt / max(rounds, 1)}
 eng.close()
 
-# C4-like: N = 60, R = 1024, 300 K, 1/ps, dt = 2 fs (no constraints: 0.5 fs would be needed for real hydrogens;
-# the timing does not depend on dt)
-mol, pos, bonds, r0, k = system(60, 1024, 60, 0.002)
+# C4-like: N = 60, R = 1024, 300 K, 1/ps, dt = 2 fs with HBonds constraints
+mol, pos, ff = system(60, 1024, 60, 0.0)
 eng = Engine(mol["params"], sd)
 eng.set_replicas(1024, [0] * 1024, [78.5] * 1024)
-eng.set_bonds(bonds, r0, k)
-p = torch.from_numpy(pos).cuda().contiguous()
+eng.set_forcefield(ff)
+hb = [i for i, (a, b) in enumerate(ff["bonds"]["idx"]) if mol["elements"][a].startswith("H") or mol["elements"][b].startswith("H")]
+eng.set_constraints(ff["bonds"]["idx"][hb], ff["bonds"]["r0"][hb])
+p, _, st_min, _ = eng.minimize(torch.from_numpy(pos).cuda(), grad_tol=20.0, max_iter=300)   # relax the synthetic start
+p = p.contiguous()
 v = torch.zeros_like(p)
 m = np.asarray(mol["masses"], dtype=np.float32)
-eng.langevin(p, v, m, 20, temperature=300.0, friction=1.0, dt=0.0005, seed=1)
+eng.langevin(p, v, m, 20, temperature=300.0, friction=5.0, dt=0.002, seed=1)
 torch.cuda.synchronize()
-steps = 500
+steps = 1000
 t0 = time.perf_counter()
-eng.langevin(p, v, m, steps, temperature=300.0, friction=1.0, dt=0.0005, seed=2, first_step=20)
+eng.langevin(p, v, m, steps, temperature=300.0, friction=5.0, dt=0.002, seed=2, first_step=20)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 t_step = dt / steps
 out["langevin_c4"] = {"replicas": 1024, "atoms": 60, "steps": steps, "ms_per_step": 1e3 * t_step,
                       "ns_per_day_per_replica_at_2fs": 86400.0 * 2e-6 / t_step,
                       "aggregate_ns_per_day_at_2fs": 1024 * 86400.0 * 2e-6 / t_step,
-                      "finite": bool(torch.isfinite(p).all())}
+                      "finite": bool(torch.isfinite(p).all()),
+                      "kinetic_T_over_300K": float((torch.from_numpy(m).cuda().reshape(1, -1, 1) * v * v).sum() / 1024
+                                                   / ((3 * 60 - len(hb)) * 0.0083144626 * 300.0))}
 print(json.dumps(out))
