@@ -160,7 +160,8 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     return -1;
   }
   if (flags & GNNIS_FLAG_MLP_BF16) {
-    c->err = "GNNIS_FLAG_MLP_BF16: the bf16 edge-MLP mode is not built in this version (the tcgen05 path runs 3xTF32)";
+    c->err = "GNNIS_FLAG_MLP_BF16: no reduced-precision MLP mode is offered -- already single-pass TF32 misses the parity "
+             "gates (energy 4e-4, forces 4e-3) and is only 2.5 % faster than the 3xTF32 default (DESIGN.md 5.1)";
     return -3;
   }
   // tensor-core (tcgen05, 3xTF32) edge kernels unless the caller forces the CUDA-core path or the unit's tables
@@ -467,7 +468,9 @@ int gnnis_set_system(gnnis_handle h, int32_t n_atoms, const float* params7, cons
   GNNIS_CUDA_OK(cudaMemcpy(c->m0, m0, uu * sizeof(float), cudaMemcpyHostToDevice));
   c->N = n_atoms;
   c->U = n_unique;
-  c->n_bonds = 0;
+  c->n_bonds = 0;        // per-molecule add-ons belong to the previous system
+  c->have_ff = false;
+  c->n_clusters = 0;
   return ensure_workspace(c);
 }
 
@@ -547,7 +550,7 @@ int gnnis_energy_force(gnnis_handle h, const float* pos_dev, float* e_rep_dev, f
 int gnnis_energy_force_host(gnnis_handle h, const float* pos_host, float* e_rep_host, float* force_host, uint32_t flags) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c) return -1;
-  if (check_ready(c, !(flags & GNNIS_FLAG_GB_ONLY))) return -1;
+  if (check_ready(c, !(flags & (GNNIS_FLAG_GB_ONLY | GNNIS_FLAG_VACUUM_ONLY)))) return -1;
   if (!pos_host || !e_rep_host) {
     c->err = "gnnis_energy_force_host: NULL argument";
     return -1;
