@@ -120,6 +120,9 @@ struct Ctx {
   int4 *ff_bond = nullptr, *ff_angle = nullptr, *ff_tors = nullptr, *ff_exc = nullptr;
   float2 *ff_bond_p = nullptr, *ff_angle_p = nullptr;
   float4 *ff_tors_p = nullptr, *ff_exc_p = nullptr;
+  // replicas whose entry is 2 (= finished, dynamics.cu LB_DONE) are skipped by the evaluation kernels while the
+  // batched minimiser runs; nullptr = evaluate everything
+  const int* skip_state = nullptr;
   // dynamics workspace
   size_t dyn_atoms = 0;
   int dyn_hist = 0;

@@ -689,6 +689,11 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
   GNNIS_CUDA_OK(cudaMemcpyAsync(a.xt, pos_dev, n3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   uint32_t eflags = flags & ~GNNIS_FLAG_NO_FORCES;
   int it = 0, active = R;
+  c->skip_state = a.state;   // finished replicas cost (almost) nothing in the following evaluations
+  struct SkipReset {
+    Ctx* c;
+    ~SkipReset() { c->skip_state = nullptr; }
+  } skip_reset{c};
   for (it = 0; it <= max_iter; ++it) {
     int rc = energy_force_impl(c, a.xt, c->lb_etmp, c->lb_ftmp, eflags, st, nullptr);
     if (rc) return rc;

@@ -49,7 +49,8 @@ __device__ __forceinline__ V3 ld3(const float* p, int i) { return {p[3 * i], p[3
 // dynamic smem: pos[3N] | q[N] | sig[N] | eps[N] | red[kFfThreads]
 __global__ void __launch_bounds__(kFfThreads) mm_forces_kernel(FfArgs g, const float* __restrict__ pos,
                                                                float* __restrict__ e_rep, float* __restrict__ force,
-                                                               int accumulate_energy) {
+                                                               int accumulate_energy, const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.x] == 2) return;
   extern __shared__ float smf[];
   float* sp = smf;
   float* sq = sp + 3 * g.N;
@@ -218,7 +219,7 @@ int launch_mm_forces(Ctx* c, const float* pos, float* e_rep, float* force, int a
     GNNIS_LAUNCH_CHECK();
   }
   size_t smem = (size_t)(6 * c->N + kFfThreads) * sizeof(float);
-  mm_forces_kernel<<<c->R, kFfThreads, smem, st>>>(g, pos, e_rep, force, accumulate);
+  mm_forces_kernel<<<c->R, kFfThreads, smem, st>>>(g, pos, e_rep, force, accumulate, c->skip_state);
   GNNIS_LAUNCH_CHECK();
   return 0;
 }

@@ -26,6 +26,7 @@ constexpr int kNtRows = 128;
 struct NodeTcArgs {
   int n, N;
   const int* solvent_id;
+  const int* skip;   // per replica: 2 = finished (minimiser), tiles made only of such replicas are skipped
   const float *a, *sbias, *W4, *b4, *b1_next;
   const uint8_t* img;   // operand image of this kernel (see Ctx::img_*)
   float *o, *P_next, *Q_next;
@@ -141,6 +142,15 @@ __device__ __forceinline__ void nt_store16(float* __restrict__ p, const float (&
   phase ^= 1;                                                                      \
   fence_after_sync();
 
+// true when every replica touched by the 128-atom tile is finished (uniform over the CTA)
+__device__ __forceinline__ bool nt_tile_skipped(const NodeTcArgs& g, int tile) {
+  if (!g.skip) return false;
+  const int r0 = (tile * kNtRows) / g.N, r1 = (min(g.n, tile * kNtRows + kNtRows) - 1) / g.N;
+  for (int r = r0; r <= r1; ++r)
+    if (g.skip[r] != 2) return false;
+  return true;
+}
+
 #define NT_EPILOGUE()                                                              \
   fence_before_sync();                                                             \
   __syncthreads();                                                                 \
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
@@ -274,6 +285,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
@@ -335,6 +347,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
@@ -415,6 +428,7 @@ static NodeTcArgs nt_args(Ctx* c, int l) {
   g.n = c->R * c->N;
   g.N = c->N;
   g.solvent_id = c->solvent_id;
+  g.skip = c->skip_state;
   g.a = c->a[l];
   g.o = c->o[l];
   g.sbias = c->L[l].sbias;

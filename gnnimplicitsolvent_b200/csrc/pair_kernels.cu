@@ -89,7 +89,8 @@ born_count_kernel(const float* __restrict__ pos, int n, int N, int U, const floa
                   const float* __restrict__ s, const int* __restrict__ radidx, const float* __restrict__ alpha,
                   const float* __restrict__ beta, const float* __restrict__ gamma, const float* __restrict__ d0,
                   const float* __restrict__ m0, float cutoff, int predicate, float* __restrict__ born,
-                  float* __restrict__ dBdI, int* __restrict__ deg, int* __restrict__ blk_sum) {
+                  float* __restrict__ dBdI, int* __restrict__ deg, int* __restrict__ blk_sum,
+                  const int* __restrict__ skip) {
   extern __shared__ float sm[];
   Stage st = cta_stage(N, n);
   float* spos = sm;
@@ -113,7 +114,9 @@ born_count_kernel(const float* __restrict__ pos, int n, int N, int U, const floa
   __syncthreads();
   int i = blockIdx.x * kPairThreads + threadIdx.x;
   int mydeg = 0;
-  if (i < n) {
+  if (i < n && skip && skip[i / N] == 2) {
+    deg[i] = 0;   // finished replica: no edges, nothing downstream touches it
+  } else if (i < n) {
     int rep = i / N, a = i - rep * N;
     const float* rp = spos + (size_t)(rep - st.first_rep) * N * 3;
     float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
@@ -195,6 +198,7 @@ fill_edges_kernel(const float* __restrict__ pos, int n, int N, int G, float cuto
   if (i >= n) return;
   int64_t w = (int64_t)blk_off[blockIdx.x] + sdeg[threadIdx.x] - mydeg;
   row_ptr[i] = (int)w;
+  if (mydeg == 0) return;
   if (w + mydeg > capacity) return;   // caller detects E > capacity from n_edges
   int rep = i / N, a = i - rep * N;
   const float* rp = spos + (size_t)(rep - st.first_rep) * N * 3;
@@ -235,7 +239,7 @@ __device__ __forceinline__ GbTerm gb_term(float r, float P) {
 // dynamic smem: pos[3*nst] | Bs[nst] | B[nst] | q[N]
 // mode bit0: delta (subtract GB energy evaluated with the unscaled B)
 __global__ void __launch_bounds__(kPairThreads)
-gb_energy_kernel(const float* __restrict__ pos, int n, int N, const float* __restrict__ q,
+gb_energy_kernel(const int* __restrict__ skip, const float* __restrict__ pos, int n, int N, const float* __restrict__ q,
                  const float* __restrict__ born_s, const float* __restrict__ born, const float* __restrict__ pref,
                  int delta, int want_grad, float* __restrict__ e_atom, float* __restrict__ dE_dBs,
                  float* __restrict__ dE_dB_direct, float* __restrict__ force) {
@@ -255,6 +259,7 @@ gb_energy_kernel(const float* __restrict__ pos, int n, int N, const float* __res
   int i = blockIdx.x * kPairThreads + threadIdx.x;
   if (i >= n) return;
   int rep = i / N, a = i - rep * N;
+  if (skip && skip[rep] == 2) return;
   int lo = (rep - st.first_rep) * N;
   const float* rp = spos + (size_t)lo * 3;
   float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
@@ -310,7 +315,7 @@ gb_energy_kernel(const float* __restrict__ pos, int n, int N, const float* __res
 
 // dynamic smem: pos[3*nst] | Ibar[nst] | rho[N] | s[N] | radidx[N] | d0[UU] | m0[UU]
 __global__ void __launch_bounds__(kPairThreads)
-born_adjoint_kernel(const float* __restrict__ pos, int n, int N, int U, const float* __restrict__ rho,
+born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos, int n, int N, int U, const float* __restrict__ rho,
                     const float* __restrict__ s, const int* __restrict__ radidx, const float* __restrict__ d0,
                     const float* __restrict__ m0, float cutoff, const float* __restrict__ Bbar,
                     const float* __restrict__ dBdI, const float* __restrict__ rbar, int use_rbar,
@@ -340,6 +345,7 @@ born_adjoint_kernel(const float* __restrict__ pos, int n, int N, int U, const fl
   int i = blockIdx.x * kPairThreads + threadIdx.x;
   if (i >= n) return;
   int rep = i / N, a = i - rep * N;
+  if (skip && skip[rep] == 2) return;
   int lo = (rep - st.first_rep) * N;
   const float* rp = spos + (size_t)lo * 3;
   float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
@@ -397,7 +403,7 @@ int launch_born_count(Ctx* c, const float* pos, int predicate, cudaStream_t st) 
   if (smem > 48 * 1024) cudaFuncSetAttribute(born_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   born_count_kernel<<<nblk, kPairThreads, smem, st>>>(pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->alpha, c->beta,
                                                      c->gamma, c->d0, c->m0, c->cutoff, predicate, c->born, c->dBdI,
-                                                     c->deg, c->blk_sum);
+                                                     c->deg, c->blk_sum, c->skip_state);
   GNNIS_LAUNCH_CHECK();
   scan_blocks_kernel<<<1, 1024, 0, st>>>(c->blk_sum, nblk, c->n_edges_dev, c->row_ptr + n);
   GNNIS_LAUNCH_CHECK();
@@ -422,7 +428,7 @@ int launch_gb_energy(Ctx* c, const float* pos, const float* born_s, int delta, i
   int nblk = (n + kPairThreads - 1) / kPairThreads;
   size_t smem = (5 * stage_atoms_max(c->N) + (size_t)c->N) * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(gb_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gb_energy_kernel<<<nblk, kPairThreads, smem, st>>>(pos, n, c->N, c->q, born_s, c->born, c->pref, delta, want_grad,
+  gb_energy_kernel<<<nblk, kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->q, born_s, c->born, c->pref, delta, want_grad,
                                                     c->e_atom, c->dE_dBs, c->Bbar, force);
   GNNIS_LAUNCH_CHECK();
   return 0;
@@ -433,7 +439,7 @@ int launch_born_adjoint(Ctx* c, const float* pos, int use_rbar, float* force, cu
   int nblk = (n + kPairThreads - 1) / kPairThreads;
   size_t smem = (4 * stage_atoms_max(c->N) + 3 * (size_t)c->N + 2 * (size_t)c->U * c->U) * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(born_adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  born_adjoint_kernel<<<nblk, kPairThreads, smem, st>>>(pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->d0, c->m0,
+  born_adjoint_kernel<<<nblk, kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->d0, c->m0,
                                                        c->cutoff, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
   GNNIS_LAUNCH_CHECK();
   return 0;
