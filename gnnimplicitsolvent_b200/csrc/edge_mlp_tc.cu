@@ -73,6 +73,101 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 // sigmoid = 1 / (1 + 2^(-x log2 e)): one MUFU.EX2 + one MUFU.RCP (~2 ulp); the parity gates guard this choice
 __device__ __forceinline__ float sig_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float silu_fast(float x) { return x * sig_fast(x); }
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issued instruction).  The epilogues are
+// bound by instruction issue, not by the FMA pipe, so halving the count of their add / mul / fma instructions pays.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// sigmoids of two packed pairs (same scheme as sig4_fast below)
+__device__ __forceinline__ void sig4_p(f2_t x01, f2_t x23, f2_t& s01, f2_t& s23) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;
+  const f2_t kL2 = pk(kL, kL), one2 = pk(1.0f, 1.0f);
+  float t0, t1, t2, t3;
+  upk(mul2(x01, kL2), t0, t1);
+  upk(mul2(x23, kL2), t2, t3);
+  const f2_t d01 = add2(pk(ex2_ftz(fminf(t0, kClamp)), ex2_ftz(fminf(t1, kClamp))), one2);
+  const f2_t d23 = add2(pk(ex2_ftz(fminf(t2, kClamp)), ex2_ftz(fminf(t3, kClamp))), one2);
+  float d0, d1, d2, d3;
+  upk(d01, d0, d1);
+  upk(d23, d2, d3);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;
+  s01 = pk(r01 * d1, r01 * d0);
+  s23 = pk(r23 * d3, r23 * d2);
+}
+// y = silu(a + b + c) for four consecutive channels (a: accumulator words, b, c: gathered rows)
+__device__ __forceinline__ float4 silu4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+__device__ __forceinline__ float4 silu4_sum2(const uint32_t* __restrict__ a, float4 b) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+// f = silu(x), d = silu'(x) = s + f (1 - s) for x = a + b + c
+__device__ __forceinline__ void silu_fd4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t one2 = pk(1.0f, 1.0f);
+  const f2_t f01 = mul2(x01, s01), f23 = mul2(x23, s23);
+  upk(f01, f[0], f[1]);
+  upk(f23, f[2], f[3]);
+  upk(fma2(f01, sub2(one2, s01), s01), d[0], d[1]);
+  upk(fma2(f23, sub2(one2, s23), s23), d[2], d[3]);
+}
+// g * silu'(a + b),  silu'(x) = s + s (x - x s)
+__device__ __forceinline__ float4 silu_d4_sum2_scaled(const uint32_t* __restrict__ a, float4 b, float4 g) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t t01 = sub2(x01, mul2(x01, s01)), t23 = sub2(x23, mul2(x23, s23));
+  float4 y;
+  upk(mul2(pk(g.x, g.y), fma2(s01, t01, s01)), y.x, y.y);
+  upk(mul2(pk(g.z, g.w), fma2(s23, t23, s23)), y.z, y.w);
+  return y;
+}
+
 // Four sigmoids from four MUFU.EX2 and ONE MUFU.RCP: 1/d_i = d_j d_k d_l / (d_0 d_1 d_2 d_3) with d = 1 + e^-x.
 // x is clamped at -20 inside the exponential (d <= 2^29, so the product of four stays below 2^116);
 // sigmoid(-20) = 2e-9, i.e. silu and its derivative are reproduced to ~1e-7 absolute below the clamp.
@@ -406,7 +501,14 @@ __device__ __forceinline__ void warp_arrive_mbar(uint64_t* bar, int lane) {
 __device__ __forceinline__ void st_split16(uint32_t t_hi, uint32_t t_lo, const float (&x)[16]) {
   uint32_t h[16], l[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) split_tf32(x[j], h[j], l[j]);
+  for (int j = 0; j < 16; j += 2) {
+    h[j] = __float_as_uint(x[j]) & 0xFFFFE000u;
+    h[j + 1] = __float_as_uint(x[j + 1]) & 0xFFFFE000u;
+    float l0, l1;
+    upk(sub2(pk(x[j], x[j + 1]), pk(__uint_as_float(h[j]), __uint_as_float(h[j + 1]))), l0, l1);
+    l[j] = __float_as_uint(l0);
+    l[j + 1] = __float_as_uint(l1);
+  }
   tmem_st16(t_hi, h);
   tmem_st16(t_lo, l);
 }
@@ -729,10 +831,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           float v[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 y = silu4_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x),
-                                        __uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y),
-                                        __uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z),
-                                        __uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w));
+            const float4 y = silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
             v[4 * j4 + 0] = y.x;
             v[4 * j4 + 1] = y.y;
             v[4 * j4 + 2] = y.z;
@@ -784,8 +883,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = bb[j4];
-            const float4 z = silu4_fast(__uint_as_float(wr[4 * j4 + 0]) + b.x, __uint_as_float(wr[4 * j4 + 1]) + b.y,
-                                        __uint_as_float(wr[4 * j4 + 2]) + b.z, __uint_as_float(wr[4 * j4 + 3]) + b.w);
+            const float4 z = silu4_sum2(&wr[4 * j4], b);
             *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
           }
         }
@@ -979,10 +1077,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           float v[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            silu_fd4_fast(__uint_as_float(ur[4 * j4 + 0]) + (p[j4].x + q[j4].x),
-                          __uint_as_float(ur[4 * j4 + 1]) + (p[j4].y + q[j4].y),
-                          __uint_as_float(ur[4 * j4 + 2]) + (p[j4].z + q[j4].z),
-                          __uint_as_float(ur[4 * j4 + 3]) + (p[j4].w + q[j4].w), &v[4 * j4], &dsu[16 * c + 4 * j4]);
+            silu_fd4_sum3(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], &dsu[16 * c + 4 * j4]);
           }
           st_split16(lane_addr + XH + col0, lane_addr + XL + col0, v);
         }
@@ -1011,12 +1106,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           float wb[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 sd = silu_d4_fast(__uint_as_float(wr[4 * j4 + 0]) + b[j4].x, __uint_as_float(wr[4 * j4 + 1]) + b[j4].y,
-                                           __uint_as_float(wr[4 * j4 + 2]) + b[j4].z, __uint_as_float(wr[4 * j4 + 3]) + b[j4].w);
-            wb[4 * j4 + 0] = a[j4].x * sd.x;
-            wb[4 * j4 + 1] = a[j4].y * sd.y;
-            wb[4 * j4 + 2] = a[j4].z * sd.z;
-            wb[4 * j4 + 3] = a[j4].w * sd.w;
+            const float4 sd = silu_d4_sum2_scaled(&wr[4 * j4], b[j4], a[j4]);
+            wb[4 * j4 + 0] = sd.x;
+            wb[4 * j4 + 1] = sd.y;
+            wb[4 * j4 + 2] = sd.z;
+            wb[4 * j4 + 3] = sd.w;
           }
           st_split16(lane_addr + XH + col0, lane_addr + XL + col0, wb);
         }
