@@ -309,6 +309,24 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
   tmem_st32(t_lo, l);
 }
 
+// radial operand rows: only the 24 columns that the K = 24 products read (20 basis functions + 4 zeros)
+__device__ __forceinline__ void st_split24(uint32_t t_hi, uint32_t t_lo, const float (&x)[32]) {
+  {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) split_tf32(x[j], h[j], l[j]);
+    tmem_st16(t_hi, h);
+    tmem_st16(t_lo, l);
+  }
+  {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_tf32(x[16 + j], h[j], l[j]);
+    tmem_st8(t_hi + 16, h);
+    tmem_st8(t_lo + 16, l);
+  }
+}
+
 // Per-tile keys (double-buffered by tile parity so that the reduction of tile t may overlap the set-up of t+1)
 struct TileKeys {
   int tgt[kTileE];        // unit-local target of row e (-1 past the end of the unit)
@@ -463,7 +481,7 @@ static int tc_grid(const Ctx* c) {
 // (or once it has drained an accumulator), and the warp whose arrival completes the count issues the tcgen05.mma
 // batch itself (one elected lane, warp converged) -- nobody waits for a dedicated issuer or for the slowest warp
 // before carrying on with independent work:
-//     cnt_u  (12 arrivals) : rbf operand of the next tile written (4 warps) + accumulators drained (8 warps)
+//     cnt_u  (8 arrivals)  : accumulators drained (8 warps), rbf operand of the next tile written (4 of them)
 //     cnt_a  ( 8 arrivals) : A operand (v, wbar) written by all warps
 //     d_full ( tcgen05.commit -> mbarrier ) : products of the last issue are in TMEM
 // Only two group-wide named barriers per tile remain, both around the shared-memory tile of the reduction.
@@ -793,7 +811,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<false>(r, g.inv_cutoff, o, od);
-        st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
+        st_split24(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
         tmem_st_wait();
         warp_arrive_i(u_ok, lane);
       }
@@ -859,7 +877,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             rbf_regs<false>(r_n, g.inv_cutoff, o, od);
             mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
             __syncwarp();
-            st_split(lane_addr + cur, lane_addr + cur + 32, o);
+            st_split24(lane_addr + cur, lane_addr + cur + 32, o);
             tmem_st_wait();
             warp_arrive_i(u_ok, lane);
           }
@@ -1027,15 +1045,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         prefetch_l1(gP + t_);
         prefetch_l1(gAb + t_);
       }
-      if (warp_arrive_last(cnt_u, 12, lane)) issue_u_du();
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<true>(r, g.inv_cutoff, o, od);
-        st_split(lane_addr + XH, lane_addr + XL, o);
-        st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
+        st_split24(lane_addr + XH, lane_addr + XL, o);
+        st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od);
         tmem_st_wait();
-        if (warp_arrive_last(cnt_u, 12, lane)) issue_u_du();
       }
+      if (warp_arrive_last(cnt_u, 8, lane)) issue_u_du();
       ws_group_sync(grp);
 
       for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
@@ -1151,6 +1168,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         __syncwarp();
         ph_d ^= 1u;
         fence_after_sync();
+        // vbar is complete, so the X operand columns are free: the radial operands of the next tile leave the
+        // registers before the last epilogue needs them
+        if (has_next && ch == 0) {
+          st_split24(lane_addr + XH, lane_addr + XL, o_n);
+          st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
+        }
         // slot of this edge in the dense pair-adjoint array; its previous value is fetched early (layers 2, 1 add)
         size_t rslot = 0;
         float rold = 0.0f;
@@ -1169,30 +1192,28 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           tmem_ld16(lane_addr + DU + col0, dr);
           tmem_ld_wait();
           float* urow = sU + row * kTileLd + col0;
-          float ra = 0.0f, rb = 0.0f;
+          f2_t rab = pk(0.0f, 0.0f);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
+            const float* ds = &dsu[16 * c + 4 * j4];
+            const f2_t u01 = mul2(pk(__uint_as_float(vr[4 * j4 + 0]), __uint_as_float(vr[4 * j4 + 1])), pk(ds[0], ds[1]));
+            const f2_t u23 = mul2(pk(__uint_as_float(vr[4 * j4 + 2]), __uint_as_float(vr[4 * j4 + 3])), pk(ds[2], ds[3]));
+            rab = fma2(u01, pk(__uint_as_float(dr[4 * j4 + 0]), __uint_as_float(dr[4 * j4 + 1])), rab);
+            rab = fma2(u23, pk(__uint_as_float(dr[4 * j4 + 2]), __uint_as_float(dr[4 * j4 + 3])), rab);
             float4 ub;
-            ub.x = __uint_as_float(vr[4 * j4 + 0]) * dsu[16 * c + 4 * j4 + 0];
-            ub.y = __uint_as_float(vr[4 * j4 + 1]) * dsu[16 * c + 4 * j4 + 1];
-            ub.z = __uint_as_float(vr[4 * j4 + 2]) * dsu[16 * c + 4 * j4 + 2];
-            ub.w = __uint_as_float(vr[4 * j4 + 3]) * dsu[16 * c + 4 * j4 + 3];
-            ra = fmaf(ub.x, __uint_as_float(dr[4 * j4 + 0]), ra);
-            rb = fmaf(ub.y, __uint_as_float(dr[4 * j4 + 1]), rb);
-            ra = fmaf(ub.z, __uint_as_float(dr[4 * j4 + 2]), ra);
-            rb = fmaf(ub.w, __uint_as_float(dr[4 * j4 + 3]), rb);
+            upk(u01, ub.x, ub.y);
+            upk(u23, ub.z, ub.w);
             *reinterpret_cast<float4*>(urow + 4 * j4) = ub;
           }
+          float ra, rb;
+          upk(rab, ra, rb);
           racc += ra + rb;
         }
-        if (has_next && warp_arrive_last(cnt_u, 12, lane)) issue_u_du();   // ACC / DU drained
-        if (ch == 1) sPart[grp][row] = racc;
-        if (has_next && ch == 0) {
-          st_split(lane_addr + XH, lane_addr + XL, o_n);
-          st_split(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
-          tmem_st_wait();
-          if (warp_arrive_last(cnt_u, 12, lane)) issue_u_du();
+        if (has_next) {
+          if (ch == 0) tmem_st_wait();
+          if (warp_arrive_last(cnt_u, 8, lane)) issue_u_du();   // ACC / DU drained, radial operands in place
         }
+        if (ch == 1) sPart[grp][row] = racc;
         ws_group_sync(grp);                          // (B) tile complete
         if (ch == 0 && valid) g.rbar[rslot] = rold + (racc + sPart[grp][row]);   // channels 0..31 + 32..63
         pr = pr_n;
