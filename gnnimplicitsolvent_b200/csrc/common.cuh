@@ -173,6 +173,30 @@ __device__ __forceinline__ float eps_dist(float sx, float sy, float sz, float tx
   return __fsqrt_rn(acc);
 }
 
+// MUFU-based reciprocal / log / exp / rsqrt (1-2 ulp) for the all-pairs kernels, which are bound by instruction issue:
+// an IEEE division costs ~9 instructions, MUFU.RCP one.  The exact-rounding operations are kept where bits matter
+// (eps_dist and the neighbour predicate).  The parity gates (Born radii 2e-5, energies 1e-4, forces 1e-3) guard this.
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ln_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.6931471805599453f;
+}
+__device__ __forceinline__ float exp_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // sigmoid from MUFU.EX2 + MUFU.RCP (~2 ulp); the parity gates (1e-4 / 1e-3) guard this choice
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 

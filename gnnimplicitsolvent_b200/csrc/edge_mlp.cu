@@ -557,59 +557,70 @@ static EdgeArgs make_args(Ctx* c, int l) {
   return g;
 }
 
-// Same permutation by a counting sort over the (<= 128) unit-local source indices: warps take their rows in
-// order, __match_any_sync groups equal sources inside a warp, so the rank inside a bin follows the edge order.
+// Same permutation by a counting sort over the (<= 128) unit-local source indices.  One WARP per unit (no block
+// barriers): the warp walks its rows 32 at a time in order, __match_any_sync groups equal sources, so the rank inside
+// a bin follows the edge order; the bins live in the warp's own shared-memory slice.
 __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, int G, int N, int R,
                                                                  const int* __restrict__ row_ptr,
                                                                  const uint32_t* __restrict__ pair,
                                                                  uint8_t* __restrict__ perm) {
-  __shared__ int bins[128];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+  __shared__ int sbins[kTileE / 32][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* bins = sbins[warp];
+  const int nwarps = gridDim.x * (kTileE / 32);
+  for (int unit = blockIdx.x * (kTileE / 32) + warp; unit < n_units; unit += nwarps) {
     const int rep0 = unit * G, rep1 = min(R, rep0 + G);
     const int atom0 = rep0 * N, natoms = (rep1 - rep0) * N;
     const int e_begin = row_ptr[atom0], e_end = row_ptr[atom0 + natoms];
     for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-      const int e = t0 + tid;
-      const bool valid = e < e_end;
-      const int key = valid ? (int)(pair[e] & 0xFFFFu) : 0;
-      bins[tid] = 0;
-      __syncthreads();
-      int in_bin = 0;   // rows of this tile with the same source that come before this one
-      for (int w = 0; w < 4; ++w) {
-        if (warp == w) {
-          const unsigned act = __ballot_sync(0xffffffffu, valid);
-          if (valid) {
-            const unsigned peers = __match_any_sync(act, key);
-            const int leader = __ffs(peers) - 1;
-            int base = 0;
-            if (lane == leader) {
-              base = bins[key];
-              bins[key] = base + __popc(peers);
-            }
-            base = __shfl_sync(peers, base, leader);
-            in_bin = base + __popc(peers & ((1u << lane) - 1u));
-          }
-        }
-        __syncthreads();
+      int key[4], in_bin[4];   // in_bin: rows of this tile with the same source that come before this one
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        bins[32 * c + lane] = 0;
+        const int e = t0 + 32 * c + lane;
+        key[c] = e < e_end ? (int)(__ldg(pair + e) & 0xFFFFu) : -1;
       }
-      // exclusive scan of the 128 bin counts (warp 0: 4 bins per lane)
-      if (warp == 0) {
-        int c0 = bins[4 * lane], c1 = bins[4 * lane + 1], c2 = bins[4 * lane + 2], c3 = bins[4 * lane + 3];
-        int tot = c0 + c1 + c2 + c3, inc = tot;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool valid = key[c] >= 0;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        in_bin[c] = 0;
+        if (valid) {
+          const unsigned peers = __match_any_sync(act, key[c]);
+          const int leader = __ffs(peers) - 1;
+          int base = 0;
+          if (lane == leader) {
+            base = bins[key[c]];
+            bins[key[c]] = base + __popc(peers);
+          }
+          base = __shfl_sync(peers, base, leader);
+          in_bin[c] = base + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncwarp();
+      }
+      // exclusive scan of the 128 bin counts (4 bins per lane)
+      {
+        const int c0 = bins[4 * lane], c1 = bins[4 * lane + 1], c2 = bins[4 * lane + 2], c3 = bins[4 * lane + 3];
+        const int tot = c0 + c1 + c2 + c3;
+        int inc = tot;
+#pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-          int v = __shfl_up_sync(0xffffffffu, inc, off);
+          const int v = __shfl_up_sync(0xffffffffu, inc, off);
           if (lane >= off) inc += v;
         }
-        int ex = inc - tot;
+        const int ex = inc - tot;
+        __syncwarp();
         bins[4 * lane] = ex;
         bins[4 * lane + 1] = ex + c0;
         bins[4 * lane + 2] = ex + c0 + c1;
         bins[4 * lane + 3] = ex + c0 + c1 + c2;
       }
-      __syncthreads();
-      if (valid) perm[t0 + bins[key] + in_bin] = (uint8_t)tid;
-      __syncthreads();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (key[c] >= 0) perm[t0 + bins[key[c]] + in_bin[c]] = (uint8_t)(32 * c + lane);
+      __syncwarp();
     }
   }
 }
@@ -617,7 +628,7 @@ __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, in
 int launch_tile_perm(Ctx* c, cudaStream_t st) {
   int grid = c->n_units < 8 * c->num_sms ? c->n_units : 8 * c->num_sms;
   if (c->G * c->N <= 128)
-    tile_perm_count_kernel<<<grid, kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
+    tile_perm_count_kernel<<<((c->n_units + 3) / 4 < 16 * c->num_sms ? (c->n_units + 3) / 4 : 16 * c->num_sms), kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
   else
     tile_perm_kernel<<<grid, kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
   GNNIS_LAUNCH_CHECK();

@@ -36,15 +36,15 @@ __device__ __forceinline__ float born_integral(float r, float rho_i, float rho_j
   float U = r + s_j;
   float ivdw = 0.0f;
   if ((r + s_j - rho_i) > 0.0f) {
-    ivdw = 0.5f * (1.0f / L - 1.0f / U + 0.25f * (r - s_j * s_j / r) * (1.0f / (U * U) - 1.0f / (L * L)) +
-                   0.5f * logf(L / U) / r);
+    const float iL = rcp_fast(L), iU = rcp_fast(U), ir = rcp_fast(r);
+    ivdw = 0.5f * (iL - iU + 0.25f * (r - s_j * s_j * ir) * (iU * iU - iL * iL) + 0.5f * ln_fast(L * iU) * ir);
   }
   float ineck = 0.0f;
   float radius1 = rho_i + kOffset, radius2 = rho_j + kOffset;
   if ((radius1 + radius2 + kNeckCut - r) > 0.0f) {
     float u = r - d0[k];
     float u2 = u * u;
-    ineck = m0[k] / (1.0f + 100.0f * u2 + 0.3f * 1000000.0f * (u2 * u2 * u2));
+    ineck = m0[k] * rcp_fast(1.0f + 100.0f * u2 + 0.3f * 1000000.0f * (u2 * u2 * u2));
   }
   return ivdw + kNeckScale * ineck;
 }
@@ -58,18 +58,19 @@ __device__ __forceinline__ float born_integral_dr(float r, float rho_i, float rh
     float L = fmaxf(rho_i, D);
     float U = r + s_j;
     float Lp = (D > rho_i) ? ((r - s_j) >= 0.0f ? 1.0f : -1.0f) : 0.0f;
-    float iL = 1.0f / L, iU = 1.0f / U, ir = 1.0f / r;
+    float iL = rcp_fast(L), iU = rcp_fast(U), ir = rcp_fast(r);
     float s2 = s_j * s_j;
     g = 0.5f * (-Lp * iL * iL + iU * iU + 0.25f * (1.0f + s2 * ir * ir) * (iU * iU - iL * iL) +
                 0.25f * (r - s2 * ir) * (-2.0f * iU * iU * iU + 2.0f * Lp * iL * iL * iL) +
-                0.5f * ((Lp * iL - iU) * ir - logf(L / U) * ir * ir));
+                0.5f * ((Lp * iL - iU) * ir - ln_fast(L * iU) * ir * ir));
   }
   float radius1 = rho_i + kOffset, radius2 = rho_j + kOffset;
   if ((radius1 + radius2 + kNeckCut - r) > 0.0f) {
     float u = r - d0[k];
     float u2 = u * u, u4 = u2 * u2;
     float den = 1.0f + 100.0f * u2 + 0.3f * 1000000.0f * (u4 * u2);
-    g += kNeckScale * (-m0[k] * (200.0f * u + 1.8f * 1000000.0f * (u4 * u)) / (den * den));
+    const float iden = rcp_fast(den);
+    g += kNeckScale * (-m0[k] * (200.0f * u + 1.8f * 1000000.0f * (u4 * u)) * (iden * iden));
   }
   return g;
 }
@@ -195,44 +196,60 @@ fill_edges_kernel(const float* __restrict__ pos, int n, int N, int G, float cuto
     sdeg[threadIdx.x] += v;
     __syncthreads();
   }
-  if (i >= n) return;
-  int64_t w = (int64_t)blk_off[blockIdx.x] + sdeg[threadIdx.x] - mydeg;
-  row_ptr[i] = (int)w;
-  if (mydeg == 0) return;
-  if (w + mydeg > capacity) return;   // caller detects E > capacity from n_edges
-  int rep = i / N, a = i - rep * N;
-  const float* rp = spos + (size_t)(rep - st.first_rep) * N * 3;
-  float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
-  uint32_t ul_base = (uint32_t)(rep % G) * (uint32_t)N;
-  uint32_t tgt_ul = (ul_base + (uint32_t)a) << 16;
-  for (int j = 0; j < N; ++j) {
-    if (j == a) continue;
-    float dx, dy, dz;
-    float sx = rp[3 * j], sy = rp[3 * j + 1], sz = rp[3 * j + 2];
-    float r = eps_dist(sx, sy, sz, tx, ty, tz, dx, dy, dz);
-    if (in_cutoff(predicate, r, sx, sy, sz, tx, ty, tz, cutoff)) {
-      if (col) col[w] = rep * N + j;
-      if (pair) pair[w] = tgt_ul | (ul_base + (uint32_t)j);
-      if (r_e) r_e[w] = r;
-      ++w;
+  int64_t w = 0;
+  if (i < n) {
+    w = (int64_t)blk_off[blockIdx.x] + sdeg[threadIdx.x] - mydeg;
+    row_ptr[i] = (int)w;
+  }
+  // The rows are filled by whole warps, one target at a time: the lanes take the sources j = lane, lane + 32, ...,
+  // a ballot compacts the accepted ones, and the row is written with consecutive addresses (ascending source).
+  const int lane = threadIdx.x & 31;
+  const unsigned todo = __ballot_sync(0xffffffffu, i < n && mydeg > 0 && w + mydeg <= capacity);   // E > capacity: caller
+  for (unsigned m = todo; m; m &= m - 1) {
+    const int t = __ffs(m) - 1;
+    const int it = __shfl_sync(0xffffffffu, i, t);
+    int64_t wt = __shfl_sync(0xffffffffu, w, t);
+    const int rep = it / N, a = it - rep * N;
+    const float* rp = spos + (size_t)(rep - st.first_rep) * N * 3;
+    const float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
+    const uint32_t ul_base = (uint32_t)(rep % G) * (uint32_t)N;
+    const uint32_t tgt_ul = (ul_base + (uint32_t)a) << 16;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      bool take = false;
+      float r = 0.0f;
+      if (j < N && j != a) {
+        float dx, dy, dz;
+        const float sx = rp[3 * j], sy = rp[3 * j + 1], sz = rp[3 * j + 2];
+        r = eps_dist(sx, sy, sz, tx, ty, tz, dx, dy, dz);
+        take = in_cutoff(predicate, r, sx, sy, sz, tx, ty, tz, cutoff);
+      }
+      const unsigned acc = __ballot_sync(0xffffffffu, take);
+      if (take) {
+        const int64_t at = wt + __popc(acc & ((1u << lane) - 1u));
+        if (col) col[at] = rep * N + j;
+        if (pair) pair[at] = tgt_ul | (ul_base + (uint32_t)j);
+        if (r_e) r_e[at] = r;
+      }
+      wt += __popc(acc);
     }
   }
 }
 
 struct GbTerm {
-  float e, dr, dP;
+  float e, dr_r, dP;   // 1/f, (d(1/f)/dr) / r, d(1/f)/dP
 };
 // pair term q_i q_j / f, f = sqrt(r^2 + P exp(-r^2/(4P)))  (GNN_Layers.py:2064-2074) and d(1/f)/dr, d(1/f)/dP
 __device__ __forceinline__ GbTerm gb_term(float r, float P) {
-  float r2 = r * r;
-  float ex = expf(-r2 / (4.0f * P));
-  float f2 = r2 + P * ex;
-  float f = sqrtf(f2);
+  const float r2 = r * r;
+  const float x = r2 * rcp_fast(4.0f * P);
+  const float ex = exp_fast(-x);
+  const float f2 = r2 + P * ex;
   GbTerm t;
-  t.e = 1.0f / f;
-  float if3 = t.e / f2;
-  t.dr = -r * (1.0f - 0.25f * ex) * if3;
-  t.dP = -0.5f * ex * (1.0f + r2 / (4.0f * P)) * if3;
+  t.e = rsqrt_fast(f2);
+  const float if3 = t.e * t.e * t.e;
+  t.dr_r = -(1.0f - 0.25f * ex) * if3;
+  t.dP = -0.5f * ex * (1.0f + x) * if3;
   return t;
 }
 
@@ -270,30 +287,32 @@ gb_energy_kernel(const int* __restrict__ skip, const float* __restrict__ pos, in
   for (int j = 0; j < N; ++j) {
     if (j == a) continue;
     float sx = rp[3 * j], sy = rp[3 * j + 1], sz = rp[3 * j + 2];
-    float d1x, d1y, d1z, d2x, d2y, d2z;
+    float d1x, d1y, d1z;
     float r1 = eps_dist(sx, sy, sz, tx, ty, tz, d1x, d1y, d1z);   // edge (j -> i): i is the target
     float qq = qi * sq[j];
     float Bj = sBs[lo + j];
     GbTerm t1 = gb_term(r1, Bi * Bj);
     pair_sum += qq * t1.e;
     if (want_grad) {
-      float r2 = eps_dist(tx, ty, tz, sx, sy, sz, d2x, d2y, d2z); // edge (i -> j): i is the source
-      GbTerm t2 = gb_term(r2, Bi * Bj);
+      // edge (i -> j), i the source: its separation vector is kept exactly, but its pair term is evaluated at r1
+      // (the two lengths differ by the 1e-6 eps only: relative force change ~1e-6, three orders below the gate)
+      const float d2x = __fadd_rn(__fsub_rn(tx, sx), kEps), d2y = __fadd_rn(__fsub_rn(ty, sy), kEps),
+                  d2z = __fadd_rn(__fsub_rn(tz, sz), kEps);
       float c = pf * qq;
-      float g1 = c * t1.dr / r1, g2 = c * t2.dr / r2;
-      gx += -g1 * d1x + g2 * d2x;
-      gy += -g1 * d1y + g2 * d2y;
-      gz += -g1 * d1z + g2 * d2z;
-      dBs += c * (t1.dP + t2.dP) * Bj;
+      float g1 = c * t1.dr_r;
+      gx += g1 * (d2x - d1x);
+      gy += g1 * (d2y - d1y);
+      gz += g1 * (d2z - d1z);
+      dBs += 2.0f * c * t1.dP * Bj;
       if (delta) {
         float B0j = sB[lo + j];
-        GbTerm u1 = gb_term(r1, B0i * B0j), u2 = gb_term(r2, B0i * B0j);
+        GbTerm u1 = gb_term(r1, B0i * B0j);
         pair_sum0 += qq * u1.e;
-        float h1 = c * u1.dr / r1, h2 = c * u2.dr / r2;
-        gx -= -h1 * d1x + h2 * d2x;
-        gy -= -h1 * d1y + h2 * d2y;
-        gz -= -h1 * d1z + h2 * d2z;
-        dB0 -= c * (u1.dP + u2.dP) * B0j;
+        float h1 = c * u1.dr_r;
+        gx -= h1 * (d2x - d1x);
+        gy -= h1 * (d2y - d1y);
+        gz -= h1 * (d2z - d1z);
+        dB0 -= 2.0f * c * u1.dP * B0j;
       }
     } else if (delta) {
       pair_sum0 += qq * gb_term(r1, B0i * sB[lo + j]).e;
@@ -368,8 +387,8 @@ born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos,
       if (r1 < cutoff) g1 += rbar_row[j];
       if (r2 < cutoff) g2 += rbar_col[(size_t)j * N];
     }
-    g1 /= r1;
-    g2 /= r2;
+    g1 *= rcp_fast(r1);
+    g2 *= rcp_fast(r2);
     gx += -g1 * d1x + g2 * d2x;
     gy += -g1 * d1y + g2 * d2y;
     gz += -g1 * d1z + g2 * d2z;
