@@ -34,7 +34,6 @@
 // while the tensor pipe works on tile t+1.
 #include "common.cuh"
 #include "umma.cuh"
-#include "fastmath.cuh"
 
 namespace gnnis {
 
@@ -61,6 +60,154 @@ struct EdgeTcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid = 1 / (1 + 2^(-x log2 e)): one MUFU.EX2 + one MUFU.RCP (~2 ulp); the parity gates guard this choice
+__device__ __forceinline__ float sig_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sig_fast(x); }
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issued instruction).  The epilogues are
+// bound by instruction issue, not by the FMA pipe, so halving the count of their add / mul / fma instructions pays.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// sigmoids of two packed pairs (same scheme as sig4_fast below)
+__device__ __forceinline__ void sig4_p(f2_t x01, f2_t x23, f2_t& s01, f2_t& s23) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;
+  const f2_t kL2 = pk(kL, kL), one2 = pk(1.0f, 1.0f);
+  float t0, t1, t2, t3;
+  upk(mul2(x01, kL2), t0, t1);
+  upk(mul2(x23, kL2), t2, t3);
+  const f2_t d01 = add2(pk(ex2_ftz(fminf(t0, kClamp)), ex2_ftz(fminf(t1, kClamp))), one2);
+  const f2_t d23 = add2(pk(ex2_ftz(fminf(t2, kClamp)), ex2_ftz(fminf(t3, kClamp))), one2);
+  float d0, d1, d2, d3;
+  upk(d01, d0, d1);
+  upk(d23, d2, d3);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;
+  s01 = pk(r01 * d1, r01 * d0);
+  s23 = pk(r23 * d3, r23 * d2);
+}
+// y = silu(a + b + c) for four consecutive channels (a: accumulator words, b, c: gathered rows)
+__device__ __forceinline__ float4 silu4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+__device__ __forceinline__ float4 silu4_sum2(const uint32_t* __restrict__ a, float4 b) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+// f = silu(x), d = silu'(x) = s + f (1 - s) for x = a + b + c
+__device__ __forceinline__ void silu_fd4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t one2 = pk(1.0f, 1.0f);
+  const f2_t f01 = mul2(x01, s01), f23 = mul2(x23, s23);
+  upk(f01, f[0], f[1]);
+  upk(f23, f[2], f[3]);
+  upk(fma2(f01, sub2(one2, s01), s01), d[0], d[1]);
+  upk(fma2(f23, sub2(one2, s23), s23), d[2], d[3]);
+}
+// g * silu'(a + b),  silu'(x) = s + s (x - x s)
+__device__ __forceinline__ float4 silu_d4_sum2_scaled(const uint32_t* __restrict__ a, float4 b, float4 g) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t t01 = sub2(x01, mul2(x01, s01)), t23 = sub2(x23, mul2(x23, s23));
+  float4 y;
+  upk(mul2(pk(g.x, g.y), fma2(s01, t01, s01)), y.x, y.y);
+  upk(mul2(pk(g.z, g.w), fma2(s23, t23, s23)), y.z, y.w);
+  return y;
+}
+
+// Four sigmoids from four MUFU.EX2 and ONE MUFU.RCP: 1/d_i = d_j d_k d_l / (d_0 d_1 d_2 d_3) with d = 1 + e^-x.
+// x is clamped at -20 inside the exponential (d <= 2^29, so the product of four stays below 2^116);
+// sigmoid(-20) = 2e-9, i.e. silu and its derivative are reproduced to ~1e-7 absolute below the clamp.
+__device__ __forceinline__ void sig4_fast(float x0, float x1, float x2, float x3, float& s0, float& s1, float& s2,
+                                          float& s3) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;   // -log2(e), 20 log2(e)
+  const float d0 = 1.0f + ex2_ftz(fminf(kL * x0, kClamp)), d1 = 1.0f + ex2_ftz(fminf(kL * x1, kClamp));
+  const float d2 = 1.0f + ex2_ftz(fminf(kL * x2, kClamp)), d3 = 1.0f + ex2_ftz(fminf(kL * x3, kClamp));
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
+  s0 = r01 * d1;
+  s1 = r01 * d0;
+  s2 = r23 * d3;
+  s3 = r23 * d2;
+}
+__device__ __forceinline__ float4 silu4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(x0 * s0, x1 * s1, x2 * s2, x3 * s3);
+}
+__device__ __forceinline__ void silu_fd4_fast(float x0, float x1, float x2, float x3, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  f[0] = x0 * s0;
+  f[1] = x1 * s1;
+  f[2] = x2 * s2;
+  f[3] = x3 * s3;
+  d[0] = fmaf(f[0], 1.0f - s0, s0);
+  d[1] = fmaf(f[1], 1.0f - s1, s1);
+  d[2] = fmaf(f[2], 1.0f - s2, s2);
+  d[3] = fmaf(f[3], 1.0f - s3, s3);
+}
+__device__ __forceinline__ float4 silu_d4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(fmaf(s0, fmaf(-x0, s0, x0), s0), fmaf(s1, fmaf(-x1, s1, x1), s1), fmaf(s2, fmaf(-x2, s2, x2), s2),
+                     fmaf(s3, fmaf(-x3, s3, x3), s3));
+}
 // stage a K-major B operand [rows][kdim] (element (n,k) = src[n*ld_n + k*ld_k], zero outside n_valid x k_valid)
 // as hi / lo TF32 parts in the SW128 layout
 __device__ __forceinline__ void stage_b_operand(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int rows,
@@ -160,24 +307,6 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
   for (int j = 0; j < 32; ++j) split_tf32(x[j], h[j], l[j]);
   tmem_st32(t_hi, h);
   tmem_st32(t_lo, l);
-}
-
-// radial operand rows: only the 24 columns that the K = 24 products read (20 basis functions + 4 zeros)
-__device__ __forceinline__ void st_split24(uint32_t t_hi, uint32_t t_lo, const float (&x)[32]) {
-  {
-    uint32_t h[16], l[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) split_tf32(x[j], h[j], l[j]);
-    tmem_st16(t_hi, h);
-    tmem_st16(t_lo, l);
-  }
-  {
-    uint32_t h[8], l[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) split_tf32(x[16 + j], h[j], l[j]);
-    tmem_st8(t_hi + 16, h);
-    tmem_st8(t_lo + 16, l);
-  }
 }
 
 // Per-tile keys (double-buffered by tile parity so that the reduction of tile t may overlap the set-up of t+1)
@@ -664,7 +793,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<false>(r, g.inv_cutoff, o, od);
-        st_split24(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
+        st_split(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
         tmem_st_wait();
         warp_arrive_i(u_ok, lane);
       }
@@ -730,7 +859,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             rbf_regs<false>(r_n, g.inv_cutoff, o, od);
             mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
             __syncwarp();
-            st_split24(lane_addr + cur, lane_addr + cur + 32, o);
+            st_split(lane_addr + cur, lane_addr + cur + 32, o);
             tmem_st_wait();
             warp_arrive_i(u_ok, lane);
           }
@@ -901,8 +1030,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<true>(r, g.inv_cutoff, o, od);
-        st_split24(lane_addr + XH, lane_addr + XL, o);
-        st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od);
+        st_split(lane_addr + XH, lane_addr + XL, o);
+        st_split(lane_addr + XH + 32, lane_addr + XL + 32, od);
         tmem_st_wait();
       }
       if (warp_arrive_last(cnt_u, 8, lane)) issue_u_du();
@@ -1024,8 +1153,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         // vbar is complete, so the X operand columns are free: the radial operands of the next tile leave the
         // registers before the last epilogue needs them
         if (has_next && ch == 0) {
-          st_split24(lane_addr + XH, lane_addr + XL, o_n);
-          st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
+          st_split(lane_addr + XH, lane_addr + XL, o_n);
+          st_split(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
         }
         // slot of this edge in the dense pair-adjoint array; its previous value is fetched early (layers 2, 1 add)
         size_t rslot = 0;
@@ -1045,21 +1174,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           tmem_ld16(lane_addr + DU + col0, dr);
           tmem_ld_wait();
           float* urow = sU + row * kTileLd + col0;
-          f2_t rab = pk(0.0f, 0.0f);
+          float ra = 0.0f, rb = 0.0f;
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float* ds = &dsu[16 * c + 4 * j4];
-            const f2_t u01 = mul2(pk(__uint_as_float(vr[4 * j4 + 0]), __uint_as_float(vr[4 * j4 + 1])), pk(ds[0], ds[1]));
-            const f2_t u23 = mul2(pk(__uint_as_float(vr[4 * j4 + 2]), __uint_as_float(vr[4 * j4 + 3])), pk(ds[2], ds[3]));
-            rab = fma2(u01, pk(__uint_as_float(dr[4 * j4 + 0]), __uint_as_float(dr[4 * j4 + 1])), rab);
-            rab = fma2(u23, pk(__uint_as_float(dr[4 * j4 + 2]), __uint_as_float(dr[4 * j4 + 3])), rab);
             float4 ub;
-            upk(u01, ub.x, ub.y);
-            upk(u23, ub.z, ub.w);
+            ub.x = __uint_as_float(vr[4 * j4 + 0]) * dsu[16 * c + 4 * j4 + 0];
+            ub.y = __uint_as_float(vr[4 * j4 + 1]) * dsu[16 * c + 4 * j4 + 1];
+            ub.z = __uint_as_float(vr[4 * j4 + 2]) * dsu[16 * c + 4 * j4 + 2];
+            ub.w = __uint_as_float(vr[4 * j4 + 3]) * dsu[16 * c + 4 * j4 + 3];
+            ra = fmaf(ub.x, __uint_as_float(dr[4 * j4 + 0]), ra);
+            rb = fmaf(ub.y, __uint_as_float(dr[4 * j4 + 1]), rb);
+            ra = fmaf(ub.z, __uint_as_float(dr[4 * j4 + 2]), ra);
+            rb = fmaf(ub.w, __uint_as_float(dr[4 * j4 + 3]), rb);
             *reinterpret_cast<float4*>(urow + 4 * j4) = ub;
           }
-          float ra, rb;
-          upk(rab, ra, rb);
           racc += ra + rb;
         }
         if (has_next) {

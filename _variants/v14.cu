@@ -34,7 +34,6 @@
 // while the tensor pipe works on tile t+1.
 #include "common.cuh"
 #include "umma.cuh"
-#include "fastmath.cuh"
 
 namespace gnnis {
 
@@ -61,6 +60,154 @@ struct EdgeTcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid = 1 / (1 + 2^(-x log2 e)): one MUFU.EX2 + one MUFU.RCP (~2 ulp); the parity gates guard this choice
+__device__ __forceinline__ float sig_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sig_fast(x); }
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issued instruction).  The epilogues are
+// bound by instruction issue, not by the FMA pipe, so halving the count of their add / mul / fma instructions pays.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// sigmoids of two packed pairs (same scheme as sig4_fast below)
+__device__ __forceinline__ void sig4_p(f2_t x01, f2_t x23, f2_t& s01, f2_t& s23) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;
+  const f2_t kL2 = pk(kL, kL), one2 = pk(1.0f, 1.0f);
+  float t0, t1, t2, t3;
+  upk(mul2(x01, kL2), t0, t1);
+  upk(mul2(x23, kL2), t2, t3);
+  const f2_t d01 = add2(pk(ex2_ftz(fminf(t0, kClamp)), ex2_ftz(fminf(t1, kClamp))), one2);
+  const f2_t d23 = add2(pk(ex2_ftz(fminf(t2, kClamp)), ex2_ftz(fminf(t3, kClamp))), one2);
+  float d0, d1, d2, d3;
+  upk(d01, d0, d1);
+  upk(d23, d2, d3);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;
+  s01 = pk(r01 * d1, r01 * d0);
+  s23 = pk(r23 * d3, r23 * d2);
+}
+// y = silu(a + b + c) for four consecutive channels (a: accumulator words, b, c: gathered rows)
+__device__ __forceinline__ float4 silu4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+__device__ __forceinline__ float4 silu4_sum2(const uint32_t* __restrict__ a, float4 b) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+// f = silu(x), d = silu'(x) = s + f (1 - s) for x = a + b + c
+__device__ __forceinline__ void silu_fd4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t one2 = pk(1.0f, 1.0f);
+  const f2_t f01 = mul2(x01, s01), f23 = mul2(x23, s23);
+  upk(f01, f[0], f[1]);
+  upk(f23, f[2], f[3]);
+  upk(fma2(f01, sub2(one2, s01), s01), d[0], d[1]);
+  upk(fma2(f23, sub2(one2, s23), s23), d[2], d[3]);
+}
+// g * silu'(a + b),  silu'(x) = s + s (x - x s)
+__device__ __forceinline__ float4 silu_d4_sum2_scaled(const uint32_t* __restrict__ a, float4 b, float4 g) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t t01 = sub2(x01, mul2(x01, s01)), t23 = sub2(x23, mul2(x23, s23));
+  float4 y;
+  upk(mul2(pk(g.x, g.y), fma2(s01, t01, s01)), y.x, y.y);
+  upk(mul2(pk(g.z, g.w), fma2(s23, t23, s23)), y.z, y.w);
+  return y;
+}
+
+// Four sigmoids from four MUFU.EX2 and ONE MUFU.RCP: 1/d_i = d_j d_k d_l / (d_0 d_1 d_2 d_3) with d = 1 + e^-x.
+// x is clamped at -20 inside the exponential (d <= 2^29, so the product of four stays below 2^116);
+// sigmoid(-20) = 2e-9, i.e. silu and its derivative are reproduced to ~1e-7 absolute below the clamp.
+__device__ __forceinline__ void sig4_fast(float x0, float x1, float x2, float x3, float& s0, float& s1, float& s2,
+                                          float& s3) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;   // -log2(e), 20 log2(e)
+  const float d0 = 1.0f + ex2_ftz(fminf(kL * x0, kClamp)), d1 = 1.0f + ex2_ftz(fminf(kL * x1, kClamp));
+  const float d2 = 1.0f + ex2_ftz(fminf(kL * x2, kClamp)), d3 = 1.0f + ex2_ftz(fminf(kL * x3, kClamp));
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
+  s0 = r01 * d1;
+  s1 = r01 * d0;
+  s2 = r23 * d3;
+  s3 = r23 * d2;
+}
+__device__ __forceinline__ float4 silu4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(x0 * s0, x1 * s1, x2 * s2, x3 * s3);
+}
+__device__ __forceinline__ void silu_fd4_fast(float x0, float x1, float x2, float x3, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  f[0] = x0 * s0;
+  f[1] = x1 * s1;
+  f[2] = x2 * s2;
+  f[3] = x3 * s3;
+  d[0] = fmaf(f[0], 1.0f - s0, s0);
+  d[1] = fmaf(f[1], 1.0f - s1, s1);
+  d[2] = fmaf(f[2], 1.0f - s2, s2);
+  d[3] = fmaf(f[3], 1.0f - s3, s3);
+}
+__device__ __forceinline__ float4 silu_d4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(fmaf(s0, fmaf(-x0, s0, x0), s0), fmaf(s1, fmaf(-x1, s1, x1), s1), fmaf(s2, fmaf(-x2, s2, x2), s2),
+                     fmaf(s3, fmaf(-x3, s3, x3), s3));
+}
 // stage a K-major B operand [rows][kdim] (element (n,k) = src[n*ld_n + k*ld_k], zero outside n_valid x k_valid)
 // as hi / lo TF32 parts in the SW128 layout
 __device__ __forceinline__ void stage_b_operand(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int rows,
@@ -123,6 +270,28 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 
 // radial basis row in registers (GNN_Layers.py:2194-2208): d = r/cutoff, env = 1/d - 28 d^5 + 48 d^6 - 21 d^7,
 // rbf_k = env sin(k pi d); sin/cos(k pi d) from one sincospi and the Chebyshev recurrence.  o[20..31] = 0.
+// radial derivative row only (d rbf_k / dr), for the warps that hold the du operand
+__device__ __forceinline__ void drbf_regs(float r, float inv_cutoff, float (&od)[32]) {
+  const float d = r * inv_cutoff;
+  const float d2 = d * d, d4 = d2 * d2, d5 = d4 * d;
+  const float env = (1.0f / d - 28.0f * d5 + 48.0f * (d5 * d) - 21.0f * (d5 * d2)) * inv_cutoff;
+  const float denv = (-1.0f / d2 - 140.0f * d4 + 288.0f * d5 - 147.0f * (d5 * d)) * inv_cutoff;
+  float s1, c1;
+  sincospif(d, &s1, &c1);
+  const float twoc = 2.0f * c1;
+  float sp = 0.0f, sc = s1, cp = 1.0f, cc = c1;
+#pragma unroll
+  for (int k = 0; k < kRbf; ++k) {
+    od[k] = fmaf(denv, sc, env * (3.14159265358979323846f * (float)(k + 1)) * cc);
+    const float sn = fmaf(twoc, sc, -sp), cn = fmaf(twoc, cc, -cp);
+    sp = sc;
+    sc = sn;
+    cp = cc;
+    cc = cn;
+  }
+#pragma unroll
+  for (int k = kRbf; k < 32; ++k) od[k] = 0.0f;
+}
 template <bool DERIV>
 __device__ __forceinline__ void rbf_regs(float r, float inv_cutoff, float (&o)[32], float (&od)[32]) {
   const float d = r * inv_cutoff;
@@ -875,17 +1044,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       bool valid = e_begin + row < e_end;
       if (valid) {
         pr = g.pair[e_begin + row];
-        if (ch == 0) {
-          r = g.r_e[e_begin + row];
-          pm = g.perm[e_begin + row];
-        }
+        r = g.r_e[e_begin + row];
+        if (ch == 0) pm = g.perm[e_begin + row];
       }
       if (e_begin + kTileE + row < e_end) {
         pr_n = g.pair[e_begin + kTileE + row];
-        if (ch == 0) {
-          r_n = g.r_e[e_begin + kTileE + row];
-          pm_n = g.perm[e_begin + kTileE + row];
-        }
+        r_n = g.r_e[e_begin + kTileE + row];
+        if (ch == 0) pm_n = g.perm[e_begin + kTileE + row];
       }
       TileKeys* tk = keys + kidx;
       if (ch == 0) {
@@ -898,11 +1063,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         prefetch_l1(gP + t_);
         prefetch_l1(gAb + t_);
       }
-      if (ch == 0) {
-        float o[32], od[32];
-        rbf_regs<true>(r, g.inv_cutoff, o, od);
-        st_split24(lane_addr + XH, lane_addr + XL, o);
-        st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od);
+      {   // column half 0 holds the radial basis row (operand of u), half 1 its derivative (operand of du)
+        float x[32], unused[32];
+        if (ch == 0) rbf_regs<false>(r, g.inv_cutoff, x, unused);
+        else drbf_regs(r, g.inv_cutoff, x);
+        st_split24(lane_addr + XH + 32 * ch, lane_addr + XL + 32 * ch, x);
         tmem_st_wait();
       }
       if (warp_arrive_last(cnt_u, 8, lane)) issue_u_du();
@@ -1004,18 +1169,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           prefetch_l1(gAb + t_);
           if (t0 + 2 * kTileE + row < e_end) {
             pr_nn = g.pair[t0 + 2 * kTileE + row];
-            if (ch == 0) {
-              r_nn = g.r_e[t0 + 2 * kTileE + row];
-              pm_nn = g.perm[t0 + 2 * kTileE + row];
-            }
+            r_nn = g.r_e[t0 + 2 * kTileE + row];
+            if (ch == 0) pm_nn = g.perm[t0 + 2 * kTileE + row];
           }
         }
         // radial operands of the next tile are computed now (registers), while vbar runs, and stored after epi3
-        float o_n[32], od_n[32];
-        if (has_next && ch == 0) {
-          rbf_regs<true>(r_n, g.inv_cutoff, o_n, od_n);
+        float x_n[32];
+        if (has_next) {
+          float unused[32];
+          if (ch == 0) rbf_regs<false>(r_n, g.inv_cutoff, x_n, unused);
+          else drbf_regs(r_n, g.inv_cutoff, x_n);
 #pragma unroll
-          for (int k = 0; k < kRbf; ++k) asm volatile("" : "+f"(o_n[k]), "+f"(od_n[k]));   // keep the work above the wait
+          for (int k = 0; k < kRbf; ++k) asm volatile("" : "+f"(x_n[k]));   // keep the work above the wait
         }
         mbar_wait(d_full, ph_d);
         __syncwarp();
@@ -1023,10 +1188,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         fence_after_sync();
         // vbar is complete, so the X operand columns are free: the radial operands of the next tile leave the
         // registers before the last epilogue needs them
-        if (has_next && ch == 0) {
-          st_split24(lane_addr + XH, lane_addr + XL, o_n);
-          st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
-        }
+        if (has_next) st_split24(lane_addr + XH + 32 * ch, lane_addr + XL + 32 * ch, x_n);
         // slot of this edge in the dense pair-adjoint array; its previous value is fetched early (layers 2, 1 add)
         size_t rslot = 0;
         float rold = 0.0f;
@@ -1063,7 +1225,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           racc += ra + rb;
         }
         if (has_next) {
-          if (ch == 0) tmem_st_wait();
+          tmem_st_wait();
           if (warp_arrive_last(cnt_u, 8, lane)) issue_u_du();   // ACC / DU drained, radial operands in place
         }
         if (ch == 1) sPart[grp][row] = racc;

@@ -1,0 +1,179 @@
+// fastmath.cuh -- activation math shared by the edge and node tensor-core kernels (sm_100a): MUFU-based sigmoid / SiLU
+// (ex2.approx + rcp.approx, ~2 ulp; guarded by the parity gates) and packed fp32 pairs (FADD2 / FMUL2 / FFMA2).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gnnis {
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid = 1 / (1 + 2^(-x log2 e)): one MUFU.EX2 + one MUFU.RCP (~2 ulp); the parity gates guard this choice
+__device__ __forceinline__ float sig_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sig_fast(x); }
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issued instruction).  The epilogues are
+// bound by instruction issue, not by the FMA pipe, so halving the count of their add / mul / fma instructions pays.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// sigmoids of two packed pairs (same scheme as sig4_fast below)
+__device__ __forceinline__ void sig4_p(f2_t x01, f2_t x23, f2_t& s01, f2_t& s23) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;
+  const f2_t kL2 = pk(kL, kL), one2 = pk(1.0f, 1.0f);
+  float t0, t1, t2, t3;
+  upk(mul2(x01, kL2), t0, t1);
+  upk(mul2(x23, kL2), t2, t3);
+  const f2_t d01 = add2(pk(ex2_ftz(fminf(t0, kClamp)), ex2_ftz(fminf(t1, kClamp))), one2);
+  const f2_t d23 = add2(pk(ex2_ftz(fminf(t2, kClamp)), ex2_ftz(fminf(t3, kClamp))), one2);
+  float d0, d1, d2, d3;
+  upk(d01, d0, d1);
+  upk(d23, d2, d3);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;
+  s01 = pk(r01 * d1, r01 * d0);
+  s23 = pk(r23 * d3, r23 * d2);
+}
+// y = silu(a + b + c) for four consecutive channels (a: accumulator words, b, c: gathered rows)
+__device__ __forceinline__ float4 silu4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+__device__ __forceinline__ float4 silu4_sum2(const uint32_t* __restrict__ a, float4 b) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+// f = silu(x), d = silu'(x) = s + f (1 - s) for x = a + b + c
+__device__ __forceinline__ void silu_fd4_sum3(const uint32_t* __restrict__ a, float4 b, float4 c, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), add2(pk(b.x, b.y), pk(c.x, c.y)));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), add2(pk(b.z, b.w), pk(c.z, c.w)));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t one2 = pk(1.0f, 1.0f);
+  const f2_t f01 = mul2(x01, s01), f23 = mul2(x23, s23);
+  upk(f01, f[0], f[1]);
+  upk(f23, f[2], f[3]);
+  upk(fma2(f01, sub2(one2, s01), s01), d[0], d[1]);
+  upk(fma2(f23, sub2(one2, s23), s23), d[2], d[3]);
+}
+// g * silu'(a + b),  silu'(x) = s + s (x - x s)
+__device__ __forceinline__ float4 silu_d4_sum2_scaled(const uint32_t* __restrict__ a, float4 b, float4 g) {
+  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
+  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t t01 = sub2(x01, mul2(x01, s01)), t23 = sub2(x23, mul2(x23, s23));
+  float4 y;
+  upk(mul2(pk(g.x, g.y), fma2(s01, t01, s01)), y.x, y.y);
+  upk(mul2(pk(g.z, g.w), fma2(s23, t23, s23)), y.z, y.w);
+  return y;
+}
+
+// plain float4 forms (node kernels)
+__device__ __forceinline__ float4 silu4(float4 x) {
+  const f2_t x01 = pk(x.x, x.y), x23 = pk(x.z, x.w);
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  float4 y;
+  upk(mul2(x01, s01), y.x, y.y);
+  upk(mul2(x23, s23), y.z, y.w);
+  return y;
+}
+__device__ __forceinline__ float4 silu_d4_scaled(float4 x, float4 g) {
+  const f2_t x01 = pk(x.x, x.y), x23 = pk(x.z, x.w);
+  f2_t s01, s23;
+  sig4_p(x01, x23, s01, s23);
+  const f2_t t01 = sub2(x01, mul2(x01, s01)), t23 = sub2(x23, mul2(x23, s23));
+  float4 y;
+  upk(mul2(pk(g.x, g.y), fma2(s01, t01, s01)), y.x, y.y);
+  upk(mul2(pk(g.z, g.w), fma2(s23, t23, s23)), y.z, y.w);
+  return y;
+}
+
+// Four sigmoids from four MUFU.EX2 and ONE MUFU.RCP: 1/d_i = d_j d_k d_l / (d_0 d_1 d_2 d_3) with d = 1 + e^-x.
+// x is clamped at -20 inside the exponential (d <= 2^29, so the product of four stays below 2^116);
+// sigmoid(-20) = 2e-9, i.e. silu and its derivative are reproduced to ~1e-7 absolute below the clamp.
+__device__ __forceinline__ void sig4_fast(float x0, float x1, float x2, float x3, float& s0, float& s1, float& s2,
+                                          float& s3) {
+  constexpr float kL = -1.4426950408889634f, kClamp = 28.853900817779268f;   // -log2(e), 20 log2(e)
+  const float d0 = 1.0f + ex2_ftz(fminf(kL * x0, kClamp)), d1 = 1.0f + ex2_ftz(fminf(kL * x1, kClamp));
+  const float d2 = 1.0f + ex2_ftz(fminf(kL * x2, kClamp)), d3 = 1.0f + ex2_ftz(fminf(kL * x3, kClamp));
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_ftz(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
+  s0 = r01 * d1;
+  s1 = r01 * d0;
+  s2 = r23 * d3;
+  s3 = r23 * d2;
+}
+__device__ __forceinline__ float4 silu4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(x0 * s0, x1 * s1, x2 * s2, x3 * s3);
+}
+__device__ __forceinline__ void silu_fd4_fast(float x0, float x1, float x2, float x3, float* __restrict__ f,
+                                              float* __restrict__ d) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  f[0] = x0 * s0;
+  f[1] = x1 * s1;
+  f[2] = x2 * s2;
+  f[3] = x3 * s3;
+  d[0] = fmaf(f[0], 1.0f - s0, s0);
+  d[1] = fmaf(f[1], 1.0f - s1, s1);
+  d[2] = fmaf(f[2], 1.0f - s2, s2);
+  d[3] = fmaf(f[3], 1.0f - s3, s3);
+}
+__device__ __forceinline__ float4 silu_d4_fast(float x0, float x1, float x2, float x3) {
+  float s0, s1, s2, s3;
+  sig4_fast(x0, x1, x2, x3, s0, s1, s2, s3);
+  return make_float4(fmaf(s0, fmaf(-x0, s0, x0), s0), fmaf(s1, fmaf(-x1, s1, x1), s1), fmaf(s2, fmaf(-x2, s2, x2), s2),
+                     fmaf(s3, fmaf(-x3, s3, x3), s3));
+}
+
+}  // namespace gnnis

@@ -1,18 +1,25 @@
 // node_mlp_tc.cu -- the per-atom ("nodewise") MLPs of IN_layer_all_swish_2pass_tokens (GNN_Layers.py:2231-2246)
 // and their adjoints on the tensor cores (tcgen05, 3xTF32, sm_100a).  Same arithmetic as node_mlp.cu (which stays
-// as the CUDA-core cross-check); rows are atoms, 128 per tile, one persistent CTA per SM, 256 threads:
-// thread = (row = TMEM lane, column half).  A operands are written to TMEM by the epilogue of the previous
-// product; weights are staged once per CTA as K-major 128B-swizzled hi / lo operands.
+// as the CUDA-core cross-check).
 //
-//   forward  (layer l):  p = a W3a^T + sbias[s]      [128 x 64] x [64 x 128]
-//                        o = silu(p) W4^T + b4       [128 x 128] x [128 x 64]   (-> global)
-//                        [P|Q]_{l+1} = silu(o) [Wi;Wj]^T (+ b1)   [128 x 64] x [64 x 128]
+// Rows are atoms, 128 per tile.  One persistent CTA per SM with TWO independent groups of 4 warps: each group walks
+// its own tiles (thread = row = TMEM lane, all columns) and owns 256 of the 512 TMEM columns, so the products of one
+// group run under the epilogue (global loads, SiLU, hi / lo split) of the other.  A operands are written to TMEM by
+// the epilogue of the previous product; weights are staged once per CTA as K-major 128B-swizzled hi / lo images.
+// Per group the TMEM columns are R0 = [0,128) (A operand: hi | lo of at most 64 features) and R1 = [128,256)
+// (accumulators); products over 128 features are issued as two K halves so that the operand fits R0:
+//
+//   forward  (layer l):  p  = a W3a^T                              R0 = a        -> R1 = p        (N 128, K 64)
+//                        o  = silu(p + sbias[s]) W4^T + b4         R0 = g[:, h]  -> R1[0,64) = o  (N 64, K 64 + 64)
+//                        [P|Q]_{l+1} = silu(o) [Wi;Wj]^T (+ b1)    R0 = silu(o)  -> R1 = [P|Q]    (N 128, K 64)
 //            last layer: o3 = silu(p) W4^T + b4 (2 outputs, CUDA cores) and the scale / SA head
-//   adjoint A (l < 2):   hbar = [Pbar|Qbar] [Wi;Wj]  [128 x 128] x [128 x 64];  obar = hbar silu'(o)
-//                        gbar = obar W4              [128 x 64] x [64 x 128]    (-> global scratch [n][128])
-//   adjoint B:           p recomputed; pbar = gbar silu'(p);  abar = pbar W3a   [128 x 128] x [128 x 64]
+//   adjoint A (l < 2):   hbar = Pbar Wi + Qbar Wj                  R0 = Pbar, Qbar -> R1[0,64)    (N 64, K 64 + 64)
+//                        gbar = (hbar silu'(o)) W4                 R0 = obar     -> R1 = gbar     (N 128, K 64)
+//   adjoint B:           p recomputed as in the forward pass;  pbar = gbar silu'(p + sbias)
+//                        abar = pbar W3a                           R0 = pbar[:, h] -> R1[0,64)    (N 64, K 64 + 64)
 #include "common.cuh"
 #include "umma.cuh"
+#include "fastmath.cuh"
 
 namespace gnnis {
 
@@ -39,110 +46,119 @@ struct NodeTcArgs {
   float *gbar, *abar, *Bbar;
 };
 
-__device__ __forceinline__ float nt_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float nt_rcp(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float nt_sig(float x) { return nt_rcp(1.0f + nt_ex2(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float nt_silu(float x) { return x * nt_sig(x); }
-__device__ __forceinline__ float nt_silu_d(float x) {
-  const float sg = nt_sig(x);
-  return fmaf(sg, fmaf(-x, sg, x), sg);
-}
-
 __device__ __forceinline__ void nt_copy_image(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int bytes) {
   for (int t = threadIdx.x * 16; t < bytes; t += blockDim.x * 16)
     *reinterpret_cast<uint4*>(dst + t) = __ldg(reinterpret_cast<const uint4*>(src + t));
 }
+__device__ __forceinline__ void nt_group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
-// D[128 x N] = A[128 x 8 KSTEPS] * B^T (3xTF32), A in TMEM, B K-major SW128 with b_rows rows
-template <int KSTEPS>
+// D[128 x N] (+)= A[128 x 8 (S1 - S0)] * B[:, 8 S0 .. 8 S1)^T (3xTF32): A (hi, lo) in TMEM starting at column 0 of
+// its region, B K-major SW128 with b_rows rows
+template <int S0, int S1>
 __device__ __forceinline__ void nt_issue(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                         int b_rows, uint32_t idesc) {
-  uint32_t acc = 0;
+                                         int b_rows, uint32_t idesc, uint32_t accumulate) {
+  uint32_t acc = accumulate;
 #pragma unroll
   for (int term = 0; term < 3; ++term) {
     const uint32_t a = term == 2 ? a_lo : a_hi;
     const uint32_t b = term == 1 ? b_lo : b_hi;
 #pragma unroll
-    for (int s = 0; s < KSTEPS; ++s) {
+    for (int s = S0; s < S1; ++s) {
       uint32_t baddr = b + (uint32_t)(s >> 2) * (uint32_t)b_rows * 128u + (uint32_t)(s & 3) * 32u;
-      mma_tf32_ts(d_tmem, a + 8u * (uint32_t)s, smem_desc_k_sw128(baddr), idesc, acc);
+      mma_tf32_ts(d_tmem, a + 8u * (uint32_t)(s - S0), smem_desc_k_sw128(baddr), idesc, acc);
       acc = 1;
     }
   }
 }
 
-__device__ __forceinline__ void nt_store_a16(uint32_t t_hi, uint32_t t_lo, const float (&x)[16]) {
+__device__ __forceinline__ void nt_store_a16(uint32_t t_hi, uint32_t t_lo, const float4 (&x)[4]) {
   uint32_t h[16], l[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) split_tf32(x[j], h[j], l[j]);
+  for (int j = 0; j < 4; ++j) {
+    h[4 * j + 0] = __float_as_uint(x[j].x) & 0xFFFFE000u;
+    h[4 * j + 1] = __float_as_uint(x[j].y) & 0xFFFFE000u;
+    h[4 * j + 2] = __float_as_uint(x[j].z) & 0xFFFFE000u;
+    h[4 * j + 3] = __float_as_uint(x[j].w) & 0xFFFFE000u;
+    float l0, l1, l2, l3;
+    upk(sub2(pk(x[j].x, x[j].y), pk(__uint_as_float(h[4 * j]), __uint_as_float(h[4 * j + 1]))), l0, l1);
+    upk(sub2(pk(x[j].z, x[j].w), pk(__uint_as_float(h[4 * j + 2]), __uint_as_float(h[4 * j + 3]))), l2, l3);
+    l[4 * j + 0] = __float_as_uint(l0);
+    l[4 * j + 1] = __float_as_uint(l1);
+    l[4 * j + 2] = __float_as_uint(l2);
+    l[4 * j + 3] = __float_as_uint(l3);
+  }
   tmem_st16(t_hi, h);
   tmem_st16(t_lo, l);
 }
 
 // 16 consecutive floats of a global row (zero when the row is past the end)
-__device__ __forceinline__ void nt_load16(const float* __restrict__ p, bool ok, float (&x)[16]) {
-#pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) {
-    float4 v = ok ? __ldg(reinterpret_cast<const float4*>(p) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    x[4 * j4 + 0] = v.x;
-    x[4 * j4 + 1] = v.y;
-    x[4 * j4 + 2] = v.z;
-    x[4 * j4 + 3] = v.w;
-  }
-}
-__device__ __forceinline__ void nt_store16(float* __restrict__ p, const float (&x)[16]) {
+__device__ __forceinline__ void nt_load16(const float* __restrict__ p, bool ok, float4 (&x)[4]) {
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4)
-    *(reinterpret_cast<float4*>(p) + j4) = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+    x[j4] = ok ? __ldg(reinterpret_cast<const float4*>(p) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void nt_store16(float* __restrict__ p, const float4 (&x)[4]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) *(reinterpret_cast<float4*>(p) + j4) = x[j4];
+}
+__device__ __forceinline__ float4 nt_acc4(const uint32_t* r) {
+  return make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+}
+__device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
+  float4 y;
+  upk(add2(pk(a.x, a.y), pk(b.x, b.y)), y.x, y.y);
+  upk(add2(pk(a.z, a.w), pk(b.z, b.w)), y.z, y.w);
+  return y;
 }
 
 #define NT_PROLOGUE()                                                              \
   extern __shared__ uint8_t smraw[];                                               \
-  __shared__ uint64_t bar;                                                         \
+  __shared__ uint64_t bar[2];                                                      \
   __shared__ uint32_t tmem_slot;                                                   \
   uint32_t base_ = smem_u32(smraw);                                                \
   uint8_t* sm = smraw + ((1024u - (base_ & 1023u)) & 1023u);                       \
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                   \
-  const int wq = warp & 3, ch = warp >> 2, row = 32 * wq + lane;                   \
+  const int grp = warp >> 2, wq = warp & 3, row = 32 * wq + lane;                  \
   if (warp == 0) tmem_alloc(&tmem_slot, 512);                                      \
-  if (tid == 0) mbar_init(&bar, 1);
+  if (tid == 0) {                                                                  \
+    mbar_init(&bar[0], 1);                                                         \
+    mbar_init(&bar[1], 1);                                                         \
+  }
 
 #define NT_STAGED()                                                                \
   fence_proxy_async_smem();                                                        \
   fence_before_sync();                                                             \
   __syncthreads();                                                                 \
   fence_after_sync();                                                              \
-  const uint32_t tm = tmem_slot;                                                   \
+  const uint32_t tm = tmem_slot + 256u * (uint32_t)grp;                            \
   const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);                     \
-  uint32_t phase = 0;
+  uint32_t phase = 0;                                                              \
+  (void)lane;
 
-// all threads: A operand stored -> one elected lane of warp 0 issues -> everybody waits for the product
-#define NT_GEMM(ISSUE_STMT)                                                        \
+// this group: A operand stored -> one elected lane of the group's first warp issues
+#define NT_ISSUE(...)                                                              \
   tmem_st_wait();                                                                  \
   fence_before_sync();                                                             \
-  __syncthreads();                                                                 \
-  if (warp == 0) {                                                                 \
+  nt_group_sync(grp);                                                              \
+  if (wq == 0) {                                                                   \
     fence_after_sync();                                                            \
     if (elect_one()) {                                                             \
-      ISSUE_STMT;                                                                  \
-      mma_commit(&bar);                                                            \
+      __VA_ARGS__;                                                                 \
+      mma_commit(&bar[grp]);                                                       \
     }                                                                              \
     __syncwarp();                                                                  \
-  }                                                                                \
-  mbar_wait(&bar, phase);                                                          \
+  }
+// ... and every thread of the group waits for the product
+#define NT_WAIT()                                                                  \
+  mbar_wait(&bar[grp], phase);                                                     \
   __syncwarp();                                                                    \
   phase ^= 1;                                                                      \
   fence_after_sync();
+#define NT_GEMM(...)    \
+  NT_ISSUE(__VA_ARGS__) \
+  NT_WAIT()
 
-// true when every replica touched by the 128-atom tile is finished (uniform over the CTA)
+// true when every replica touched by the 128-atom tile is finished (uniform over the group)
 __device__ __forceinline__ bool nt_tile_skipped(const NodeTcArgs& g, int tile) {
   if (!g.skip) return false;
   const int r0 = (tile * kNtRows) / g.N, r1 = (min(g.n, tile * kNtRows + kNtRows) - 1) / g.N;
@@ -156,69 +172,66 @@ __device__ __forceinline__ bool nt_tile_skipped(const NodeTcArgs& g, int tile) {
   __syncthreads();                                                                 \
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 
+// one 64-feature global row -> hi | lo operand in R0
+__device__ __forceinline__ void nt_row64_to_r0(uint32_t lane_addr, const float* __restrict__ src, bool ok) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float4 x[4];
+    nt_load16(src + 16 * c, ok, x);
+    nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, x);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ forward
-// smem: W3a (128 x 64) hi|lo 64 KB | W4 (64 x 128) hi|lo 64 KB | [Wi;Wj]_next (128 x 64) hi|lo 64 KB | head scratch
-// TMEM: [0,128) a hi|lo -> o accumulator ; [128,256) p accumulator -> silu(o) hi|lo ; [256,512) silu(p) hi|lo -> [P|Q]
+// smem: W3a (128 x 64) hi|lo 64 KB | W4 (64 x 128) hi|lo 64 KB | [Wi;Wj]_next (128 x 64) hi|lo 64 KB
 template <bool LAST>
 __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
   uint8_t *sWpH = sm + 131072, *sWpL = sm + 163840;
-  float* sHead = reinterpret_cast<float*>(sm + (LAST ? 65536 : 196608));   // [128][2] partial head sums
   nt_copy_image(sm, g.img, LAST ? 65536 : 196608);
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aW3H = smem_u32(sW3H), aW3L = smem_u32(sW3L), aW4H = smem_u32(sW4H), aW4L = smem_u32(sW4L);
   const uint32_t aWpH = smem_u32(sWpH), aWpL = smem_u32(sWpL);
+  (void)aW4H; (void)aW4L; (void)aWpH; (void)aWpL; (void)idesc64;
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
     if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-    // ---- a rows -> TMEM (this thread: 32 of the 64 columns)
+    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok);
+    NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128, 0u));
+    const float* sb = g.sbias + (size_t)g.solvent_id[rr / g.N] * 128;
+    if constexpr (LAST) {
+      // o3 = W4 silu(p + sbias) + b4 (2 outputs) and the head: B' = B (f + kappa sig(c)), SA = gamma_s sig(s) (rho + off + 0.14)^2
+      float h0 = 0.0f, h1 = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = 32 * ch + 16 * c;
-      float x[16];
-      nt_load16(g.a + (size_t)rr * 64 + col0, ok, x);
-      nt_store_a16(lane_addr + col0, lane_addr + 64 + col0, x);
-    }
-    NT_GEMM(nt_issue<8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128));
-    // ---- g = silu(p + sbias[s])  (this thread: 64 of the 128 columns)
-    const float* sb = g.sbias + (size_t)g.solvent_id[rr / g.N] * 128 + 64 * ch;
-    float h0 = 0.0f, h1 = 0.0f;   // last layer: partial dot products with the two rows of W4
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pr[16];
+        tmem_ld16(lane_addr + 128 + 16 * c, pr);
+        float4 bs[4];
+        nt_load16(sb + 16 * c, true, bs);
+        tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col0 = 64 * ch + 16 * c;
-      uint32_t pr[16];
-      tmem_ld16(lane_addr + 128 + col0, pr);
-      float bs[16];
-      nt_load16(sb + 16 * c, true, bs);
-      tmem_ld_wait();
-      float gv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) gv[j] = nt_silu(__uint_as_float(pr[j]) + bs[j]);
-      if (LAST) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          h0 = fmaf(gv[j], __ldg(g.W4 + col0 + j), h0);
-          h1 = fmaf(gv[j], __ldg(g.W4 + 128 + col0 + j), h1);
+        for (int j = 0; j < 4; ++j) {
+          const float4 gv = silu4_sum2(&pr[4 * j], bs[j]);
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.W4 + 16 * c) + j);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.W4 + 128 + 16 * c) + j);
+          h0 = fmaf(gv.x, w0.x, h0);
+          h0 = fmaf(gv.y, w0.y, h0);
+          h0 = fmaf(gv.z, w0.z, h0);
+          h0 = fmaf(gv.w, w0.w, h0);
+          h1 = fmaf(gv.x, w1.x, h1);
+          h1 = fmaf(gv.y, w1.y, h1);
+          h1 = fmaf(gv.z, w1.z, h1);
+          h1 = fmaf(gv.w, w1.w, h1);
         }
-      } else {
-        nt_store_a16(lane_addr + 256 + col0, lane_addr + 384 + col0, gv);
       }
-    }
-    if (LAST) {
-      // o3 = W4 g + b4 (2 outputs) and the head: B' = B (f + kappa sig(c)), SA = gamma_s sig(s) (rho + off + 0.14)^2
-      if (ch == 1) {
-        sHead[2 * row] = h0;
-        sHead[2 * row + 1] = h1;
-      }
-      __syncthreads();
-      if (ch == 0 && ok) {
-        const float c0 = (h0 + sHead[2 * row]) + g.b4[0], c1 = (h1 + sHead[2 * row + 1]) + g.b4[1];
+      if (ok) {
+        const float c0 = h0 + g.b4[0], c1 = h1 + g.b4[1];
         g.o[2 * (size_t)r] = c0;
         g.o[2 * (size_t)r + 1] = c1;
         const int a = r % g.N;
@@ -226,55 +239,79 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
         g.sa_atom[r] = g.gamma_emb[g.solvent_id[r / g.N]] * (sigmoidf_(c1) * (rp * rp));
         g.born_s[r] = g.born[r] * (g.fraction + sigmoidf_(c0) * g.kappa);
       }
-      fence_before_sync();
-      __syncthreads();   // sHead and the TMEM regions are reused by the next tile
       continue;
     }
-    NT_GEMM(nt_issue<16>(tm + 0, tm + 256, tm + 384, aW4H, aW4L, 64, idesc64));
-    // ---- o = acc + b4 -> global ; h = silu(o) -> TMEM  (this thread: 32 of the 64 columns)
+    if constexpr (!LAST) {
+    // ---- g = silu(p + sbias[s]), first 64 features -> R0
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = 32 * ch + 16 * c;
-      uint32_t orr[16];
-      tmem_ld16(lane_addr + col0, orr);
-      float bs[16];
-      nt_load16(g.b4 + col0, true, bs);
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pr[16];
+      tmem_ld16(lane_addr + 128 + 16 * c, pr);
+      float4 bs[4], gv[4];
+      nt_load16(sb + 16 * c, true, bs);
       tmem_ld_wait();
-      float ov[16], hv[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        ov[j] = __uint_as_float(orr[j]) + bs[j];
-        hv[j] = nt_silu(ov[j]);
-      }
-      if (ok) nt_store16(g.o + (size_t)r * 64 + col0, ov);
-      nt_store_a16(lane_addr + 128 + col0, lane_addr + 192 + col0, hv);
+      for (int j = 0; j < 4; ++j) gv[j] = silu4_sum2(&pr[4 * j], bs[j]);
+      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, gv);
     }
-    NT_GEMM(nt_issue<8>(tm + 256, tm + 128, tm + 192, aWpH, aWpL, 128, idesc128));
-    // ---- tables of the next layer: ch 0 -> P = . + b1, ch 1 -> Q
-    {
-      float* dst = (ch == 0 ? g.P_next : g.Q_next) + (size_t)rr * 64;
+    NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW4H, aW4L, 64, idesc64, 0u));
+    // ---- second 64 features are evaluated while the first half product runs (it writes R1[0,64), read above)
+    float4 g2[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t ar[16];
-        tmem_ld16(lane_addr + 256 + 64 * ch + 16 * c, ar);
-        float bs[16];
-        nt_load16(g.b1_next + 16 * c, ch == 0, bs);
-        tmem_ld_wait();
-        float v[16];
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pr[16];
+      tmem_ld16(lane_addr + 192 + 16 * c, pr);
+      float4 bs[4];
+      nt_load16(sb + 64 + 16 * c, true, bs);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ar[j]) + bs[j];
-        if (ok) nt_store16(dst + 16 * c, v);
-      }
+      for (int j = 0; j < 4; ++j) g2[4 * c + j] = silu4_sum2(&pr[4 * j], bs[j]);
     }
-    fence_before_sync();
-    __syncthreads();
+    NT_WAIT();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4(&gv)[4] = *reinterpret_cast<const float4(*)[4]>(&g2[4 * c]);
+      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, gv);
+    }
+    NT_GEMM(nt_issue<8, 16>(tm + 128, tm + 0, tm + 64, aW4H, aW4L, 64, idesc64, 1u));
+    // ---- o = acc + b4 -> global ; h = silu(o) -> R0
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t orr[16];
+      tmem_ld16(lane_addr + 128 + 16 * c, orr);
+      float4 bs[4];
+      nt_load16(g.b4 + 16 * c, true, bs);
+      tmem_ld_wait();
+      float4 ov[4], hv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ov[j] = nt_add4(nt_acc4(&orr[4 * j]), bs[j]);
+        hv[j] = silu4(ov[j]);
+      }
+      if (ok) nt_store16(g.o + (size_t)r * 64 + 16 * c, ov);
+      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, hv);
+    }
+    NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 128, idesc128, 0u));
+    // ---- tables of the next layer: columns [0,64) -> P = . + b1, [64,128) -> Q
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t ar[16];
+      tmem_ld16(lane_addr + 128 + 16 * c, ar);
+      float4 bs[4];
+      nt_load16(g.b1_next + 16 * (c & 3), c < 4, bs);
+      tmem_ld_wait();
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = nt_add4(nt_acc4(&ar[4 * j]), bs[j]);
+      if (ok) nt_store16((c < 4 ? g.P_next : g.Q_next) + (size_t)r * 64 + 16 * (c & 3), v);
+    }
+    }   // !LAST
   }
   NT_EPILOGUE();
 }
 
 // ------------------------------------------------------------------------------------------ adjoint A (layers 1, 2)
 // smem: [Wi;Wj]^T as B[n = c_in (64)][k = (which, c_out) (128)] hi|lo 64 KB | W4^T as B[n = m (128)][k = c (64)] hi|lo 64 KB
-// TMEM: [0,256) [Pbar|Qbar] hi (128) | lo (128) -> gbar accumulator [0,128) ; [256,320) hbar ; [320,448) obar hi|lo
 __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sWpH = sm, *sWpL = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
@@ -284,140 +321,139 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
   const uint32_t aWpH = smem_u32(sWpH), aWpL = smem_u32(sWpL), aW4H = smem_u32(sW4H), aW4L = smem_u32(sW4L);
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
     if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-    {
-      const float* src = (ch == 0 ? g.Pbar : g.Qbar) + (size_t)rr * 64;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float x[16];
-        nt_load16(src + 16 * c, ok, x);
-        nt_store_a16(lane_addr + 64 * ch + 16 * c, lane_addr + 128 + 64 * ch + 16 * c, x);
-      }
-    }
-    NT_GEMM(nt_issue<16>(tm + 256, tm + 0, tm + 128, aWpH, aWpL, 64, idesc64));
-    // ---- obar = hbar * silu'(o)  (this thread: 32 of the 64 columns)
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = 32 * ch + 16 * c;
-      uint32_t hr[16];
-      tmem_ld16(lane_addr + 256 + col0, hr);
-      float ov[16];
-      nt_load16(g.o + (size_t)rr * 64 + col0, ok, ov);
-      tmem_ld_wait();
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(hr[j]) * nt_silu_d(ov[j]);
-      nt_store_a16(lane_addr + 320 + col0, lane_addr + 384 + col0, v);
-    }
-    NT_GEMM(nt_issue<8>(tm + 0, tm + 320, tm + 384, aW4H, aW4L, 128, idesc128));
-    // ---- gbar -> global scratch (this thread: 64 of the 128 columns)
+    nt_row64_to_r0(lane_addr, g.Pbar + (size_t)rr * 64, ok);
+    NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 64, idesc64, 0u));
+    float4 q[16];   // the Qbar row is fetched while the Pbar half runs
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int col0 = 64 * ch + 16 * c;
-      uint32_t gr[16];
-      tmem_ld16(lane_addr + col0, gr);
-      tmem_ld_wait();
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(gr[j]);
-      if (ok) nt_store16(g.gbar + (size_t)r * 128 + col0, v);
+      float4(&qc)[4] = *reinterpret_cast<float4(*)[4]>(&q[4 * c]);
+      nt_load16(g.Qbar + (size_t)rr * 64 + 16 * c, ok, qc);
     }
-    fence_before_sync();
-    __syncthreads();
+    NT_WAIT();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4(&qc)[4] = *reinterpret_cast<const float4(*)[4]>(&q[4 * c]);
+      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, qc);
+    }
+    NT_GEMM(nt_issue<8, 16>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 64, idesc64, 1u));
+    // ---- obar = hbar * silu'(o) -> R0
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t hr[16];
+      tmem_ld16(lane_addr + 128 + 16 * c, hr);
+      float4 ov[4], v[4];
+      nt_load16(g.o + (size_t)rr * 64 + 16 * c, ok, ov);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = silu_d4_scaled(ov[j], nt_acc4(&hr[4 * j]));
+      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, v);
+    }
+    NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW4H, aW4L, 128, idesc128, 0u));
+    // ---- gbar -> global scratch
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t gr[16];
+      tmem_ld16(lane_addr + 128 + 16 * c, gr);
+      tmem_ld_wait();
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = nt_acc4(&gr[4 * j]);
+      if (ok) nt_store16(g.gbar + (size_t)r * 128 + 16 * c, v);
+    }
   }
   NT_EPILOGUE();
 }
 
 // ------------------------------------------------------------------------------------------ adjoint B
-// smem: W3a (128 x 64) hi|lo 64 KB | W3a^T as B[n = k_in (64)][k = m (128)] hi|lo 64 KB | head scratch
-// TMEM: [0,128) a hi|lo -> abar accumulator [0,64) ; [128,256) p accumulator ; [256,512) pbar hi (128) | lo (128)
+// smem: W3a (128 x 64) hi|lo 64 KB | W3a^T as B[n = k_in (64)][k = m (128)] hi|lo 64 KB
 template <bool LAST>
 __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sWtH = sm + 65536, *sWtL = sm + 98304;
-  float* sHead = reinterpret_cast<float*>(sm + 131072);   // [128][2] (cbar, sbar)
   nt_copy_image(sm, g.img, 131072);   // B[n = m][k] = W3a[m][k] ; B[n = k_in][k = m] = W3a[m][k_in]
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aW3H = smem_u32(sW3H), aW3L = smem_u32(sW3L), aWtH = smem_u32(sWtH), aWtL = smem_u32(sWtL);
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
     if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = 32 * ch + 16 * c;
-      float x[16];
-      nt_load16(g.a + (size_t)rr * 64 + col0, ok, x);
-      nt_store_a16(lane_addr + col0, lane_addr + 64 + col0, x);
-    }
-    if (LAST) {
-      // head adjoint (SURVEY.md App. D.2): cbar, sbar from dE/dB' and the SA term; Bbar += dE/dB' dB'/dB
-      if (ch == 0) {
-        float cb = 0.0f, sbv = 0.0f;
-        if (ok) {
-          const float c0 = g.o[2 * (size_t)r], c1 = g.o[2 * (size_t)r + 1];
-          const float sc = sigmoidf_(c0), ss = sigmoidf_(c1);
-          const float dEdBs = g.dE_dBs[r];
-          cb = dEdBs * g.born[r] * g.kappa * sc * (1.0f - sc);
-          const int a = r % g.N;
-          const float rp = g.rho[a] + kOffset + kProbe;
-          sbv = g.gamma_emb[g.solvent_id[r / g.N]] * (rp * rp) * ss * (1.0f - ss);
-          g.Bbar[r] += dEdBs * (g.fraction + g.kappa * sc);
-        }
-        sHead[2 * row] = cb;
-        sHead[2 * row + 1] = sbv;
-      }
-    }
-    NT_GEMM(nt_issue<8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128));
-    // ---- pbar = gbar * silu'(p + sbias[s])  (this thread: 64 of the 128 columns)
-    const float* sb = g.sbias + (size_t)g.solvent_id[rr / g.N] * 128 + 64 * ch;
+    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok);
+    NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128, 0u));
     float cb = 0.0f, sbv = 0.0f;
-    if (LAST) {
-      cb = sHead[2 * row];
-      sbv = sHead[2 * row + 1];
+    if (LAST && ok) {
+      // head adjoint (SURVEY.md App. D.2): cbar, sbar from dE/dB' and the SA term; Bbar += dE/dB' dB'/dB
+      const float c0 = g.o[2 * (size_t)r], c1 = g.o[2 * (size_t)r + 1];
+      const float sc = sigmoidf_(c0), ss = sigmoidf_(c1);
+      const float dEdBs = g.dE_dBs[r];
+      cb = dEdBs * g.born[r] * g.kappa * sc * (1.0f - sc);
+      const int a = r % g.N;
+      const float rp = g.rho[a] + kOffset + kProbe;
+      sbv = g.gamma_emb[g.solvent_id[r / g.N]] * (rp * rp) * ss * (1.0f - ss);
+      g.Bbar[r] += dEdBs * (g.fraction + g.kappa * sc);
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col0 = 64 * ch + 16 * c;
+    NT_WAIT();
+    const float* sb = g.sbias + (size_t)g.solvent_id[rr / g.N] * 128;
+    // pbar = gbar * silu'(p + sbias[s]) for 16 features starting at col0
+    auto pbar16 = [&](int col0, float4(&v)[4]) {
       uint32_t pr[16];
       tmem_ld16(lane_addr + 128 + col0, pr);
-      float bs[16], gb[16];
-      nt_load16(sb + 16 * c, true, bs);
+      float4 bs[4], gb[4];
+      nt_load16(sb + col0, true, bs);
       if (LAST) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) gb[j] = cb * __ldg(g.W4 + col0 + j) + sbv * __ldg(g.W4 + 128 + col0 + j);
+        for (int j = 0; j < 4; ++j) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.W4 + col0) + j);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.W4 + 128 + col0) + j);
+          gb[j] = make_float4(cb * w0.x + sbv * w1.x, cb * w0.y + sbv * w1.y, cb * w0.z + sbv * w1.z,
+                              cb * w0.w + sbv * w1.w);
+        }
       } else {
         nt_load16(g.gbar + (size_t)rr * 128 + col0, ok, gb);
       }
       tmem_ld_wait();
-      float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = gb[j] * nt_silu_d(__uint_as_float(pr[j]) + bs[j]);
-      nt_store_a16(lane_addr + 256 + col0, lane_addr + 384 + col0, v);
+      for (int j = 0; j < 4; ++j) v[j] = silu_d4_sum2_scaled(&pr[4 * j], bs[j], gb[j]);
+    };
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 v[4];
+      pbar16(16 * c, v);
+      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, v);
     }
-    NT_GEMM(nt_issue<16>(tm + 0, tm + 256, tm + 384, aWtH, aWtL, 64, idesc64));
-    // ---- abar -> global (this thread: 32 of the 64 columns)
+    NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWtH, aWtL, 64, idesc64, 0u));
+    float4 v2[16];   // second 64 features, evaluated while the first half product runs
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = 32 * ch + 16 * c;
+    for (int c = 0; c < 4; ++c) {
+      float4(&vc)[4] = *reinterpret_cast<float4(*)[4]>(&v2[4 * c]);
+      pbar16(64 + 16 * c, vc);
+    }
+    NT_WAIT();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4(&vc)[4] = *reinterpret_cast<const float4(*)[4]>(&v2[4 * c]);
+      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, vc);
+    }
+    NT_GEMM(nt_issue<8, 16>(tm + 128, tm + 0, tm + 64, aWtH, aWtL, 64, idesc64, 1u));
+    // ---- abar -> global
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
       uint32_t ar[16];
-      tmem_ld16(lane_addr + col0, ar);
+      tmem_ld16(lane_addr + 128 + 16 * c, ar);
       tmem_ld_wait();
-      float v[16];
+      float4 v[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ar[j]);
-      if (ok) nt_store16(g.abar + (size_t)r * 64 + col0, v);
+      for (int j = 0; j < 4; ++j) v[j] = nt_acc4(&ar[4 * j]);
+      if (ok) nt_store16(g.abar + (size_t)r * 64 + 16 * c, v);
     }
-    fence_before_sync();
-    __syncthreads();
   }
   NT_EPILOGUE();
 }
@@ -455,9 +491,9 @@ static NodeTcArgs nt_args(Ctx* c, int l) {
   return g;
 }
 
-static int nt_grid(const Ctx* c) {
-  int ntiles = (c->R * c->N + kNtRows - 1) / kNtRows;
-  return ntiles < c->num_sms ? ntiles : c->num_sms;
+static int nt_grid(const Ctx* c) {   // two tiles (one per warp group) in flight per CTA
+  int npairs = ((c->R * c->N + kNtRows - 1) / kNtRows + 1) / 2;
+  return npairs < c->num_sms ? npairs : c->num_sms;
 }
 
 int build_node_images(Ctx* c, cudaStream_t st) {
@@ -488,11 +524,11 @@ int launch_node_fwd_tc(Ctx* c, int l, cudaStream_t st) {
   NodeTcArgs g = nt_args(c, l);
   g.img = c->img_nf[l];
   if (l == 2) {
-    size_t smem = 65536 + 1024 + 1024;
+    size_t smem = 65536 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_fwd_tc_kernel<true><<<nt_grid(c), kNtThreads, smem, st>>>(g);
   } else {
-    size_t smem = 196608 + 1024 + 1024;
+    size_t smem = 196608 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_fwd_tc_kernel<false><<<nt_grid(c), kNtThreads, smem, st>>>(g);
   }
@@ -510,7 +546,7 @@ int launch_node_bwd_tc(Ctx* c, int l, cudaStream_t st) {
     GNNIS_LAUNCH_CHECK();
   }
   g.img = c->img_nbb[l];
-  size_t smem = 131072 + 1024 + 1024;
+  size_t smem = 131072 + 1024;
   if (l == 2) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_b_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_bwd_b_tc_kernel<true><<<nt_grid(c), kNtThreads, smem, st>>>(g);
