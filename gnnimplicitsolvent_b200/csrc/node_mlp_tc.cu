@@ -2,8 +2,8 @@
 // and their adjoints on the tensor cores (tcgen05, 3xTF32, sm_100a).  Same arithmetic as node_mlp.cu (which stays
 // as the CUDA-core cross-check).
 //
-// Rows are atoms, 128 per tile.  One persistent CTA per SM with TWO independent groups of 4 warps: each group walks
-// its own tiles (thread = row = TMEM lane, all columns) and owns 256 of the 512 TMEM columns, so the products of one
+// Rows are atoms, 128 per tile.  One persistent CTA per SM with TWO independent groups of 8 warps: each group walks
+// its own tiles (thread = row = TMEM lane x column half) and owns 256 of the 512 TMEM columns, so the products of one
 // group run under the epilogue (global loads, SiLU, hi / lo split) of the other.  A operands are written to TMEM by
 // the epilogue of the previous product; weights are staged once per CTA as K-major 128B-swizzled hi / lo images.
 // Per group the TMEM columns are R0 = [0,128) (A operand: hi | lo of at most 64 features) and R1 = [128,256)
@@ -27,7 +27,7 @@ using namespace umma;
 
 int launch_build_operand(Ctx*, uint8_t*, uint8_t*, const float*, int, int, int, int, int, int, cudaStream_t);
 
-constexpr int kNtThreads = 256;
+constexpr int kNtThreads = 512;   // 2 groups x 8 warps: thread = (row, column half)
 constexpr int kNtRows = 128;
 
 struct NodeTcArgs {
@@ -50,7 +50,7 @@ __device__ __forceinline__ void nt_copy_image(uint8_t* __restrict__ dst, const u
   for (int t = threadIdx.x * 16; t < bytes; t += blockDim.x * 16)
     *reinterpret_cast<uint4*>(dst + t) = __ldg(reinterpret_cast<const uint4*>(src + t));
 }
-__device__ __forceinline__ void nt_group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+__device__ __forceinline__ void nt_group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
 // D[128 x N] (+)= A[128 x 8 (S1 - S0)] * B[:, 8 S0 .. 8 S1)^T (3xTF32): A (hi, lo) in TMEM starting at column 0 of
 // its region, B K-major SW128 with b_rows rows
@@ -118,7 +118,7 @@ __device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
   uint32_t base_ = smem_u32(smraw);                                                \
   uint8_t* sm = smraw + ((1024u - (base_ & 1023u)) & 1023u);                       \
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                   \
-  const int grp = warp >> 2, wq = warp & 3, row = 32 * wq + lane;                  \
+  const int grp = warp >> 3, ch = (warp >> 2) & 1, wq = warp & 3, row = 32 * wq + lane; \
   if (warp == 0) tmem_alloc(&tmem_slot, 512);                                      \
   if (tid == 0) {                                                                  \
     mbar_init(&bar[0], 1);                                                         \
@@ -140,7 +140,7 @@ __device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
   tmem_st_wait();                                                                  \
   fence_before_sync();                                                             \
   nt_group_sync(grp);                                                              \
-  if (wq == 0) {                                                                   \
+  if ((warp & 7) == 0) {                                                           \
     fence_after_sync();                                                            \
     if (elect_one()) {                                                             \
       __VA_ARGS__;                                                                 \
@@ -173,9 +173,9 @@ __device__ __forceinline__ bool nt_tile_skipped(const NodeTcArgs& g, int tile) {
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 
 // one 64-feature global row -> hi | lo operand in R0
-__device__ __forceinline__ void nt_row64_to_r0(uint32_t lane_addr, const float* __restrict__ src, bool ok) {
+__device__ __forceinline__ void nt_row64_to_r0(uint32_t lane_addr, const float* __restrict__ src, bool ok, int ch) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
     float4 x[4];
     nt_load16(src + 16 * c, ok, x);
     nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, x);
@@ -202,14 +202,14 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok);
+    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok, ch);
     NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128, 0u));
     const float* sb = g.sbias + (size_t)g.solvent_id[rr / g.N] * 128;
     if constexpr (LAST) {
       // o3 = W4 silu(p + sbias) + b4 (2 outputs) and the head: B' = B (f + kappa sig(c)), SA = gamma_s sig(s) (rho + off + 0.14)^2
       float h0 = 0.0f, h1 = 0.0f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 4 * ch; c < 4 * ch + 4; ++c) {
         uint32_t pr[16];
         tmem_ld16(lane_addr + 128 + 16 * c, pr);
         float4 bs[4];
@@ -230,8 +230,14 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
           h1 = fmaf(gv.w, w1.w, h1);
         }
       }
-      if (ok) {
-        const float c0 = h0 + g.b4[0], c1 = h1 + g.b4[1];
+      float* sHead = reinterpret_cast<float*>(sm + 65536) + 256 * grp;   // [128][2] partial sums of column half 1
+      if (ch == 1) {
+        sHead[2 * row] = h0;
+        sHead[2 * row + 1] = h1;
+      }
+      nt_group_sync(grp);
+      if (ch == 0 && ok) {
+        const float c0 = (h0 + sHead[2 * row]) + g.b4[0], c1 = (h1 + sHead[2 * row + 1]) + g.b4[1];
         g.o[2 * (size_t)r] = c0;
         g.o[2 * (size_t)r + 1] = c1;
         const int a = r % g.N;
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
     if constexpr (!LAST) {
     // ---- g = silu(p + sbias[s]), first 64 features -> R0
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
       uint32_t pr[16];
       tmem_ld16(lane_addr + 128 + 16 * c, pr);
       float4 bs[4], gv[4];
@@ -256,27 +262,27 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
     }
     NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW4H, aW4L, 64, idesc64, 0u));
     // ---- second 64 features are evaluated while the first half product runs (it writes R1[0,64), read above)
-    float4 g2[16];
+    float4 g2[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t pr[16];
-      tmem_ld16(lane_addr + 192 + 16 * c, pr);
+      tmem_ld16(lane_addr + 192 + 16 * (2 * ch + c), pr);
       float4 bs[4];
-      nt_load16(sb + 64 + 16 * c, true, bs);
+      nt_load16(sb + 64 + 16 * (2 * ch + c), true, bs);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 4; ++j) g2[4 * c + j] = silu4_sum2(&pr[4 * j], bs[j]);
     }
     NT_WAIT();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       const float4(&gv)[4] = *reinterpret_cast<const float4(*)[4]>(&g2[4 * c]);
-      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, gv);
+      nt_store_a16(lane_addr + 16 * (2 * ch + c), lane_addr + 64 + 16 * (2 * ch + c), gv);
     }
     NT_GEMM(nt_issue<8, 16>(tm + 128, tm + 0, tm + 64, aW4H, aW4L, 64, idesc64, 1u));
     // ---- o = acc + b4 -> global ; h = silu(o) -> R0
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
       uint32_t orr[16];
       tmem_ld16(lane_addr + 128 + 16 * c, orr);
       float4 bs[4];
@@ -292,9 +298,9 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
       nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, hv);
     }
     NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 128, idesc128, 0u));
-    // ---- tables of the next layer: columns [0,64) -> P = . + b1, [64,128) -> Q
+    // ---- tables of the next layer: columns [0,64) -> P = . + b1 (column half 0), [64,128) -> Q (half 1)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 4 * ch; c < 4 * ch + 4; ++c) {
       uint32_t ar[16];
       tmem_ld16(lane_addr + 128 + 16 * c, ar);
       float4 bs[4];
@@ -326,24 +332,24 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-    nt_row64_to_r0(lane_addr, g.Pbar + (size_t)rr * 64, ok);
+    nt_row64_to_r0(lane_addr, g.Pbar + (size_t)rr * 64, ok, ch);
     NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 64, idesc64, 0u));
-    float4 q[16];   // the Qbar row is fetched while the Pbar half runs
+    float4 q[8];   // the Qbar row is fetched while the Pbar half runs
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       float4(&qc)[4] = *reinterpret_cast<float4(*)[4]>(&q[4 * c]);
-      nt_load16(g.Qbar + (size_t)rr * 64 + 16 * c, ok, qc);
+      nt_load16(g.Qbar + (size_t)rr * 64 + 16 * (2 * ch + c), ok, qc);
     }
     NT_WAIT();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       const float4(&qc)[4] = *reinterpret_cast<const float4(*)[4]>(&q[4 * c]);
-      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, qc);
+      nt_store_a16(lane_addr + 16 * (2 * ch + c), lane_addr + 64 + 16 * (2 * ch + c), qc);
     }
     NT_GEMM(nt_issue<8, 16>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 64, idesc64, 1u));
     // ---- obar = hbar * silu'(o) -> R0
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
       uint32_t hr[16];
       tmem_ld16(lane_addr + 128 + 16 * c, hr);
       float4 ov[4], v[4];
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
     NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW4H, aW4L, 128, idesc128, 0u));
     // ---- gbar -> global scratch
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 4 * ch; c < 4 * ch + 4; ++c) {
       uint32_t gr[16];
       tmem_ld16(lane_addr + 128 + 16 * c, gr);
       tmem_ld_wait();
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok);
+    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok, ch);
     NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128, 0u));
     float cb = 0.0f, sbv = 0.0f;
     if (LAST && ok) {
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
       const int a = r % g.N;
       const float rp = g.rho[a] + kOffset + kProbe;
       sbv = g.gamma_emb[g.solvent_id[r / g.N]] * (rp * rp) * ss * (1.0f - ss);
-      g.Bbar[r] += dEdBs * (g.fraction + g.kappa * sc);
+      if (ch == 0) g.Bbar[r] += dEdBs * (g.fraction + g.kappa * sc);
     }
     NT_WAIT();
     const float* sb = g.sbias + (size_t)g.solvent_id[rr / g.N] * 128;
@@ -424,28 +430,28 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
       for (int j = 0; j < 4; ++j) v[j] = silu_d4_sum2_scaled(&pr[4 * j], bs[j], gb[j]);
     };
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
       float4 v[4];
       pbar16(16 * c, v);
       nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, v);
     }
     NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWtH, aWtL, 64, idesc64, 0u));
-    float4 v2[16];   // second 64 features, evaluated while the first half product runs
+    float4 v2[8];   // second 64 features, evaluated while the first half product runs
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       float4(&vc)[4] = *reinterpret_cast<float4(*)[4]>(&v2[4 * c]);
-      pbar16(64 + 16 * c, vc);
+      pbar16(64 + 16 * (2 * ch + c), vc);
     }
     NT_WAIT();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       const float4(&vc)[4] = *reinterpret_cast<const float4(*)[4]>(&v2[4 * c]);
-      nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, vc);
+      nt_store_a16(lane_addr + 16 * (2 * ch + c), lane_addr + 64 + 16 * (2 * ch + c), vc);
     }
     NT_GEMM(nt_issue<8, 16>(tm + 128, tm + 0, tm + 64, aWtH, aWtL, 64, idesc64, 1u));
     // ---- abar -> global
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
       uint32_t ar[16];
       tmem_ld16(lane_addr + 128 + 16 * c, ar);
       tmem_ld_wait();
@@ -524,7 +530,7 @@ int launch_node_fwd_tc(Ctx* c, int l, cudaStream_t st) {
   NodeTcArgs g = nt_args(c, l);
   g.img = c->img_nf[l];
   if (l == 2) {
-    size_t smem = 65536 + 1024;
+    size_t smem = 65536 + 2048 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_fwd_tc_kernel<true><<<nt_grid(c), kNtThreads, smem, st>>>(g);
   } else {
