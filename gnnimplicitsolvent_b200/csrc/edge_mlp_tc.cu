@@ -556,12 +556,18 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       mbar_init(&bars.u_ok[i], 12);
     }
   }
-  copy_image(sm, g.img, kFwdWeights);   // B[n = c][k] = Wr[c][k] and W2[c][k], hi | lo
+  __shared__ uint64_t ibar;
+  if (tid == 0) {
+    mbar_init(&ibar, 1);
+    bulk_copy_image(sm, g.img, kFwdWeights, &ibar);   // B[n = c][k] = Wr[c][k] and W2[c][k], hi | lo
+  }
   if (tid < 64) sb2[tid] = g.b2[tid];
   fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  mbar_wait(&ibar, 0);
+  __syncwarp();
   constexpr uint32_t VH = 128, VL = 192;
   constexpr uint32_t idesc64 = idesc_tf32(128, 64);
 
@@ -800,12 +806,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       bars.cnt_u[i] = 0;
     }
   }
-  copy_image(sm, g.img, kBwdWeights);   // Wr, W2 as above and B[n = k'][k = c] = W2[c][k'] for vbar
+  __shared__ uint64_t ibar;
+  if (tid == 0) {
+    mbar_init(&ibar, 1);
+    bulk_copy_image(sm, g.img, kBwdWeights, &ibar);   // Wr, W2 as above and B[n = k'][k = c] = W2[c][k'] for vbar
+  }
   if (tid < 64) sb2[tid] = g.b2[tid];
   fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  mbar_wait(&ibar, 0);
+  __syncwarp();
   constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
   constexpr uint32_t idesc64 = idesc_tf32(128, 64);
 

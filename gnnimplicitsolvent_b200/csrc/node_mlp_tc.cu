@@ -46,10 +46,6 @@ struct NodeTcArgs {
   float *gbar, *abar, *Bbar;
 };
 
-__device__ __forceinline__ void nt_copy_image(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int bytes) {
-  for (int t = threadIdx.x * 16; t < bytes; t += blockDim.x * 16)
-    *reinterpret_cast<uint4*>(dst + t) = __ldg(reinterpret_cast<const uint4*>(src + t));
-}
 __device__ __forceinline__ void nt_group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
 // D[128 x N] (+)= A[128 x 8 (S1 - S0)] * B[:, 8 S0 .. 8 S1)^T (3xTF32): A (hi, lo) in TMEM starting at column 0 of
@@ -113,7 +109,7 @@ __device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
 
 #define NT_PROLOGUE()                                                              \
   extern __shared__ uint8_t smraw[];                                               \
-  __shared__ uint64_t bar[2];                                                      \
+  __shared__ uint64_t bar[2], ibar;                                                \
   __shared__ uint32_t tmem_slot;                                                   \
   uint32_t base_ = smem_u32(smraw);                                                \
   uint8_t* sm = smraw + ((1024u - (base_ & 1023u)) & 1023u);                       \
@@ -123,6 +119,7 @@ __device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
   if (tid == 0) {                                                                  \
     mbar_init(&bar[0], 1);                                                         \
     mbar_init(&bar[1], 1);                                                         \
+    mbar_init(&ibar, 1);                                                           \
   }
 
 #define NT_STAGED()                                                                \
@@ -130,6 +127,8 @@ __device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
   fence_before_sync();                                                             \
   __syncthreads();                                                                 \
   fence_after_sync();                                                              \
+  mbar_wait(&ibar, 0);   /* operand images have landed */                          \
+  __syncwarp();                                                                    \
   const uint32_t tm = tmem_slot + 256u * (uint32_t)grp;                            \
   const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);                     \
   uint32_t phase = 0;                                                              \
@@ -189,7 +188,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
   NT_PROLOGUE();
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
   uint8_t *sWpH = sm + 131072, *sWpL = sm + 163840;
-  nt_copy_image(sm, g.img, LAST ? 65536 : 196608);
+  if (tid == 0) bulk_copy_image(sm, g.img, LAST ? 65536 : 196608, &ibar);
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aW3H = smem_u32(sW3H), aW3L = smem_u32(sW3L), aW4H = smem_u32(sW4H), aW4L = smem_u32(sW4L);
@@ -321,7 +320,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
 __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sWpH = sm, *sWpL = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
-  nt_copy_image(sm, g.img, 131072);   // B[n = c_in][k = c_out] = Wi|Wj[c_out][c_in] ; B[n = m][k = c] = W4[c][m]
+  if (tid == 0) bulk_copy_image(sm, g.img, 131072, &ibar);   // B[n = c_in][k = c_out] = Wi|Wj[c_out][c_in] ; B[n = m][k = c] = W4[c][m]
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aWpH = smem_u32(sWpH), aWpL = smem_u32(sWpL), aW4H = smem_u32(sW4H), aW4L = smem_u32(sW4L);
@@ -381,7 +380,7 @@ template <bool LAST>
 __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sWtH = sm + 65536, *sWtL = sm + 98304;
-  nt_copy_image(sm, g.img, 131072);   // B[n = m][k] = W3a[m][k] ; B[n = k_in][k = m] = W3a[m][k_in]
+  if (tid == 0) bulk_copy_image(sm, g.img, 131072, &ibar);   // B[n = m][k] = W3a[m][k] ; B[n = k_in][k = m] = W3a[m][k_in]
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
   const uint32_t aW3H = smem_u32(sW3H), aW3L = smem_u32(sW3L), aWtH = smem_u32(sWtH), aWtL = smem_u32(sWtL);

@@ -56,6 +56,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// One thread: asynchronous bulk copy (TMA engine, cp.async.bulk) of a prebuilt operand image from global to shared
+// memory; `bar` (initialised with count 1 by the same thread) completes when all bytes have landed.  Both pointers
+// 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_copy_image(uint8_t* dst, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst + off)),
+                 "l"(src + off), "r"(n), "r"(smem_u32(bar))
+                 : "memory");
+  }
+}
 // plain arrive (release.cta) and non-blocking completion test of a phase
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
