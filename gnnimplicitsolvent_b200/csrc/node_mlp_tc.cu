@@ -97,6 +97,44 @@ __device__ __forceinline__ void nt_store16(float* __restrict__ p, const float4 (
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) *(reinterpret_cast<float4*>(p) + j4) = x[j4];
 }
+// Row-per-lane accesses to global memory cost one L1 wavefront per lane (32 different 128-byte lines per
+// instruction), which made the plain row loads / stores the longest phases of these kernels.  The 32 rows x 16 floats
+// block of a warp therefore goes through a 2 KB shared-memory slice: global side = 4 lanes per row (64 contiguous
+// bytes, 8 rows per instruction), register side = row per lane; quads are XOR-swizzled so both sides are free of
+// bank conflicts.  g0 = first row of the warp's block (already offset to the chunk's first column).
+struct NtRows {
+  float* stage;   // this warp's [32][16] slice
+  int nvalid;     // rows of the warp's block that exist (0..32)
+  int lane;
+};
+__device__ __forceinline__ int nt_swz(int row, int q) { return row * 16 + 4 * (q ^ ((row >> 1) & 3)); }
+__device__ __forceinline__ void nt_warp_load16(const NtRows& w, const float* __restrict__ g0, int ld, float4 (&x)[4]) {
+  const int q = w.lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = 8 * i + (w.lane >> 2);
+    const float4 v = row < w.nvalid ? __ldg(reinterpret_cast<const float4*>(g0 + (size_t)row * ld) + q)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(w.stage + nt_swz(row, q)) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(w.stage + nt_swz(w.lane, j));
+  __syncwarp();
+}
+__device__ __forceinline__ void nt_warp_store16(const NtRows& w, float* __restrict__ g0, int ld, const float4 (&x)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(w.stage + nt_swz(w.lane, j)) = x[j];
+  __syncwarp();
+  const int q = w.lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = 8 * i + (w.lane >> 2);
+    const float4 v = *reinterpret_cast<const float4*>(w.stage + nt_swz(row, q));
+    if (row < w.nvalid) *(reinterpret_cast<float4*>(g0 + (size_t)row * ld) + q) = v;
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ float4 nt_acc4(const uint32_t* r) {
   return make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
 }
@@ -172,11 +210,11 @@ __device__ __forceinline__ bool nt_tile_skipped(const NodeTcArgs& g, int tile) {
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 
 // one 64-feature global row -> hi | lo operand in R0
-__device__ __forceinline__ void nt_row64_to_r0(uint32_t lane_addr, const float* __restrict__ src, bool ok, int ch) {
+__device__ __forceinline__ void nt_row64_to_r0(uint32_t lane_addr, const NtRows& w, const float* __restrict__ src0, int ch) {
 #pragma unroll
   for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
     float4 x[4];
-    nt_load16(src + 16 * c, ok, x);
+    nt_warp_load16(w, src0 + 16 * c, 64, x);
     nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, x);
   }
 }
@@ -188,6 +226,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
   NT_PROLOGUE();
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
   uint8_t *sWpH = sm + 131072, *sWpL = sm + 163840;
+  float* sStage = reinterpret_cast<float*>(sm + (LAST ? 65536 : 196608));   // [16 warps][32][16] row staging
   if (tid == 0) bulk_copy_image(sm, g.img, LAST ? 65536 : 196608, &ibar);
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
@@ -201,7 +240,9 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok, ch);
+    const int r0w = tile * kNtRows + 32 * wq;   // first row of this warp's 32-row block
+    const NtRows wr{sStage + 512 * warp, max(0, min(32, g.n - r0w)), lane};
+    nt_row64_to_r0(lane_addr, wr, g.a + (size_t)r0w * 64, ch);
     NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128, 0u));
     const float* sb = g.sbias + (size_t)g.solvent_id[rr / g.N] * 128;
     if constexpr (LAST) {
@@ -229,7 +270,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
           h1 = fmaf(gv.w, w1.w, h1);
         }
       }
-      float* sHead = reinterpret_cast<float*>(sm + 65536) + 256 * grp;   // [128][2] partial sums of column half 1
+      float* sHead = reinterpret_cast<float*>(sm + 65536 + 32768) + 256 * grp;   // [128][2] partial sums of column half 1
       if (ch == 1) {
         sHead[2 * row] = h0;
         sHead[2 * row + 1] = h1;
@@ -293,7 +334,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
         ov[j] = nt_add4(nt_acc4(&orr[4 * j]), bs[j]);
         hv[j] = silu4(ov[j]);
       }
-      if (ok) nt_store16(g.o + (size_t)r * 64 + 16 * c, ov);
+      nt_warp_store16(wr, g.o + (size_t)r0w * 64 + 16 * c, 64, ov);
       nt_store_a16(lane_addr + 16 * c, lane_addr + 64 + 16 * c, hv);
     }
     NT_GEMM(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 128, idesc128, 0u));
@@ -308,7 +349,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
       float4 v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = nt_add4(nt_acc4(&ar[4 * j]), bs[j]);
-      if (ok) nt_store16((c < 4 ? g.P_next : g.Q_next) + (size_t)r * 64 + 16 * (c & 3), v);
+      nt_warp_store16(wr, (c < 4 ? g.P_next : g.Q_next) + (size_t)r0w * 64 + 16 * (c & 3), 64, v);
     }
     }   // !LAST
   }
@@ -320,6 +361,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
 __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sWpH = sm, *sWpL = sm + 32768, *sW4H = sm + 65536, *sW4L = sm + 98304;
+  float* sStage = reinterpret_cast<float*>(sm + 131072);
   if (tid == 0) bulk_copy_image(sm, g.img, 131072, &ibar);   // B[n = c_in][k = c_out] = Wi|Wj[c_out][c_in] ; B[n = m][k = c] = W4[c][m]
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
@@ -328,16 +370,15 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
 
   for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
     if (nt_tile_skipped(g, tile)) continue;
-    const int r = tile * kNtRows + row;
-    const bool ok = r < g.n;
-    const int rr = ok ? r : g.n - 1;
-    nt_row64_to_r0(lane_addr, g.Pbar + (size_t)rr * 64, ok, ch);
+    const int r0w = tile * kNtRows + 32 * wq;   // first row of this warp's 32-row block
+    const NtRows wr{sStage + 512 * warp, max(0, min(32, g.n - r0w)), lane};
+    nt_row64_to_r0(lane_addr, wr, g.Pbar + (size_t)r0w * 64, ch);
     NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aWpH, aWpL, 64, idesc64, 0u));
     float4 q[8];   // the Qbar row is fetched while the Pbar half runs
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float4(&qc)[4] = *reinterpret_cast<float4(*)[4]>(&q[4 * c]);
-      nt_load16(g.Qbar + (size_t)rr * 64 + 16 * (2 * ch + c), ok, qc);
+      nt_warp_load16(wr, g.Qbar + (size_t)r0w * 64 + 16 * (2 * ch + c), 64, qc);
     }
     NT_WAIT();
 #pragma unroll
@@ -352,7 +393,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
       uint32_t hr[16];
       tmem_ld16(lane_addr + 128 + 16 * c, hr);
       float4 ov[4], v[4];
-      nt_load16(g.o + (size_t)rr * 64 + 16 * c, ok, ov);
+      nt_warp_load16(wr, g.o + (size_t)r0w * 64 + 16 * c, 64, ov);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = silu_d4_scaled(ov[j], nt_acc4(&hr[4 * j]));
@@ -368,7 +409,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
       float4 v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = nt_acc4(&gr[4 * j]);
-      if (ok) nt_store16(g.gbar + (size_t)r * 128 + 16 * c, v);
+      nt_warp_store16(wr, g.gbar + (size_t)r0w * 128 + 16 * c, 128, v);
     }
   }
   NT_EPILOGUE();
@@ -380,6 +421,7 @@ template <bool LAST>
 __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs g) {
   NT_PROLOGUE();
   uint8_t *sW3H = sm, *sW3L = sm + 32768, *sWtH = sm + 65536, *sWtL = sm + 98304;
+  float* sStage = reinterpret_cast<float*>(sm + 131072);
   if (tid == 0) bulk_copy_image(sm, g.img, 131072, &ibar);   // B[n = m][k] = W3a[m][k] ; B[n = k_in][k = m] = W3a[m][k_in]
   NT_STAGED();
   constexpr uint32_t idesc128 = idesc_tf32(128, 128), idesc64 = idesc_tf32(128, 64);
@@ -391,7 +433,9 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
     const int rr = ok ? r : g.n - 1;
-    nt_row64_to_r0(lane_addr, g.a + (size_t)rr * 64, ok, ch);
+    const int r0w = tile * kNtRows + 32 * wq;   // first row of this warp's 32-row block
+    const NtRows wr{sStage + 512 * warp, max(0, min(32, g.n - r0w)), lane};
+    nt_row64_to_r0(lane_addr, wr, g.a + (size_t)r0w * 64, ch);
     NT_ISSUE(nt_issue<0, 8>(tm + 128, tm + 0, tm + 64, aW3H, aW3L, 128, idesc128, 0u));
     float cb = 0.0f, sbv = 0.0f;
     if (LAST && ok) {
@@ -422,7 +466,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
                               cb * w0.w + sbv * w1.w);
         }
       } else {
-        nt_load16(g.gbar + (size_t)rr * 128 + col0, ok, gb);
+        nt_warp_load16(wr, g.gbar + (size_t)r0w * 128 + col0, 128, gb);
       }
       tmem_ld_wait();
 #pragma unroll
@@ -457,7 +501,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
       float4 v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = nt_acc4(&ar[4 * j]);
-      if (ok) nt_store16(g.abar + (size_t)r * 64 + 16 * c, v);
+      nt_warp_store16(wr, g.abar + (size_t)r0w * 64 + 16 * c, 64, v);
     }
   }
   NT_EPILOGUE();
@@ -529,11 +573,11 @@ int launch_node_fwd_tc(Ctx* c, int l, cudaStream_t st) {
   NodeTcArgs g = nt_args(c, l);
   g.img = c->img_nf[l];
   if (l == 2) {
-    size_t smem = 65536 + 2048 + 1024;
+    size_t smem = 65536 + 32768 + 2048 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_fwd_tc_kernel<true><<<nt_grid(c), kNtThreads, smem, st>>>(g);
   } else {
-    size_t smem = 196608 + 1024;
+    size_t smem = 196608 + 32768 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_fwd_tc_kernel<false><<<nt_grid(c), kNtThreads, smem, st>>>(g);
   }
@@ -545,13 +589,13 @@ int launch_node_bwd_tc(Ctx* c, int l, cudaStream_t st) {
   NodeTcArgs g = nt_args(c, l);
   if (l < 2) {
     g.img = c->img_nba[l];
-    size_t smem = 131072 + 1024;
+    size_t smem = 131072 + 32768 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_bwd_a_tc_kernel<<<nt_grid(c), kNtThreads, smem, st>>>(g);
     GNNIS_LAUNCH_CHECK();
   }
   g.img = c->img_nbb[l];
-  size_t smem = 131072 + 1024;
+  size_t smem = 131072 + 32768 + 1024;
   if (l == 2) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_b_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     node_bwd_b_tc_kernel<true><<<nt_grid(c), kNtThreads, smem, st>>>(g);
