@@ -26,7 +26,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import gbneck
+from . import _lib, gbneck
 from .engine import Engine, GnnisError
 
 DEFAULT_UNIQUE_RADII = list(gbneck.DEFAULT_UNIQUE_RADII)   # GNN_Models.py:38 (unsorted on purpose)
@@ -310,6 +310,16 @@ class GNN3_Multisolvent_embedding_run_multiple(GNN3_Multisolvent_embedding):
         self._select_solvents(-1, 78.5)
         return self._engine_ready().langevin(positions, velocities, masses, n_steps, delta=self._delta, **kw)
 
+    def scripted(self, outputs_forces: bool = False):
+        """What the reference obtains from `torch.jit.optimize_for_inference(torch.jit.script(run_model.eval()))`
+        (`helper_functions.py:777-782`): a TorchScript module for `openmmtorch.TorchForce`, here a thin scripted
+        wrapper over `torch.ops.gnnis.*` (csrc/torch_op.cpp) bound to this model's resident engine.  Keep the model
+        alive while the scripted module (or a file saved from it) is in use."""
+        from . import torch_op
+        self._select_solvents(-1, 78.5)
+        return torch_op.script_engine(self._engine_ready(), outputs_forces=outputs_forces,
+                                      flags=_lib.FLAG_DELTA if self._delta else 0)
+
 
 class GNN3_Multisolvent_embedding_run_multiple_Delta(GNN3_Multisolvent_embedding_run_multiple):
     """GNN - GBNeck2 difference + SA (GNN_Models.py:947-1065): forward(positions) only."""
@@ -331,11 +341,16 @@ class GNN3_Multisolvent_embedding_run_multiple_split(GNN3_Multisolvent_embedding
         return e.reshape(-1, 1), sa.reshape(-1, 1)
 
 
+_KEEP_ALIVE: list = []
+
+
 def create_gnn_model(parameters, state_dict, num_reps=1, solvent_models: List[int] = (0,),
                      solvent_dielectric: List[float] = (78.5,), cls=GNN3_Multisolvent_embedding_run_multiple,
-                     device=None, fraction=0.1, scaling_factor=2.0):
+                     device=None, fraction=0.1, scaling_factor=2.0, jit=False):
     """The model-building half of Simulation/helper_functions.py:create_gnn_model / create_gnn_sim (:750-790):
-    instantiate a run model for `num_reps` replicas, load the checkpoint's state dict, freeze it."""
+    instantiate a run model for `num_reps` replicas, load the checkpoint's state dict, freeze it.  `jit=True` returns
+    the TorchScript form (`model.scripted()`), as the reference does for TorchForce; the eager model that owns the
+    engine is kept alive by this module."""
     num_solvents = int(state_dict["solvent_embedding.weight"].shape[0])
     model = cls(fraction=fraction, radius=0.6, max_num_neighbors=10000, parameters=parameters, device=device,
                 num_reps=num_reps, unique_radii=DEFAULT_UNIQUE_RADII, hidden=64,
@@ -345,4 +360,8 @@ def create_gnn_model(parameters, state_dict, num_reps=1, solvent_models: List[in
     model.eval()
     for p in model.parameters():
         p.requires_grad_(False)
+    if jit:
+        scripted = model.scripted()
+        _KEEP_ALIVE.append(model)      # the scripted module only holds the engine's handle
+        return scripted
     return model

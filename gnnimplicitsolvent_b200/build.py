@@ -63,5 +63,33 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+TORCH_OP_OUT = os.path.join(HERE, "libgnnis_torch.so")
+
+
+def build_torch_op(force: bool = False) -> str:
+    """Compiles csrc/torch_op.cpp (TORCH_LIBRARY shim over the C ABI) with g++ against the installed libtorch and
+    links it to libgnnis.so (rpath $ORIGIN).  No CUDA compiler is involved: the shim only forwards pointers."""
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    lib = build_library()
+    src = os.path.join(CSRC, "torch_op.cpp")
+    hdr = os.path.join(os.path.dirname(HERE), "include", "gnnis.h")
+    if not (force or _stale(TORCH_OP_OUT, [src, hdr, lib])):
+        return TORCH_OP_OUT
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc = [f"-I{d}" for d in ce.include_paths()] + [f"-I{os.path.join(cuda_home, 'include')}",
+                                                   f"-I{os.path.join(os.path.dirname(HERE), 'include')}"]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           *inc, src, "-o", TORCH_OP_OUT, f"-L{HERE}", "-l:libgnnis.so", f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu",
+           "-ltorch_cuda", "-ltorch", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed on torch_op.cpp:\n{r.stdout}\n{r.stderr}")
+    return TORCH_OP_OUT
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_op(force="--force" in sys.argv))
