@@ -14,6 +14,14 @@ CASES = ["c1_n13_dmso", "mixed_n21", "c2_n50_water", "mixed_n50", "n100_mixed"]
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run under gpurun on a B200)")
+    # a fresh clone has no built libraries (they are git-ignored): build them once; failures surface in the tests
+    try:
+        from gnnimplicitsolvent_b200 import _lib, build, torch_op
+        if not os.path.exists(_lib.LIB_PATH) or not os.path.exists(torch_op.LIB_PATH):
+            build.build_library()
+            build.build_torch_op()
+    except Exception as exc:   # noqa: BLE001
+        print(f"conftest: could not build the native libraries: {exc}", file=sys.stderr)
 
 
 def load_case(name):
