@@ -279,7 +279,7 @@ static size_t group_bytes(const Ctx* c, int ntables) {
   if (c->smem_tables) b += (size_t)ntables * c->G * c->N * kTabLd * 4;
   return (b + 15) / 16 * 16;
 }
-static size_t fwd_tc_smem(const Ctx* c) { return kFwdWeights + 256 + kGroups * group_bytes(c, 1) + 1024; }
+static size_t fwd_tc_smem(const Ctx* c) { return kFwdWeights + 256 + kGroups * group_bytes(c, 2) + 1024; }
 static size_t bwd_tc_smem(const Ctx* c) { return kBwdWeights + 256 + kGroups * group_bytes(c, 2) + 1024; }
 
 // ---------------------------------------------------------------------------------------------- launchers
@@ -634,17 +634,19 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
       const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
       const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
-      const float* gP = g.P + (size_t)atom0 * 64;
       float* gA = g.a_out + (size_t)atom0 * 64;
-      const float* tQ;
+      const float *tQ, *gP;   // gP: the P rows of the unit (shared-memory copy when the tables fit)
       int ld;
       if (SMEM_TABLES) {
         ld = kTabLd;
         copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
+        copy_rows_n(sTab + (size_t)g.unit_atoms * kTabLd, ld, g.P + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
         tQ = sTab;
+        gP = sTab + (size_t)g.unit_atoms * kTabLd;
       } else {
         ld = 64;
         tQ = g.Q + (size_t)atom0 * 64;
+        gP = g.P + (size_t)atom0 * 64;
       }
       zero_rows_n(gA, 64, natoms, gt, kWsGroupThreads);
       if (e_begin >= e_end) {
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       }
       TileKeys* tk = keys + kidx;
       if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
-      prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
+      if (!SMEM_TABLES) prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
       warp_arrive_i(u_ok, lane);                       // accumulators are free
       if (ch == 0) {
         float o[32], od[32];
@@ -696,12 +698,12 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           const int col0 = 32 * ch + 16 * c;
           uint32_t ur[16];
           tmem_ld16(lane_addr + cur + col0, ur);
-          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + col0);
+          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * ld + col0);
           const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
           float4 p[4], q[4];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            p[j4] = __ldg(pp + j4);
+            p[j4] = SMEM_TABLES ? pp[j4] : __ldg(pp + j4);
             q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
           }
           tmem_ld_wait();
@@ -726,7 +728,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         if (has_next) {
           valid_n = t0 + kTileE + row < e_end;
           if (ch == 0) tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
-          prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
+          if (!SMEM_TABLES) prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
           if (t0 + 2 * kTileE + row < e_end) {
             pr_nn = g.pair[t0 + 2 * kTileE + row];
             if (ch == 0) r_nn = g.r_e[t0 + 2 * kTileE + row];
@@ -1108,7 +1110,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
 int launch_edge_fwd_ws(Ctx* c, int l, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
   size_t smem = fwd_tc_smem(c);
-  uint32_t gb = (uint32_t)group_bytes(c, 1);
+  uint32_t gb = (uint32_t)group_bytes(c, 2);
   if (c->smem_tables) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     edge_fwd_wsi_kernel<true><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
