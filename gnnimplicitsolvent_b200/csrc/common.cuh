@@ -71,7 +71,7 @@ struct Ctx {
   float fraction = 0.1f, scaling = 2.0f, cutoff = 0.6f;
   float* wblob = nullptr;  // one allocation backing all weight matrices
   // tensor-core operand images: the exact shared-memory bytes (hi | lo TF32 parts, K-major 128B swizzle) of the B
-  // operands of every tcgen05 kernel, built once when the weights are loaded; kernels copy them with 16-byte loads
+  // operands of every tcgen05 kernel, built once when the weights are loaded; kernels fetch them with cp.async.bulk
   uint8_t* img = nullptr;
   uint8_t *img_edge[3] = {nullptr, nullptr, nullptr};   // 80 KB: Wr | W2 | W2^T        (forward uses the first 48 KB)
   uint8_t *img_nf[3] = {nullptr, nullptr, nullptr};     // 192 KB: W3a | W4 | [Wi;Wj]    (last layer: first 64 KB)

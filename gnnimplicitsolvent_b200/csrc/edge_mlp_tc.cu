@@ -21,7 +21,8 @@
 //     w    = v    . W2^T   [128 x 64] x [64 x 64]
 //     vbar = wbar . W2     [128 x 64] x [64 x 64]   (W2^T staged as a second K-major operand: kind::tf32 only
 //                                                    reads MN-major operands in the 128B_BASE32B layout)
-// Weights are staged once per CTA in the canonical K-major 128B-swizzle layout.
+// Weights are staged once per CTA in the canonical K-major 128B-swizzle layout: prebuilt hi / lo images
+// (build_edge_images, once per weight load) fetched with one cp.async.bulk per 32 KB.
 //
 // Precision: fp32-accurate.  Each product is three TF32 MMAs, A_hi B_hi + A_hi B_lo + A_lo B_hi with x_hi = top 19
 // bits of x and x_lo = x - x_hi ("3xTF32"), accumulated in fp32 in TMEM; the dropped term is O(2^-22).
@@ -113,11 +114,6 @@ int launch_build_operand(Ctx* c, uint8_t* hi, uint8_t* lo, const float* src, int
   build_operand_image_kernel<<<32, 256, 0, st>>>(hi, lo, src, rows_total, n0, nrows, k0, kcount, ld_n);
   GNNIS_LAUNCH_CHECK();
   return 0;
-}
-// block-wide copy of a prebuilt operand image into shared memory (16-byte vectors)
-__device__ __forceinline__ void copy_image(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int bytes) {
-  for (int t = threadIdx.x * 16; t < bytes; t += blockDim.x * 16)
-    *reinterpret_cast<uint4*>(dst + t) = __ldg(reinterpret_cast<const uint4*>(src + t));
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
