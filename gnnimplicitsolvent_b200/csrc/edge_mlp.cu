@@ -557,9 +557,10 @@ static EdgeArgs make_args(Ctx* c, int l) {
   return g;
 }
 
-// Same permutation by a counting sort over the (<= 128) unit-local source indices.  One WARP per unit (no block
-// barriers): the warp walks its rows 32 at a time in order, __match_any_sync groups equal sources, so the rank inside
-// a bin follows the edge order; the bins live in the warp's own shared-memory slice.
+// Same permutation by a counting sort over the (<= 128) unit-local source indices.  One WARP per tile (no block
+// barriers; the warps of a CTA share a unit and take its tiles round-robin): the warp walks its rows 32 at a time in
+// order, __match_any_sync groups equal sources, so the rank inside a bin follows the edge order; the bins live in
+// the warp's own shared-memory slice.
 __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, int G, int N, int R,
                                                                  const int* __restrict__ row_ptr,
                                                                  const uint32_t* __restrict__ pair,
@@ -567,12 +568,12 @@ __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, in
   __shared__ int sbins[kTileE / 32][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* bins = sbins[warp];
-  const int nwarps = gridDim.x * (kTileE / 32);
-  for (int unit = blockIdx.x * (kTileE / 32) + warp; unit < n_units; unit += nwarps) {
+  constexpr int kWarps = kTileE / 32;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int rep0 = unit * G, rep1 = min(R, rep0 + G);
     const int atom0 = rep0 * N, natoms = (rep1 - rep0) * N;
     const int e_begin = row_ptr[atom0], e_end = row_ptr[atom0 + natoms];
-    for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
+    for (int t0 = e_begin + warp * kTileE; t0 < e_end; t0 += kWarps * kTileE) {
       int key[4], in_bin[4];   // in_bin: rows of this tile with the same source that come before this one
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, in
 int launch_tile_perm(Ctx* c, cudaStream_t st) {
   int grid = c->n_units < 8 * c->num_sms ? c->n_units : 8 * c->num_sms;
   if (c->G * c->N <= 128)
-    tile_perm_count_kernel<<<((c->n_units + 3) / 4 < 16 * c->num_sms ? (c->n_units + 3) / 4 : 16 * c->num_sms), kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
+    tile_perm_count_kernel<<<(c->n_units < 16 * c->num_sms ? c->n_units : 16 * c->num_sms), kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
   else
     tile_perm_kernel<<<grid, kTileE, 0, st>>>(c->n_units, c->G, c->N, c->R, c->row_ptr, c->pair, c->perm);
   GNNIS_LAUNCH_CHECK();
