@@ -68,6 +68,7 @@ SIGNATURES = {
 }
 
 FLAG_DELTA, FLAG_NO_FORCES, FLAG_GB_ONLY, FLAG_MLP_BF16, FLAG_MLP_CUDA_CORES = 0x1, 0x2, 0x4, 0x8, 0x10
+FLAG_MLP_TF32X1 = 0x80
 FLAG_DATA_PREDICATE = 0x20
 FLAG_VACUUM_ONLY = 0x40
 

@@ -16,8 +16,8 @@ int launch_born_adjoint(Ctx*, const float*, int, float*, cudaStream_t);
 int launch_reduce_energy(Ctx*, const float*, float*, cudaStream_t);
 int launch_edge_fwd(Ctx*, int, cudaStream_t);
 int launch_tile_perm(Ctx*, cudaStream_t);
-int launch_edge_fwd_ws(Ctx*, int, cudaStream_t);
-int launch_edge_bwd_ws(Ctx*, int, int, cudaStream_t);
+int launch_edge_fwd_ws(Ctx*, int, int, cudaStream_t);
+int launch_edge_bwd_ws(Ctx*, int, int, int, cudaStream_t);
 int launch_umma_selftest(Ctx*, const float*, const float*, float*, int, int, cudaStream_t);
 bool tc_path_fits(const Ctx*);
 int launch_edge_bwd(Ctx*, int, int, cudaStream_t);
@@ -160,10 +160,11 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     return -1;
   }
   if (flags & GNNIS_FLAG_MLP_BF16) {
-    c->err = "GNNIS_FLAG_MLP_BF16: no reduced-precision MLP mode is offered -- already single-pass TF32 misses the parity "
-             "gates (energy 4e-4, forces 4e-3) and is only 2.5 % faster than the 3xTF32 default (DESIGN.md 5.1)";
+    c->err = "GNNIS_FLAG_MLP_BF16: no bf16 MLP mode is offered -- already single-pass TF32 (GNNIS_FLAG_MLP_TF32X1) misses "
+             "the fp32 parity gates (DESIGN.md 5.1)";
     return -3;
   }
+  const int terms = (flags & GNNIS_FLAG_MLP_TF32X1) ? 1 : 3;
   // tensor-core (tcgen05, 3xTF32) edge kernels unless the caller forces the CUDA-core path or the unit's tables
   // do not fit next to the staged weight operands
   const bool tc_ok = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && tc_path_fits(c);
@@ -180,7 +181,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
     if (launch_node_pre1(c, st)) return -1;
     for (int l = 0; l < 3; ++l) {
       if (tm) tm->mark(kStEdgeFwd);
-      if (tc_fwd ? launch_edge_fwd_ws(c, l, st) : launch_edge_fwd(c, l, st)) return -1;
+      if (tc_fwd ? launch_edge_fwd_ws(c, l, terms, st) : launch_edge_fwd(c, l, st)) return -1;
       if (tm) tm->mark(kStNodeFwd);
       if ((node_tc ? launch_node_fwd_tc(c, l, st) : launch_node_fwd(c, l, st))) return -1;
     }
@@ -198,7 +199,7 @@ int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint
         if (tm) tm->mark(kStNodeBwd);
         if ((node_tc ? launch_node_bwd_tc(c, l, st) : launch_node_bwd(c, l, st))) return -1;
         if (tm) tm->mark(kStEdgeBwd);
-        if (tc_bwd ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
+        if (tc_bwd ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, terms, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
       }
       if (tm) tm->mark(kStNodeBwd);
       if (launch_node_pre1_bwd(c, st)) return -1;

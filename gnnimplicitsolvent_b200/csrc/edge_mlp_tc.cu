@@ -79,12 +79,12 @@ __device__ __forceinline__ void stage_b_operand(uint8_t* hi, uint8_t* lo, const 
 
 // D[128 x N] (+)= A[128 x k in [8 S0, 8 S1)] * B^T, three TF32 products; A (hi, lo) in TMEM, B (hi, lo) K-major SW128
 // in smem.  `accumulate` = 0 overwrites D with the first product.
-template <int S0, int S1>
+template <int S0, int S1, int TERMS = 3>
 __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_addr,
                                                   uint32_t b_lo_addr, int b_rows, uint32_t idesc, uint32_t accumulate) {
   uint32_t acc = accumulate;
 #pragma unroll
-  for (int term = 0; term < 3; ++term) {
+  for (int term = 0; term < TERMS; ++term) {   // TERMS = 1: single TF32 product (opt-in reduced-precision mode)
     const uint32_t a = term == 2 ? a_lo : a_hi;
     const uint32_t b = term == 1 ? b_lo_addr : b_hi_addr;
 #pragma unroll
@@ -159,7 +159,18 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
 }
 
 // radial operand rows: only the 24 columns that the K = 24 products read (20 basis functions + 4 zeros)
+template <int TERMS = 3>
 __device__ __forceinline__ void st_split24(uint32_t t_hi, uint32_t t_lo, const float (&x)[32]) {
+  if (TERMS == 1) {   // single-product mode: the raw fp32 words (kind::tf32 reads their top 19 bits), no lo part
+    uint32_t h[16], h8[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = __float_as_uint(x[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h8[j] = __float_as_uint(x[16 + j]);
+    tmem_st16(t_hi, h);
+    tmem_st8(t_hi + 16, h8);
+    return;
+  }
   {
     uint32_t h[16], l[16];
 #pragma unroll
@@ -365,7 +376,15 @@ __device__ __forceinline__ bool warp_arrive_last(int* cnt, int expected, int lan
 __device__ __forceinline__ void warp_arrive_mbar(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
+template <int TERMS = 3>
 __device__ __forceinline__ void st_split16(uint32_t t_hi, uint32_t t_lo, const float (&x)[16]) {
+  if (TERMS == 1) {
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(x[j]);
+    tmem_st16(t_hi, w);
+    return;
+  }
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
@@ -533,7 +552,7 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
 }
 
 // ---------------------------------------------------------------------------------------------- forward (ws, dedicated issuer warp)
-template <bool SMEM_TABLES>
+template <bool SMEM_TABLES, int TERMS>
 __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   extern __shared__ uint8_t smraw[];
   __shared__ WsiBars bars;
@@ -588,7 +607,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             x.ph_u ^= 1u;
             fence_after_sync();
             if (elect_one()) {
-              issue_gemm_3xtf32<0, 3>(tm + x.cur, tm + (x.cur ^ 64u), tm + (x.cur ^ 64u) + 32, aWrH, aWrL, 64, idesc64, 0u);
+              issue_gemm_3xtf32<0, 3, TERMS>(tm + x.cur, tm + (x.cur ^ 64u), tm + (x.cur ^ 64u) + 32, aWrH, aWrL, 64, idesc64, 0u);
               mma_commit(&bars.d_full[i]);
             }
             __syncwarp();
@@ -598,7 +617,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             x.ph_a ^= 1u;
             fence_after_sync();
             if (elect_one()) {
-              issue_gemm_3xtf32<0, 8>(tm + (x.cur ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
+              issue_gemm_3xtf32<0, 8, TERMS>(tm + (x.cur ^ 64u), tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
               mma_commit(&bars.d_full[i]);
             }
             __syncwarp();
@@ -668,7 +687,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<false>(r, g.inv_cutoff, o, od);
-        st_split24(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
+        st_split24<TERMS>(lane_addr + (cur ^ 64u), lane_addr + (cur ^ 64u) + 32, o);
         tmem_st_wait();
         warp_arrive_i(u_ok, lane);
       }
@@ -712,7 +731,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             v[4 * j4 + 2] = y.z;
             v[4 * j4 + 3] = y.w;
           }
-          st_split16(lane_addr + VH + col0, lane_addr + VL + col0, v);
+          st_split16<TERMS>(lane_addr + VH + col0, lane_addr + VL + col0, v);
         }
         tmem_st_wait();
         warp_arrive_i(a_full, lane);
@@ -734,7 +753,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             rbf_regs<false>(r_n, g.inv_cutoff, o, od);
             mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
             __syncwarp();
-            st_split24(lane_addr + cur, lane_addr + cur + 32, o);
+            st_split24<TERMS>(lane_addr + cur, lane_addr + cur + 32, o);
             tmem_st_wait();
             warp_arrive_i(u_ok, lane);
           }
@@ -782,7 +801,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 }
 
 // ---------------------------------------------------------------------------------------------- adjoint (ws)
-template <bool SMEM_TABLES>
+template <bool SMEM_TABLES, int TERMS>
 __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   extern __shared__ uint8_t smraw[];
   __shared__ WsBars bars;
@@ -833,15 +852,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     const uint32_t aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
     auto issue_u_du = [&]() {      // u = rbf . Wr^T ; du = drbf . Wr^T
       if (elect_one()) {
-        issue_gemm_3xtf32<0, 3>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
-        issue_gemm_3xtf32<0, 3>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
+        issue_gemm_3xtf32<0, 3, TERMS>(tm + ACC, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
+        issue_gemm_3xtf32<0, 3, TERMS>(tm + DU, tm + XH + 32, tm + XL + 32, aWrH, aWrL, 64, idesc64, 0u);
         mma_commit(d_full);
       }
       __syncwarp();
     };
     auto issue_x = [&](uint32_t bH, uint32_t bL) {   // ACC = X . B^T  (w with W2, vbar with W2^T)
       if (elect_one()) {
-        issue_gemm_3xtf32<0, 8>(tm + ACC, tm + XH, tm + XL, bH, bL, 64, idesc64, 0u);
+        issue_gemm_3xtf32<0, 8, TERMS>(tm + ACC, tm + XH, tm + XL, bH, bL, 64, idesc64, 0u);
         mma_commit(d_full);
       }
       __syncwarp();
@@ -911,8 +930,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       if (ch == 0) {
         float o[32], od[32];
         rbf_regs<true>(r, g.inv_cutoff, o, od);
-        st_split24(lane_addr + XH, lane_addr + XL, o);
-        st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od);
+        st_split24<TERMS>(lane_addr + XH, lane_addr + XL, o);
+        st_split24<TERMS>(lane_addr + XH + 32, lane_addr + XL + 32, od);
         tmem_st_wait();
       }
       if (warp_arrive_last(cnt_u, 8, lane)) issue_u_du();
@@ -959,7 +978,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           for (int j4 = 0; j4 < 4; ++j4) {
             silu_fd4_sum3(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], &dsu[16 * c + 4 * j4]);
           }
-          st_split16(lane_addr + XH + col0, lane_addr + XL + col0, v);
+          st_split16<TERMS>(lane_addr + XH + col0, lane_addr + XL + col0, v);
         }
         tmem_st_wait();
         if (warp_arrive_last(cnt_a, 8, lane)) issue_x(aW2H, aW2L);              // w = v . W2^T
@@ -992,7 +1011,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
             wb[4 * j4 + 2] = sd.z;
             wb[4 * j4 + 3] = sd.w;
           }
-          st_split16(lane_addr + XH + col0, lane_addr + XL + col0, wb);
+          st_split16<TERMS>(lane_addr + XH + col0, lane_addr + XL + col0, wb);
         }
         tmem_st_wait();
         if (warp_arrive_last(cnt_a, 8, lane)) issue_x(aW2tH, aW2tL);            // vbar = wbar . W2
@@ -1034,8 +1053,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
         // vbar is complete, so the X operand columns are free: the radial operands of the next tile leave the
         // registers before the last epilogue needs them
         if (has_next && ch == 0) {
-          st_split24(lane_addr + XH, lane_addr + XL, o_n);
-          st_split24(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
+          st_split24<TERMS>(lane_addr + XH, lane_addr + XL, o_n);
+          st_split24<TERMS>(lane_addr + XH + 32, lane_addr + XL + 32, od_n);
         }
         // slot of this edge in the dense pair-adjoint array; its previous value is fetched early (layers 2, 1 add)
         size_t rslot = 0;
@@ -1103,33 +1122,43 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
-int launch_edge_fwd_ws(Ctx* c, int l, cudaStream_t st) {
+template <bool T, int TERMS>
+static int launch_fwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
+  GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_fwd_wsi_kernel<T, TERMS><<<grid, kWsiThreads, smem, st>>>(g, gb);
+  return 0;
+}
+template <bool T, int TERMS>
+static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
+  GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<T, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_bwd_ws_kernel<T, TERMS><<<grid, kWsThreads, smem, st>>>(g, gb);
+  return 0;
+}
+
+// terms = 3: 3xTF32 (fp32-accurate, default); terms = 1: one TF32 product per contraction (GNNIS_FLAG_MLP_TF32X1)
+int launch_edge_fwd_ws(Ctx* c, int l, int terms, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
-  size_t smem = fwd_tc_smem(c);
-  uint32_t gb = (uint32_t)group_bytes(c, 2);
-  if (c->smem_tables) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_wsi_kernel<true><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
-  } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_wsi_kernel<false><<<tc_grid(c), kWsiThreads, smem, st>>>(g, gb);
-  }
+  const size_t smem = fwd_tc_smem(c);
+  const uint32_t gb = (uint32_t)group_bytes(c, 2);
+  const int grid = tc_grid(c);
+  int rc;
+  if (c->smem_tables) rc = terms == 1 ? launch_fwd_t<true, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<true, 3>(c, g, grid, smem, gb, st);
+  else rc = terms == 1 ? launch_fwd_t<false, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<false, 3>(c, g, grid, smem, gb, st);
+  if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, cudaStream_t st) {
+int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
   g.rbar_accumulate = rbar_accumulate;
-  size_t smem = bwd_tc_smem(c);
-  uint32_t gb = (uint32_t)group_bytes(c, 2);
-  if (c->smem_tables) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_ws_kernel<true><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
-  } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_ws_kernel<false><<<tc_grid(c), kWsThreads, smem, st>>>(g, gb);
-  }
+  const size_t smem = bwd_tc_smem(c);
+  const uint32_t gb = (uint32_t)group_bytes(c, 2);
+  const int grid = tc_grid(c);
+  int rc;
+  if (c->smem_tables) rc = terms == 1 ? launch_bwd_t<true, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<true, 3>(c, g, grid, smem, gb, st);
+  else rc = terms == 1 ? launch_bwd_t<false, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<false, 3>(c, g, grid, smem, gb, st);
+  if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
   return 0;
 }

@@ -180,7 +180,7 @@ class Engine:
 
     # ------------------------------------------------------------------ hot path
     def energy_force(self, positions: torch.Tensor, *, delta=False, forces=True, gb_only=False, cuda_cores=False,
-                     data_predicate=False, vacuum_only=False, out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
+                     data_predicate=False, vacuum_only=False, tf32x1=False, out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
         """positions [R,N,3] (or [R*N,3]) fp32 on the engine's device -> (E[R], F[R,N,3] or None)."""
         p = self._pos(positions)
         e = out_energy if out_energy is not None else torch.empty(self.n_rep, dtype=torch.float32, device=self.device)
@@ -189,7 +189,8 @@ class Engine:
             f = out_force if out_force is not None else torch.empty_like(p)
         flags = ((_lib.FLAG_DELTA if delta else 0) | (0 if forces else _lib.FLAG_NO_FORCES)
                  | (_lib.FLAG_GB_ONLY if gb_only else 0) | (_lib.FLAG_MLP_CUDA_CORES if cuda_cores else 0)
-                 | (_lib.FLAG_DATA_PREDICATE if data_predicate else 0) | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0))
+                 | (_lib.FLAG_DATA_PREDICATE if data_predicate else 0) | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0)
+                 | (_lib.FLAG_MLP_TF32X1 if tf32x1 else 0))
         self._check(self.lib.gnnis_energy_force(self._h, p.data_ptr(), e.data_ptr(), f.data_ptr() if forces else None,
                                                 flags, self._stream()))
         return e, f

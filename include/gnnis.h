@@ -28,8 +28,12 @@ typedef struct gnnis_ctx* gnnis_handle;
                                       polar energy = E_GB(B') - E_GB(B)                                    */
 #define GNNIS_FLAG_NO_FORCES 0x2u  /* energy only (skips the adjoint pass)                                */
 #define GNNIS_FLAG_GB_ONLY 0x4u    /* plain GB-Neck2 (GNN_GBNeck_2, GNN_Models.py:173): B' = B, no SA term */
-#define GNNIS_FLAG_MLP_BF16 0x8u   /* reserved, returns -3: reduced-precision MLP modes were measured and rejected
-                                      (single-pass TF32 already misses the parity gates)     */
+#define GNNIS_FLAG_MLP_BF16 0x8u   /* reserved, returns -3: no bf16 MLP mode (single-pass TF32 already misses the fp32
+                                      parity gates)                                         */
+#define GNNIS_FLAG_MLP_TF32X1 0x80u /* opt-in reduced-precision mode of the edge MLPs: ONE TF32 product per contraction
+                                      instead of the fp32-accurate 3xTF32 default.  Accuracy is stated separately
+                                      (tests/test_gpu_parity.py::test_tf32x1_mode: energies ~1e-3, forces ~1e-2 rel);
+                                      never used for the benchmark's headline number                        */
 #define GNNIS_FLAG_DATA_PREDICATE 0x20u /* GNN graph by torch_cluster.radius_graph semantics, sum((x_i-x_j)^2) < r^2
                                       (data path, GNN_Models.py:345-357), instead of eps-distance r < cutoff */
 #define GNNIS_FLAG_VACUUM_ONLY 0x40u  /* only the vacuum force field of gnnis_set_forcefield (no GB, no GNN): the

@@ -231,3 +231,21 @@ def test_cuda_graph_capture(weights):
     torch.cuda.synchronize()
     e2, f2 = eng.energy_force(pos)
     assert torch.equal(e, e2) and torch.equal(f, f2)
+
+
+@pytest.mark.parametrize("name", ["c2_n50_water", "n100_mixed"])
+def test_tf32x1_mode(name, weights):
+    """Opt-in reduced-precision mode of the edge MLPs (GNNIS_FLAG_MLP_TF32X1: one TF32 product per contraction).
+    north_star asks for the tolerance of a reduced-precision MLP mode to be stated separately: it misses the fp32
+    gates (1e-4 / 1e-3) and is held to energies 2e-3, forces 2e-2 relative; the default path is unaffected."""
+    c = load_case(name)
+    eng = _engine(c, weights)
+    pos = torch.from_numpy(c["pos"]).cuda()
+    e3, f3 = eng.energy_force(pos)
+    e1, f1 = eng.energy_force(pos, tf32x1=True)
+    e_rel = float((e1 - e3).abs().max() / e3.abs().max())
+    f_rel = rel_rms(f1.cpu().numpy(), f3.cpu().numpy())
+    print(f"tf32x1 vs 3xTF32 [{name}]: energy max rel {e_rel:.2e}, force rel-RMS {f_rel:.2e}")
+    assert 0.0 < e_rel < 2e-3 and 0.0 < f_rel < 2e-2          # different from, and close to, the fp32-accurate result
+    e3b, f3b = eng.energy_force(pos)                           # the default mode is bit-reproducible afterwards
+    assert torch.equal(e3, e3b) and torch.equal(f3, f3b)
