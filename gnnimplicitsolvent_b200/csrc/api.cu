@@ -76,8 +76,13 @@ static int ensure_workspace(Ctx* c) {
     return -1;
   }
   if (c->N <= kUnitAtomsMax) {
+    // replicas per unit: as many as the shared-memory tables hold (full 128-edge tiles), but never so many that
+    // fewer than two units per SM remain -- with few replicas the length of one group's serial tile chain, not the
+    // tile fill, decides the latency of an evaluation
     c->G = kUnitAtomsMax / c->N;
-    if (c->G > c->R) c->G = c->R;
+    const int spread = c->R / (2 * (c->num_sms > 0 ? c->num_sms : 148));
+    if (c->G > spread) c->G = spread;
+    if (c->G < 1) c->G = 1;
     c->smem_tables = true;
   } else {
     c->G = 1;
