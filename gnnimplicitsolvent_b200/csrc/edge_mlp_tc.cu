@@ -327,10 +327,9 @@ int build_edge_images(Ctx* c, cudaStream_t st) {
 
 bool tc_path_fits(const Ctx* c) { return fwd_tc_smem(c) <= 227 * 1024 && bwd_tc_smem(c) <= 227 * 1024; }
 
-static int tc_grid(const Ctx* c) {
-  int want = (c->n_units + kGroups - 1) / kGroups;
-  return want < c->num_sms ? want : c->num_sms;
-}
+// Units are dealt out CTA-first (unit u -> CTA u % grid, group (u / grid) % 2), so that with fewer units than
+// 2 x #SM every unit gets an SM of its own before any SM runs two groups.
+static int tc_grid(const Ctx* c) { return c->n_units < c->num_sms ? c->n_units : c->num_sms; }
 
 // ================================================================================================================
 // 16-warp variant (default): 2 groups x 8 warps per CTA, no group-wide barrier on the MMA hand-off.
@@ -593,7 +592,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
       IssueState st[kGroups];
       for (int i = 0; i < kGroups; ++i) {
-        st[i] = IssueState{(int)blockIdx.x * kGroups + i, 0, 0, 0, 0u, 0u, 0u, false};
+        st[i] = IssueState{(int)blockIdx.x + i * (int)gridDim.x, 0, 0, 0, 0u, 0u, 0u, false};
         issue_next_unit(st[i], g);
       }
       while (!(st[0].done && st[1].done)) {
@@ -645,7 +644,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     uint32_t ph_d = 0, ph_a = 0, cur = 0;
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
-    for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
+    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
       const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
       const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
       const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
@@ -868,7 +867,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     uint32_t ph_d = 0;
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
-    for (int unit = blockIdx.x * kGroups + grp; unit < g.n_units; unit += gridDim.x * kGroups) {
+    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
       const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
       const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
       const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];

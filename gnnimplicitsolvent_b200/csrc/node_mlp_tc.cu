@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_fwd_tc_kernel(NodeTcArgs g
   (void)aW4H; (void)aW4L; (void)aWpH; (void)aWpL; (void)idesc64;
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
-  for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
+  for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
     if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_a_tc_kernel(NodeTcArgs
   const uint32_t aWpH = smem_u32(sWpH), aWpL = smem_u32(sWpL), aW4H = smem_u32(sW4H), aW4L = smem_u32(sW4L);
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
-  for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
+  for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
     if (nt_tile_skipped(g, tile)) continue;
     const int r0w = tile * kNtRows + 32 * wq;   // first row of this warp's 32-row block
     const NtRows wr{sStage + 512 * warp, max(0, min(32, g.n - r0w)), lane};
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_bwd_b_tc_kernel(NodeTcArgs
   const uint32_t aW3H = smem_u32(sW3H), aW3L = smem_u32(sW3L), aWtH = smem_u32(sWtH), aWtL = smem_u32(sWtL);
   const int ntiles = (g.n + kNtRows - 1) / kNtRows;
 
-  for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
+  for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
     if (nt_tile_skipped(g, tile)) continue;
     const int r = tile * kNtRows + row;
     const bool ok = r < g.n;
@@ -540,9 +540,9 @@ static NodeTcArgs nt_args(Ctx* c, int l) {
   return g;
 }
 
-static int nt_grid(const Ctx* c) {   // two tiles (one per warp group) in flight per CTA
-  int npairs = ((c->R * c->N + kNtRows - 1) / kNtRows + 1) / 2;
-  return npairs < c->num_sms ? npairs : c->num_sms;
+static int nt_grid(const Ctx* c) {   // tiles are dealt out CTA-first; the second warp group of a CTA takes tile blockIdx + grid
+  int ntiles = (c->R * c->N + kNtRows - 1) / kNtRows;
+  return ntiles < c->num_sms ? ntiles : c->num_sms;
 }
 
 int build_node_images(Ctx* c, cudaStream_t st) {
