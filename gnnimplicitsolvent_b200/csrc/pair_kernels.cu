@@ -84,8 +84,30 @@ __device__ __forceinline__ bool in_cutoff(int predicate, float r, float sx, floa
   return d2 < __fmul_rn(cutoff, cutoff);
 }
 
+// The all-pairs kernels come in two shapes (template LANES): one thread per target (LANES = 1: large batches, where
+// they are bound by instruction issue) or four lanes per target that share the source loop and combine their partial
+// sums with two shuffles in a fixed order (LANES = 4: small batches, where one thread's 50-iteration dependent chain
+// is the latency of the whole launch).  A CTA covers kPairThreads consecutive atoms in both shapes.
+template <int LANES>
+__device__ __forceinline__ float lanes_sum(float x) {
+#pragma unroll
+  for (int o = 1; o < LANES; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+template <int LANES>
+__device__ __forceinline__ int lanes_sum_int(int x) {
+#pragma unroll
+  for (int o = 1; o < LANES; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+static int pair_lanes(const Ctx* c) {   // few CTAs per SM: latency matters more than issue slots
+  const int nblk = (c->R * c->N + kPairThreads - 1) / kPairThreads;
+  return nblk < 4 * c->num_sms ? 4 : 1;
+}
+
 // dynamic smem: pos[3*nst] | rho[N] | s[N] | radidx[N] | d0[UU] | m0[UU]
-__global__ void __launch_bounds__(kPairThreads)
+template <int LANES>
+__global__ void __launch_bounds__(kPairThreads * LANES)
 born_count_kernel(const float* __restrict__ pos, int n, int N, int U, const float* __restrict__ rho,
                   const float* __restrict__ s, const int* __restrict__ radidx, const float* __restrict__ alpha,
                   const float* __restrict__ beta, const float* __restrict__ gamma, const float* __restrict__ d0,
@@ -102,29 +124,32 @@ born_count_kernel(const float* __restrict__ pos, int n, int N, int U, const floa
   float* sm0 = sd0 + U * U;
   __shared__ int s_blk;
   if (threadIdx.x == 0) s_blk = 0;
-  for (int t = threadIdx.x; t < 3 * st.n_stage_atoms; t += kPairThreads) spos[t] = pos[(size_t)st.base_atom * 3 + t];
-  for (int t = threadIdx.x; t < N; t += kPairThreads) {
+  for (int t = threadIdx.x; t < 3 * st.n_stage_atoms; t += blockDim.x) spos[t] = pos[(size_t)st.base_atom * 3 + t];
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
     srho[t] = rho[t];
     ss[t] = s[t];
     sidx[t] = radidx[t];
   }
-  for (int t = threadIdx.x; t < U * U; t += kPairThreads) {
+  for (int t = threadIdx.x; t < U * U; t += blockDim.x) {
     sd0[t] = d0[t];
     sm0[t] = m0[t];
   }
   __syncthreads();
-  int i = blockIdx.x * kPairThreads + threadIdx.x;
+  const int sub = threadIdx.x % LANES;
+  int i = blockIdx.x * kPairThreads + threadIdx.x / LANES;
+  const bool skipped = i < n && skip && skip[i / N] == 2;
+  const bool act = i < n && !skipped;
   int mydeg = 0;
-  if (i < n && skip && skip[i / N] == 2) {
-    deg[i] = 0;   // finished replica: no edges, nothing downstream touches it
-  } else if (i < n) {
-    int rep = i / N, a = i - rep * N;
+  float I = 0.0f;
+  int rep = 0, a = 0;
+  if (act) {
+    rep = i / N;
+    a = i - rep * N;
     const float* rp = spos + (size_t)(rep - st.first_rep) * N * 3;
     float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
     float rho_i = srho[a];
     int ri = sidx[a];
-    float I = 0.0f;
-    for (int j = 0; j < N; ++j) {
+    for (int j = sub; j < N; j += LANES) {
       if (j == a) continue;
       float dx, dy, dz;
       float sx = rp[3 * j], sy = rp[3 * j + 1], sz = rp[3 * j + 2];
@@ -132,6 +157,14 @@ born_count_kernel(const float* __restrict__ pos, int n, int N, int U, const floa
       mydeg += in_cutoff(predicate, r, sx, sy, sz, tx, ty, tz, cutoff) ? 1 : 0;
       I += born_integral(r, rho_i, srho[j], ss[j], U * sidx[j] + ri, sd0, sm0);
     }
+  }
+  I = lanes_sum<LANES>(I);
+  mydeg = lanes_sum_int<LANES>(mydeg);
+  if (sub != 0) mydeg = 0;           // one lane per target carries the degree into the block sum
+  if (skipped && sub == 0) {
+    deg[i] = 0;   // finished replica: no edges, nothing downstream touches it
+  } else if (act && sub == 0) {
+    float rho_i = srho[a];
     float radius = rho_i + kOffset;
     float psi = I * rho_i;
     float al = alpha[a], be = beta[a], ga = gamma[a];
@@ -255,7 +288,8 @@ __device__ __forceinline__ GbTerm gb_term(float r, float P) {
 
 // dynamic smem: pos[3*nst] | Bs[nst] | B[nst] | q[N]
 // mode bit0: delta (subtract GB energy evaluated with the unscaled B)
-__global__ void __launch_bounds__(kPairThreads)
+template <int LANES>
+__global__ void __launch_bounds__(kPairThreads * LANES)
 gb_energy_kernel(const int* __restrict__ skip, const float* __restrict__ pos, int n, int N, const float* __restrict__ q,
                  const float* __restrict__ born_s, const float* __restrict__ born, const float* __restrict__ pref,
                  int delta, int want_grad, float* __restrict__ e_atom, float* __restrict__ dE_dBs,
@@ -266,25 +300,27 @@ gb_energy_kernel(const int* __restrict__ skip, const float* __restrict__ pos, in
   float* sBs = spos + 3 * st.n_stage_atoms;
   float* sB = sBs + st.n_stage_atoms;
   float* sq = sB + st.n_stage_atoms;
-  for (int t = threadIdx.x; t < 3 * st.n_stage_atoms; t += kPairThreads) spos[t] = pos[(size_t)st.base_atom * 3 + t];
-  for (int t = threadIdx.x; t < st.n_stage_atoms; t += kPairThreads) {
+  for (int t = threadIdx.x; t < 3 * st.n_stage_atoms; t += blockDim.x) spos[t] = pos[(size_t)st.base_atom * 3 + t];
+  for (int t = threadIdx.x; t < st.n_stage_atoms; t += blockDim.x) {
     sBs[t] = born_s[st.base_atom + t];
     sB[t] = delta ? born[st.base_atom + t] : 0.0f;
   }
-  for (int t = threadIdx.x; t < N; t += kPairThreads) sq[t] = q[t];
+  for (int t = threadIdx.x; t < N; t += blockDim.x) sq[t] = q[t];
   __syncthreads();
-  int i = blockIdx.x * kPairThreads + threadIdx.x;
-  if (i >= n) return;
+  const int sub = threadIdx.x % LANES;
+  int i = blockIdx.x * kPairThreads + threadIdx.x / LANES;
+  const bool act = i < n && !(skip && skip[i / N] == 2);   // uniform over the LANES lanes of a target
+  if (LANES == 1 && !act) return;
+  if (!act) i = 0;                                          // idle lane groups still take part in the shuffles
   int rep = i / N, a = i - rep * N;
-  if (skip && skip[rep] == 2) return;
-  int lo = (rep - st.first_rep) * N;
+  int lo = act ? (rep - st.first_rep) * N : 0;
   const float* rp = spos + (size_t)lo * 3;
   float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
   float qi = sq[a], Bi = sBs[lo + a], B0i = sB[lo + a];
   float pf = pref[rep];
   float pair_sum = 0.0f, pair_sum0 = 0.0f;
   float gx = 0.0f, gy = 0.0f, gz = 0.0f, dBs = 0.0f, dB0 = 0.0f;
-  for (int j = 0; j < N; ++j) {
+  for (int j = sub; j < (act ? N : 0); j += LANES) {
     if (j == a) continue;
     float sx = rp[3 * j], sy = rp[3 * j + 1], sz = rp[3 * j + 2];
     float d1x, d1y, d1z;
@@ -318,6 +354,16 @@ gb_energy_kernel(const int* __restrict__ skip, const float* __restrict__ pos, in
       pair_sum0 += qq * gb_term(r1, B0i * sB[lo + j]).e;
     }
   }
+  if (LANES > 1) {
+    pair_sum = lanes_sum<LANES>(pair_sum);
+    pair_sum0 = lanes_sum<LANES>(pair_sum0);
+    gx = lanes_sum<LANES>(gx);
+    gy = lanes_sum<LANES>(gy);
+    gz = lanes_sum<LANES>(gz);
+    dBs = lanes_sum<LANES>(dBs);
+    dB0 = lanes_sum<LANES>(dB0);
+    if (!act || sub != 0) return;
+  }
   float e = pf * (pair_sum + qi * qi / Bi);
   if (delta) e -= pf * (pair_sum0 + qi * qi / B0i);
   e_atom[i] = e;
@@ -333,7 +379,8 @@ gb_energy_kernel(const int* __restrict__ skip, const float* __restrict__ pos, in
 }
 
 // dynamic smem: pos[3*nst] | Ibar[nst] | rho[N] | s[N] | radidx[N] | d0[UU] | m0[UU]
-__global__ void __launch_bounds__(kPairThreads)
+template <int LANES>
+__global__ void __launch_bounds__(kPairThreads * LANES)
 born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos, int n, int N, int U, const float* __restrict__ rho,
                     const float* __restrict__ s, const int* __restrict__ radidx, const float* __restrict__ d0,
                     const float* __restrict__ m0, float cutoff, const float* __restrict__ Bbar,
@@ -348,24 +395,26 @@ born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos,
   int* sidx = reinterpret_cast<int*>(ss + N);
   float* sd0 = reinterpret_cast<float*>(sidx + N);
   float* sm0 = sd0 + U * U;
-  for (int t = threadIdx.x; t < 3 * st.n_stage_atoms; t += kPairThreads) spos[t] = pos[(size_t)st.base_atom * 3 + t];
-  for (int t = threadIdx.x; t < st.n_stage_atoms; t += kPairThreads)
+  for (int t = threadIdx.x; t < 3 * st.n_stage_atoms; t += blockDim.x) spos[t] = pos[(size_t)st.base_atom * 3 + t];
+  for (int t = threadIdx.x; t < st.n_stage_atoms; t += blockDim.x)
     sIbar[t] = Bbar[st.base_atom + t] * dBdI[st.base_atom + t];
-  for (int t = threadIdx.x; t < N; t += kPairThreads) {
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
     srho[t] = rho[t];
     ss[t] = s[t];
     sidx[t] = radidx[t];
   }
-  for (int t = threadIdx.x; t < U * U; t += kPairThreads) {
+  for (int t = threadIdx.x; t < U * U; t += blockDim.x) {
     sd0[t] = d0[t];
     sm0[t] = m0[t];
   }
   __syncthreads();
-  int i = blockIdx.x * kPairThreads + threadIdx.x;
-  if (i >= n) return;
+  const int sub = threadIdx.x % LANES;
+  int i = blockIdx.x * kPairThreads + threadIdx.x / LANES;
+  const bool act = i < n && !(skip && skip[i / N] == 2);
+  if (LANES == 1 && !act) return;
+  if (!act) i = 0;
   int rep = i / N, a = i - rep * N;
-  if (skip && skip[rep] == 2) return;
-  int lo = (rep - st.first_rep) * N;
+  int lo = act ? (rep - st.first_rep) * N : 0;
   const float* rp = spos + (size_t)lo * 3;
   float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
   float rho_i = srho[a], s_i = ss[a], Ibar_i = sIbar[lo + a];
@@ -373,7 +422,7 @@ born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos,
   const float* rbar_row = rbar + (size_t)i * N;                 // slots [i][j]: edges (j -> i)
   const float* rbar_col = rbar + (size_t)rep * N * N + a;       // slots [j][i]: edges (i -> j), stride N
   float gx = 0.0f, gy = 0.0f, gz = 0.0f;
-  for (int j = 0; j < N; ++j) {
+  for (int j = sub; j < (act ? N : 0); j += LANES) {
     if (j == a) continue;
     float sx = rp[3 * j], sy = rp[3 * j + 1], sz = rp[3 * j + 2];
     float d1x, d1y, d1z, d2x, d2y, d2z;
@@ -392,6 +441,12 @@ born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos,
     gx += -g1 * d1x + g2 * d2x;
     gy += -g1 * d1y + g2 * d2y;
     gz += -g1 * d1z + g2 * d2z;
+  }
+  if (LANES > 1) {
+    gx = lanes_sum<LANES>(gx);
+    gy = lanes_sum<LANES>(gy);
+    gz = lanes_sum<LANES>(gz);
+    if (!act || sub != 0) return;
   }
   force[3 * (size_t)i] -= gx;
   force[3 * (size_t)i + 1] -= gy;
@@ -419,10 +474,17 @@ int launch_born_count(Ctx* c, const float* pos, int predicate, cudaStream_t st) 
   int n = c->R * c->N;
   int nblk = (n + kPairThreads - 1) / kPairThreads;
   size_t smem = (3 * stage_atoms_max(c->N) + 3 * (size_t)c->N + 2 * (size_t)c->U * c->U) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(born_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  born_count_kernel<<<nblk, kPairThreads, smem, st>>>(pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->alpha, c->beta,
-                                                     c->gamma, c->d0, c->m0, c->cutoff, predicate, c->born, c->dBdI,
-                                                     c->deg, c->blk_sum, c->skip_state);
+  if (pair_lanes(c) == 4) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(born_count_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    born_count_kernel<4><<<nblk, 4 * kPairThreads, smem, st>>>(pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->alpha, c->beta,
+                                                              c->gamma, c->d0, c->m0, c->cutoff, predicate, c->born,
+                                                              c->dBdI, c->deg, c->blk_sum, c->skip_state);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(born_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    born_count_kernel<1><<<nblk, kPairThreads, smem, st>>>(pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->alpha, c->beta,
+                                                          c->gamma, c->d0, c->m0, c->cutoff, predicate, c->born, c->dBdI,
+                                                          c->deg, c->blk_sum, c->skip_state);
+  }
   GNNIS_LAUNCH_CHECK();
   scan_blocks_kernel<<<1, 1024, 0, st>>>(c->blk_sum, nblk, c->n_edges_dev, c->row_ptr + n);
   GNNIS_LAUNCH_CHECK();
@@ -446,9 +508,15 @@ int launch_gb_energy(Ctx* c, const float* pos, const float* born_s, int delta, i
   int n = c->R * c->N;
   int nblk = (n + kPairThreads - 1) / kPairThreads;
   size_t smem = (5 * stage_atoms_max(c->N) + (size_t)c->N) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(gb_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gb_energy_kernel<<<nblk, kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->q, born_s, c->born, c->pref, delta, want_grad,
-                                                    c->e_atom, c->dE_dBs, c->Bbar, force);
+  if (pair_lanes(c) == 4) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(gb_energy_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gb_energy_kernel<4><<<nblk, 4 * kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->q, born_s, c->born, c->pref, delta,
+                                                             want_grad, c->e_atom, c->dE_dBs, c->Bbar, force);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(gb_energy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gb_energy_kernel<1><<<nblk, kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->q, born_s, c->born, c->pref, delta,
+                                                         want_grad, c->e_atom, c->dE_dBs, c->Bbar, force);
+  }
   GNNIS_LAUNCH_CHECK();
   return 0;
 }
@@ -457,9 +525,15 @@ int launch_born_adjoint(Ctx* c, const float* pos, int use_rbar, float* force, cu
   int n = c->R * c->N;
   int nblk = (n + kPairThreads - 1) / kPairThreads;
   size_t smem = (4 * stage_atoms_max(c->N) + 3 * (size_t)c->N + 2 * (size_t)c->U * c->U) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(born_adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  born_adjoint_kernel<<<nblk, kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->d0, c->m0,
-                                                       c->cutoff, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
+  if (pair_lanes(c) == 4) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(born_adjoint_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    born_adjoint_kernel<4><<<nblk, 4 * kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->d0,
+                                                                c->m0, c->cutoff, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(born_adjoint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    born_adjoint_kernel<1><<<nblk, kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->d0,
+                                                            c->m0, c->cutoff, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
+  }
   GNNIS_LAUNCH_CHECK();
   return 0;
 }
