@@ -20,7 +20,8 @@
 namespace gnnis {
 
 constexpr float kCoulombMM = 138.935456f;   // Simulator.py:2047 (the GB term uses 138.935485)
-constexpr int kFfThreads = 128;
+constexpr int kFfThreads = 256;   // 64 atoms per pass x 4 lanes per atom
+constexpr int kFfLanes = 4;
 
 struct FfArgs {
   int N, n_words;
@@ -66,8 +67,13 @@ __global__ void __launch_bounds__(kFfThreads) mm_forces_kernel(FfArgs g, const f
     se[t] = g.epsilon[t];
   }
   __syncthreads();
+  // Four lanes share an atom: they split its source loop and its term list and combine their partial force / energy
+  // with two shuffles in a fixed order (one thread per atom left 60 of 128 threads with a 60-iteration dependent chain).
   float e_acc = 0.0f;
-  for (int i = tid; i < g.N; i += kFfThreads) {
+  const int ln = tid % kFfLanes;
+  for (int base = 0; base < g.N; base += kFfThreads / kFfLanes) {
+    const int i = min(base + tid / kFfLanes, g.N - 1);
+    const bool act = base + tid / kFfLanes < g.N;
     const V3 xi = ld3(sp, i);
     const float qi = sq[i] * kCoulombMM, si = ss[i], ei = se[i];
     float fx = 0.f, fy = 0.f, fz = 0.f, e = 0.f;
@@ -75,8 +81,8 @@ __global__ void __launch_bounds__(kFfThreads) mm_forces_kernel(FfArgs g, const f
     const uint32_t* row = g.excl + (size_t)i * g.n_words;
     for (int w = 0; w < g.n_words; ++w) {
       const uint32_t mask = row[w];
-      const int j1 = min(g.N, 32 * w + 32);
-      for (int j = 32 * w; j < j1; ++j) {
+      const int j1 = act ? min(g.N, 32 * w + 32) : 0;
+      for (int j = 32 * w + ln; j < j1; j += kFfLanes) {
         if (j == i || ((mask >> (j & 31)) & 1u)) continue;
         const V3 d = sub(xi, ld3(sp, j));
         const float r2 = dot(d, d);
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(kFfThreads) mm_forces_kernel(FfArgs g, const f
       }
     }
     // ---- bonded terms and exceptions this atom takes part in
-    for (int t = g.term_ptr[i]; t < g.term_ptr[i + 1]; ++t) {
+    for (int t = g.term_ptr[i] + ln; t < (act ? g.term_ptr[i + 1] : 0); t += kFfLanes) {
       const int ref = g.term_ref[t], type = ref & 3, role = (ref >> 2) & 3, idx = ref >> 4;
       if (type == 0) {
         const int4 a = g.bond[idx];
@@ -172,6 +178,14 @@ __global__ void __launch_bounds__(kFfThreads) mm_forces_kernel(FfArgs g, const f
         fz += gmag * d.z;
       }
     }
+#pragma unroll
+    for (int o = 1; o < kFfLanes; o <<= 1) {
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+      fx += __shfl_xor_sync(0xffffffffu, fx, o);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o);
+      fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (!act || ln != 0) continue;
     e_acc += e;
     if (force) {
       float* f = force + ((size_t)rep * g.N + i) * 3;
