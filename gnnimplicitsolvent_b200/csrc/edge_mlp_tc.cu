@@ -1062,7 +1062,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           rslot = ((size_t)atom0 + tg) * g.N + (sr - (tg / g.N) * g.N);
           if (g.rbar_accumulate) rold = g.rbar[rslot];
         }
-        ws_group_sync(grp);                          // (A) reductions of the previous tile are complete
+        // No barrier is needed before the shared tile is overwritten: this warp is past the vbar wait, vbar was issued
+        // by the last of the eight warps to finish the wbar epilogue, and every warp runs both reductions of the
+        // previous tile before that epilogue -- so all reads of the tile are complete.
         // ---- ubar = vbar * silu'(u) -> smem tile ; rbar = ubar . du (this thread's 32 channels)
         float racc = 0.0f;
 #pragma unroll
