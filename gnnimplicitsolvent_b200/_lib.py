@@ -49,6 +49,8 @@ SIGNATURES = {
                                         C.c_int64, c_int64_p, C.c_void_p]),
     "gnnis_energy_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "gnnis_energy_force_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "gnnis_energy_force_host_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "gnnis_energy_force_host_wait": (C.c_int, [C.c_void_p]),
     "gnnis_get_atom_energies": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnis_get_born_radii": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnis_last_edge_count": (C.c_int, [C.c_void_p, c_int64_p, C.c_void_p]),

@@ -305,6 +305,16 @@ int gnnis_destroy(gnnis_handle h) {
   dev_free(&c->pair);
   dev_free(&c->perm);
   dev_free(&c->n_edges_dev);
+  for (Ctx::HostSlot& s : c->hs) {
+    dev_free(&s.pos);
+    dev_free(&s.e);
+    dev_free(&s.f);
+    if (s.in) cudaEventDestroy(s.in);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.out) cudaEventDestroy(s.out);
+  }
+  if (c->hs_in) cudaStreamDestroy(c->hs_in);
+  if (c->hs_out) cudaStreamDestroy(c->hs_out);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return 0;
@@ -572,6 +582,69 @@ int gnnis_energy_force_host(gnnis_handle h, const float* pos_host, float* e_rep_
   if (want && force_host)
     GNNIS_CUDA_OK(cudaMemcpyAsync(force_host, c->h_f_dev, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   GNNIS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- pipelined variant: up to two calls in flight; copies on their own streams, evaluations in submission order
+int gnnis_energy_force_host_submit(gnnis_handle h, const float* pos_host, float* e_rep_host, float* force_host,
+                                   uint32_t flags) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (check_ready(c, !(flags & (GNNIS_FLAG_GB_ONLY | GNNIS_FLAG_VACUUM_ONLY)))) return -1;
+  if (!pos_host || !e_rep_host) {
+    c->err = "gnnis_energy_force_host_submit: NULL argument";
+    return -1;
+  }
+  if (c->hs_inflight >= 2) {
+    c->err = "gnnis_energy_force_host_submit: two calls are already in flight; call gnnis_energy_force_host_wait first";
+    return -4;
+  }
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  if (!c->hs_in) {
+    GNNIS_CUDA_OK(cudaStreamCreateWithFlags(&c->hs_in, cudaStreamNonBlocking));
+    GNNIS_CUDA_OK(cudaStreamCreateWithFlags(&c->hs_out, cudaStreamNonBlocking));
+  }
+  const size_t n = (size_t)c->R * c->N;
+  Ctx::HostSlot& s = c->hs[c->hs_next];
+  if (s.atoms != n || s.R != c->R) {   // the slot is idle here: its previous call has been waited for
+    if (dev_alloc(c, &s.pos, n * 3) || dev_alloc(c, &s.f, n * 3) || dev_alloc(c, &s.e, (size_t)c->R)) return -1;
+    s.atoms = n;
+    s.R = c->R;
+  }
+  if (!s.in) {
+    GNNIS_CUDA_OK(cudaEventCreateWithFlags(&s.in, cudaEventDisableTiming));
+    GNNIS_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    GNNIS_CUDA_OK(cudaEventCreateWithFlags(&s.out, cudaEventDisableTiming));
+  }
+  const bool want = !(flags & GNNIS_FLAG_NO_FORCES);
+  GNNIS_CUDA_OK(cudaMemcpyAsync(s.pos, pos_host, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->hs_in));
+  GNNIS_CUDA_OK(cudaEventRecord(s.in, c->hs_in));
+  GNNIS_CUDA_OK(cudaStreamWaitEvent(c->own_stream, s.in, 0));
+  int rc = energy_force_impl(c, s.pos, s.e, want ? s.f : nullptr, flags, c->own_stream, nullptr);
+  if (rc) return rc;
+  GNNIS_CUDA_OK(cudaEventRecord(s.done, c->own_stream));
+  GNNIS_CUDA_OK(cudaStreamWaitEvent(c->hs_out, s.done, 0));
+  GNNIS_CUDA_OK(cudaMemcpyAsync(e_rep_host, s.e, c->R * sizeof(float), cudaMemcpyDeviceToHost, c->hs_out));
+  if (want && force_host)
+    GNNIS_CUDA_OK(cudaMemcpyAsync(force_host, s.f, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->hs_out));
+  GNNIS_CUDA_OK(cudaEventRecord(s.out, c->hs_out));
+  c->hs_next ^= 1u;
+  c->hs_inflight += 1;
+  return 0;
+}
+
+int gnnis_energy_force_host_wait(gnnis_handle h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (c->hs_inflight <= 0) {
+    c->err = "gnnis_energy_force_host_wait: nothing in flight";
+    return -4;
+  }
+  // oldest call in flight: with two in flight it sits in the slot the next submission would take
+  const unsigned k = c->hs_inflight == 2 ? c->hs_next : (c->hs_next ^ 1u);
+  GNNIS_CUDA_OK(cudaSetDevice(c->device));
+  GNNIS_CUDA_OK(cudaEventSynchronize(c->hs[k].out));
+  c->hs_inflight -= 1;
   return 0;
 }
 

@@ -108,6 +108,18 @@ struct Ctx {
   // host-staging for gnnis_energy_force_host
   float *h_pos_dev = nullptr, *h_e_dev = nullptr, *h_f_dev = nullptr;
   cudaStream_t own_stream = nullptr;
+  // pipelined host entry point (gnnis_energy_force_host_submit / _wait): two staging slots, so that the H2D copy of
+  // call i+1 and the D2H copy of call i-1 run on their own streams under the evaluation of call i
+  struct HostSlot {
+    float *pos = nullptr, *e = nullptr, *f = nullptr;
+    cudaEvent_t in = nullptr, done = nullptr, out = nullptr;
+    size_t atoms = 0;
+    int R = 0;
+  };
+  HostSlot hs[2];
+  cudaStream_t hs_in = nullptr, hs_out = nullptr;
+  unsigned hs_next = 0;    // slot of the next submission
+  int hs_inflight = 0;     // submissions not yet waited for (<= 2)
   // bonds (optional harmonic terms)
   int n_bonds = 0;
   int* bond_idx = nullptr;

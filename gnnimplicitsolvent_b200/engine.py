@@ -204,6 +204,19 @@ class Engine:
                                                      f_host.data_ptr() if f_host is not None else None, flags))
         return e_host, f_host
 
+    def energy_force_host_submit(self, pos_host: torch.Tensor, e_host: torch.Tensor, f_host: Optional[torch.Tensor], *,
+                                 delta=False, gb_only=False):
+        """Pipelined form of energy_force_host: enqueues H2D + evaluation + D2H and returns at once (at most two
+        submissions in flight).  The tensors must stay alive and unread until the matching energy_force_host_wait()."""
+        flags = (_lib.FLAG_DELTA if delta else 0) | (_lib.FLAG_GB_ONLY if gb_only else 0) | (0 if f_host is not None else _lib.FLAG_NO_FORCES)
+        assert pos_host.dtype == torch.float32 and pos_host.is_contiguous() and not pos_host.is_cuda
+        self._check(self.lib.gnnis_energy_force_host_submit(self._h, pos_host.data_ptr(), e_host.data_ptr(),
+                                                            f_host.data_ptr() if f_host is not None else None, flags))
+
+    def energy_force_host_wait(self):
+        """Blocks until the OLDEST submission in flight has delivered its energies / forces."""
+        self._check(self.lib.gnnis_energy_force_host_wait(self._h))
+
     def atom_energies(self):
         """Per-atom polar and SA energies of the last evaluation (..._split, GNN_Models.py:1068-1083)."""
         n = self.n_rep * self.n_atoms

@@ -101,6 +101,16 @@ int gnnis_energy_force(gnnis_handle h, const float* pos_dev, float* e_rep_dev, f
 int gnnis_energy_force_host(gnnis_handle h, const float* pos_host, float* e_rep_host, float* force_host,
                             uint32_t flags);
 
+/* pipelined form of the call above for back-to-back batches (conformer streams, trajectory re-evaluation): submit
+ * enqueues H2D copy, evaluation and D2H copy and returns at once; wait blocks until the OLDEST submission has
+ * delivered its results.  At most two submissions may be in flight (a third returns -4); evaluations run in
+ * submission order, the copies of neighbouring calls overlap them on separate streams.  The host buffers of a
+ * submission must stay valid, and its results must not be read, until its wait returns; use pinned memory for the
+ * copies to be asynchronous.  Do not mix with other calls on the handle while submissions are in flight. */
+int gnnis_energy_force_host_submit(gnnis_handle h, const float* pos_host, float* e_rep_host, float* force_host,
+                                   uint32_t flags);
+int gnnis_energy_force_host_wait(gnnis_handle h);
+
 /* ..._run_multiple_split (GNN_Models.py:1068-1083): per-atom polar and SA energies of the LAST evaluation */
 int gnnis_get_atom_energies(gnnis_handle h, float* e_atom_dev, float* sa_atom_dev, void* stream);
 /* Born radii B (GBNeck_interaction output, GNN_Layers.py:982-1008) and scaled B' of the LAST evaluation */

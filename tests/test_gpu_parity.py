@@ -174,6 +174,41 @@ def test_host_api_matches_device_api(weights):
     assert torch.equal(e.cpu(), e_h) and torch.equal(f.cpu(), f_h)
 
 
+def test_pipelined_host_api(weights):
+    """submit / wait: results of a stream of batches equal the blocking host call bit for bit, arrive in submission
+    order, a third submission in flight is refused (-4) and a wait with nothing in flight is refused."""
+    from gnnimplicitsolvent_b200.engine import GnnisError
+    c = load_case("mixed_n21")
+    eng = _engine(c, weights)
+    R = c["pos"].shape[0]
+    g = torch.Generator().manual_seed(5)
+    batches = [torch.from_numpy(c["pos"]) + 0.002 * k * torch.randn(c["pos"].shape, generator=g) for k in range(5)]
+    batches = [b.float().contiguous().pin_memory() for b in batches]
+    ref = []
+    for b in batches:
+        e_h, f_h = torch.empty(R).pin_memory(), torch.empty(c["pos"].shape).pin_memory()
+        eng.energy_force_host(b, e_h, f_h)
+        ref.append((e_h.clone(), f_h.clone()))
+    outs = [(torch.empty(R).pin_memory(), torch.empty(c["pos"].shape).pin_memory()) for _ in batches]
+    with pytest.raises(GnnisError):
+        eng.energy_force_host_wait()
+    for k, b in enumerate(batches):
+        eng.energy_force_host_submit(b, outs[k][0], outs[k][1])
+        if k == 1:
+            with pytest.raises(GnnisError):
+                eng.energy_force_host_submit(b, outs[k][0], outs[k][1])   # two already in flight
+        if k >= 1:
+            eng.energy_force_host_wait()
+            assert torch.equal(outs[k - 1][0], ref[k - 1][0]) and torch.equal(outs[k - 1][1], ref[k - 1][1])
+    eng.energy_force_host_wait()
+    assert torch.equal(outs[-1][0], ref[-1][0]) and torch.equal(outs[-1][1], ref[-1][1])
+    # energies only
+    e_only = torch.empty(R).pin_memory()
+    eng.energy_force_host_submit(batches[0], e_only, None)
+    eng.energy_force_host_wait()
+    assert torch.equal(e_only, ref[0][0])
+
+
 @pytest.mark.parametrize("K,N", [(32, 64), (64, 64), (64, 32)])
 def test_umma_building_blocks(K, N):
     """tcgen05 building blocks (TMEM-resident A, 128B-swizzled smem B, 3xTF32): D = A B^T to fp32 accuracy."""
