@@ -185,6 +185,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -308,8 +310,13 @@ def main():
                 tj = json.load(f)
             if dom in tj and int(tj.get("replicas", 0)) == R:
                 traffic = tj[dom]
+        # explanatory only: tensor work the kernel EXECUTES per launch = 3 TF32 products per contraction; the adjoint
+        # runs u, du (K = 24) and w, vbar (K = 64) per tile, the forward u and w
+        k_exec = {"edge_bwd": 2 * 24 * 64 + 2 * 64 * 64, "edge_fwd": 24 * 64 + 64 * 64}.get(dom)
+        executed = 3 * 2.0 * e_per_launch * k_exec / (dur_ms * 1e-3) / 1e12 if k_exec else None
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
+                    "executed_tflops_3xtf32": executed, "executed_frac": executed / peak if executed else None,
                     "peak_source": f"{peak_kind} bf16 sustained / 2 (kind::tf32 rate); kernel computes in 3xTF32",
                     "algorithmic_flops_per_launch": flops_launch, "avg_launch_ms": dur_ms, "stage_ms": stage_acc}
         cpu_baseline = None
