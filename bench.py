@@ -160,7 +160,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def main():
@@ -172,6 +172,11 @@ def main():
     ap.add_argument("--replicas", type=int, default=R_PER_GPU, help="replicas per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries write to fd 1 (e.g. NCCL's version banner) goes to stderr
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -185,8 +190,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -340,7 +343,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if dist:
         dist.destroy_process_group()
 
