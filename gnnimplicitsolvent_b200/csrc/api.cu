@@ -257,7 +257,6 @@ int gnnis_create(gnnis_handle* out, int device) {
     delete c;
     return -1;
   }
-  if (const char* e = getenv("GNNIS_PP")) c->pp_mask = atoi(e);   // debug / A-B: ping-pong variants of the edge kernels
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;

@@ -62,7 +62,6 @@ struct Ctx {
   std::string err;
   int64_t launches = 0;
   int num_sms = 148;
-  int pp_mask = 0;   // "ping-pong" edge kernels (one 16-warp pipeline over two tiles): bit0 forward
   int tc_mask = 7;   // tcgen05 kernels in use: bit0 edge forward, bit1 edge adjoint, bit2 node MLPs (else fp32 CUDA cores)
   // model
   bool have_weights = false;

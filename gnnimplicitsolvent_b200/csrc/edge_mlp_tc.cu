@@ -414,12 +414,11 @@ __device__ __forceinline__ void zero_rows_n(float* __restrict__ dst, int ld_dst,
 
 // target-segment sums to global rows, 256 threads = 8 warps.  Warp w takes segments w, w+8, ...; its lanes are
 // 16 column quads x 2 row halves (first / second half of the segment), combined in fixed order through one shuffle.
-template <int NW = 8>
 __device__ __forceinline__ void reduce_targets_global_256(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
                                                           float* __restrict__ out, int gt) {
   const int lane = gt & 31, cq = lane & 15, half = lane >> 4, w = gt >> 5;
   const int nseg = tk->n_seg_t;
-  for (int s = w; s < nseg; s += NW) {
+  for (int s = w; s < nseg; s += 8) {
     const int p0 = tk->seg_t[s], p1 = tk->seg_t[s + 1];
     const int mid = p0 + ((p1 - p0 + 1) >> 1);
     const int a0 = half ? mid : p0, a1 = half ? p1 : mid;
@@ -800,307 +799,6 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
-
-// ================================================================================================================
-// "Ping-pong" forward variant: ONE pipeline of 16 epilogue warps working on TWO tiles in flight (TMEM slots 0 / 1)
-// instead of two independent 8-warp groups with one tile each.  A thread is (edge row, 16-column quarter), so every
-// epilogue is one 16-column chunk per thread, and the warps alternate between the tiles:
-//     iteration j:  E1(j): v = silu(u + P + Q) -> TMEM, hand-off of w(j)   |   E2(j-1): z = silu(w + b2) -> smem tile
-//                   barrier, then a[tgt] += z(j-1) (column quarters 1-3) next to rbf(j+2) (column quarter 0)
-// so the tensor pipe works on tile j while the warps run the other epilogue of tile j-1 and vice versa.  A 17th warp
-// issues all tcgen05.mma (one state machine per slot).  Per slot: ACC 64 columns (u, then w), radial operand hi / lo
-// at +64 / +96, v hi / lo at +128 / +192.  mbarriers per slot: u_ok (16 "accumulator drained" + 4 "radial operand
-// stored"), a_full (16), d_full (tcgen05.commit).  The pipeline is drained at unit boundaries.
-constexpr int kPpEpi = 512, kPpThreads = kPpEpi + 32, kPpKeys = 4;
-struct PpBars {
-  uint64_t d_full[2], a_full[2], u_ok[2];
-};
-__device__ __forceinline__ void pp_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-struct PpIssue {
-  int unit, j, T, stage;
-  uint32_t ph_a, ph_u;
-  bool done;
-};
-// next unit (from x.unit on) that has a tile for this slot (tile j of a unit lives in slot j & 1)
-__device__ __forceinline__ void pp_issue_seek(PpIssue& x, const EdgeTcArgs& g, int slot) {
-  for (;;) {
-    if (x.unit >= g.n_units) {
-      x.done = true;
-      return;
-    }
-    const int rep0 = x.unit * g.G, rep1 = min(g.R, rep0 + g.G);
-    const int ne = g.row_ptr[rep1 * g.N] - g.row_ptr[rep0 * g.N];
-    x.T = (ne + kTileE - 1) / kTileE;
-    if (x.T > slot) {
-      x.j = slot;
-      return;
-    }
-    x.unit += gridDim.x;
-  }
-}
-static size_t fwd_pp_smem(const Ctx* c) {
-  size_t b = kFwdWeights + 256 + 2 * (size_t)kTileE * kTileLd * 4 + kPpKeys * sizeof(TileKeys);
-  if (c->smem_tables) b += 2 * (size_t)c->G * c->N * kTabLd * 4;
-  return b + 1024 + 16;
-}
-
-template <bool SMEM_TABLES, int TERMS>
-__global__ void __launch_bounds__(kPpThreads, 1) edge_fwd_pp_kernel(EdgeTcArgs g) {
-  extern __shared__ uint8_t smraw[];
-  __shared__ PpBars bars;
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint64_t ibar;
-  uint32_t base = smem_u32(smraw);
-  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
-  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
-  float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars.d_full[i], 1);
-      mbar_init(&bars.a_full[i], 16);
-      mbar_init(&bars.u_ok[i], 20);
-    }
-    mbar_init(&ibar, 1);
-    bulk_copy_image(sm, g.img, kFwdWeights, &ibar);
-  }
-  if (tid < 64) sb2[tid] = g.b2[tid];
-  fence_proxy_async_smem();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  mbar_wait(&ibar, 0);
-  __syncwarp();
-  constexpr uint32_t ACC = 0, RH = 64, RL = 96, VH = 128, VL = 192;
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
-
-  if (warp == 16) {
-    // ===================================== MMA issuer =====================================
-    const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
-    PpIssue st[2];
-    for (int i = 0; i < 2; ++i) {
-      st[i] = PpIssue{(int)blockIdx.x, 0, 0, 0, 0u, 0u, false};
-      pp_issue_seek(st[i], g, i);
-    }
-    while (!(st[0].done && st[1].done)) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        PpIssue& x = st[i];
-        if (x.done) continue;
-        const uint32_t tm = tmem_slot + (uint32_t)i * 256u;
-        if (x.stage == 0) {
-          if (!mbar_test(&bars.u_ok[i], x.ph_u)) continue;
-          x.ph_u ^= 1u;
-          fence_after_sync();
-          if (elect_one()) {
-            issue_gemm_3xtf32<0, 3, TERMS>(tm + ACC, tm + RH, tm + RL, aWrH, aWrL, 64, idesc64, 0u);
-            mma_commit(&bars.d_full[i]);
-          }
-          __syncwarp();
-          x.stage = 1;
-        } else {
-          if (!mbar_test(&bars.a_full[i], x.ph_a)) continue;
-          x.ph_a ^= 1u;
-          fence_after_sync();
-          if (elect_one()) {
-            issue_gemm_3xtf32<0, 8, TERMS>(tm + ACC, tm + VH, tm + VL, aW2H, aW2L, 64, idesc64, 0u);
-            mma_commit(&bars.d_full[i]);
-          }
-          __syncwarp();
-          x.stage = 0;
-          x.j += 2;
-          if (x.j >= x.T) {
-            x.unit += gridDim.x;
-            pp_issue_seek(x, g, i);
-          }
-        }
-      }
-    }
-  } else {
-    // ===================================== epilogue warps =====================================
-    const int gt = tid, wq = warp & 3, cq = warp >> 2, row = 32 * wq + lane, col0 = 16 * cq;
-    uint8_t* gsm = sm + kFwdWeights + 256;
-    float* sZ = reinterpret_cast<float*>(gsm);                                   // two [128][68] tiles
-    TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + 2 * kTileE * kTileLd * 4);
-    float* sTab = reinterpret_cast<float*>(gsm + 2 * kTileE * kTileLd * 4 + kPpKeys * sizeof(TileKeys));
-    const uint32_t lane_base = tmem_slot + ((uint32_t)(32 * wq) << 16);
-    uint32_t ph_d = 0u;   // bit s = parity of d_full[s] this thread waits for next
-    int kidx = 0;   // key buffer of the current tile (kPpKeys buffers in rotation)
-
-    for (int unit = blockIdx.x; unit < g.n_units; unit += gridDim.x) {
-      const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
-      const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
-      const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
-      float* gA = g.a_out + (size_t)atom0 * 64;
-      const float *tQ, *gP;
-      int ld;
-      if (SMEM_TABLES) {
-        ld = kTabLd;
-        copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kPpEpi);
-        copy_rows_n(sTab + (size_t)g.unit_atoms * kTabLd, ld, g.P + (size_t)atom0 * 64, 64, natoms, gt, kPpEpi);
-        tQ = sTab;
-        gP = sTab + (size_t)g.unit_atoms * kTabLd;
-      } else {
-        ld = 64;
-        tQ = g.Q + (size_t)atom0 * 64;
-        gP = g.P + (size_t)atom0 * 64;
-      }
-      zero_rows_n(gA, 64, natoms, gt, kPpEpi);
-      if (e_begin >= e_end) {
-        pp_sync();
-        continue;
-      }
-      const int T = (e_end - e_begin + kTileE - 1) / kTileE;
-      // ---- prologue: keys of tile 0, radial operands of tiles 0 and 1, both accumulators declared free
-      uint32_t pr = 0u, pr_n = 0u;
-      bool valid = e_begin + row < e_end;
-      if (valid) pr = g.pair[e_begin + row];
-      if (e_begin + kTileE + row < e_end) pr_n = g.pair[e_begin + kTileE + row];
-      TileKeys* tk = keys + kidx;
-      if (cq == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
-      warp_arrive_i(&bars.u_ok[0], lane);
-      if (T > 1) warp_arrive_i(&bars.u_ok[1], lane);
-      if (cq == 0) {
-#pragma unroll 1
-        for (int i = 0; i < 2 && i < T; ++i) {
-          const int e = e_begin + i * kTileE + row;
-          const float r = e < e_end ? g.r_e[e] : 0.3f;
-          float o[32], od[32];
-          rbf_regs<false>(r, g.inv_cutoff, o, od);
-          st_split24<TERMS>(lane_base + 256u * i + RH, lane_base + 256u * i + RL, o);
-          tmem_st_wait();
-          warp_arrive_i(&bars.u_ok[i], lane);
-        }
-      }
-      pp_sync();   // tables, zeroed rows and keys of tile 0 visible
-
-      for (int j = 0; j < T; ++j) {
-        const int s = j & 1;
-        const int t0 = e_begin + j * kTileE;
-        const bool has_next = j + 1 < T;
-        const uint32_t tms = lane_base + 256u * (uint32_t)s, tmo = lane_base + 256u * (uint32_t)(s ^ 1);
-        const int tgc = valid ? (int)(pr >> 16) : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
-        if (warp == 4) {
-          const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
-          if (lane == 0) {
-            tk->n_seg_t = ns;
-            tk->cont_prev = (j > 0 && keys[(kidx + kPpKeys - 1) % kPpKeys].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
-          }
-        }
-        // ---- E1(j): v = silu(u + P[tgt] + Q[src]) -> TMEM
-        mbar_wait(&bars.d_full[s], (ph_d >> s) & 1u);
-        __syncwarp();
-        ph_d ^= 1u << s;
-        fence_after_sync();
-        {
-          uint32_t ur[16];
-          tmem_ld16(tms + ACC + col0, ur);
-          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * ld + col0);
-          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
-          float4 p[4], q[4];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            p[j4] = SMEM_TABLES ? pp[j4] : __ldg(pp + j4);
-            q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
-          }
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 y = silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
-            v[4 * j4 + 0] = y.x;
-            v[4 * j4 + 1] = y.y;
-            v[4 * j4 + 2] = y.z;
-            v[4 * j4 + 3] = y.w;
-          }
-          st_split16<TERMS>(tms + VH + col0, tms + VL + col0, v);
-        }
-        tmem_st_wait();
-        warp_arrive_i(&bars.a_full[s], lane);
-        // ---- look ahead: keys of tile j+1, edge data of tile j+2
-        TileKeys* tkn = keys + (kidx + 1) % kPpKeys;
-        bool valid_n = false;
-        uint32_t pr_nn = 0u;
-        float r2 = 0.3f;
-        if (has_next) {
-          valid_n = t0 + kTileE + row < e_end;
-          if (cq == 0) tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
-          if (t0 + 2 * kTileE + row < e_end) {
-            pr_nn = g.pair[t0 + 2 * kTileE + row];
-            if (cq == 0) r2 = g.r_e[t0 + 2 * kTileE + row];
-          }
-        }
-        // ---- E2(j-1): z = silu(w + b2) -> smem tile (j-1) & 1
-        if (j > 0) {
-          mbar_wait(&bars.d_full[s ^ 1], (ph_d >> (s ^ 1)) & 1u);
-          __syncwarp();
-          ph_d ^= 1u << (s ^ 1);
-          fence_after_sync();
-          uint32_t wr[16];
-          tmem_ld16(tmo + ACC + col0, wr);
-          tmem_ld_wait();
-          if (has_next) warp_arrive_i(&bars.u_ok[s ^ 1], lane);   // accumulator drained: u(j+1) may be issued
-          const float4* bb = reinterpret_cast<const float4*>(sb2 + col0);
-          float* zrow = sZ + (size_t)(s ^ 1) * kTileE * kTileLd + row * kTileLd + col0;
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = bb[j4];
-            const float4 z = silu4_sum2(&wr[4 * j4], b);
-            *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
-          }
-        }
-        pp_sync();   // tile j-1 complete in shared memory; keys of tile j+1 visible
-        // ---- a[tgt] += z(j-1) by the column quarters 1-3, radial operand of tile j+2 by column quarter 0
-        if (cq == 0) {
-          if (j + 2 < T) {
-            float o[32], od[32];
-            rbf_regs<false>(r2, g.inv_cutoff, o, od);
-            st_split24<TERMS>(tms + RH, tms + RL, o);   // u(j) was consumed before E1(j): the slot's operand columns are free
-            tmem_st_wait();
-            warp_arrive_i(&bars.u_ok[s], lane);
-          }
-        } else if (j > 0) {
-          reduce_targets_global_256<12>(sZ + (size_t)(s ^ 1) * kTileE * kTileLd, keys + (kidx + kPpKeys - 1) % kPpKeys, gA, gt - 128);
-        }
-        pr = pr_n;
-        valid = valid_n;
-        pr_n = pr_nn;
-        tk = tkn;
-        kidx = (kidx + 1) % kPpKeys;
-      }
-      // ---- drain: E2(T-1) and its reduction
-      {
-        const int s = (T - 1) & 1;
-        const uint32_t tms = lane_base + 256u * (uint32_t)s;
-        mbar_wait(&bars.d_full[s], (ph_d >> s) & 1u);
-        __syncwarp();
-        ph_d ^= 1u << s;
-        fence_after_sync();
-        uint32_t wr[16];
-        tmem_ld16(tms + ACC + col0, wr);
-        tmem_ld_wait();
-        const float4* bb = reinterpret_cast<const float4*>(sb2 + col0);
-        float* zrow = sZ + (size_t)s * kTileE * kTileLd + row * kTileLd + col0;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b = bb[j4];
-          const float4 z = silu4_sum2(&wr[4 * j4], b);
-          *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
-        }
-        pp_sync();
-        reduce_targets_global_256<16>(sZ + (size_t)s * kTileE * kTileLd, keys + (kidx + kPpKeys - 1) % kPpKeys, gA, gt);
-        fence_before_sync();
-        pp_sync();   // rows of the unit written, tile buffers and tables free
-      }
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_slot, 512);
-}
-
 // ---------------------------------------------------------------------------------------------- adjoint (ws)
 template <bool SMEM_TABLES, int TERMS>
 __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
@@ -1432,12 +1130,6 @@ static int launch_fwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint
   return 0;
 }
 template <bool T, int TERMS>
-static int launch_fwd_pp_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, cudaStream_t st) {
-  GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_pp_kernel<T, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_fwd_pp_kernel<T, TERMS><<<grid, kPpThreads, smem, st>>>(g);
-  return 0;
-}
-template <bool T, int TERMS>
 static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
   GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<T, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   edge_bwd_ws_kernel<T, TERMS><<<grid, kWsThreads, smem, st>>>(g, gb);
@@ -1447,16 +1139,6 @@ static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint
 // terms = 3: 3xTF32 (fp32-accurate, default); terms = 1: one TF32 product per contraction (GNNIS_FLAG_MLP_TF32X1)
 int launch_edge_fwd_ws(Ctx* c, int l, int terms, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
-  if (c->pp_mask & 1) {
-    const size_t smem = fwd_pp_smem(c);
-    const int grid = tc_grid(c);
-    int rc;
-    if (c->smem_tables) rc = terms == 1 ? launch_fwd_pp_t<true, 1>(c, g, grid, smem, st) : launch_fwd_pp_t<true, 3>(c, g, grid, smem, st);
-    else rc = terms == 1 ? launch_fwd_pp_t<false, 1>(c, g, grid, smem, st) : launch_fwd_pp_t<false, 3>(c, g, grid, smem, st);
-    if (rc) return rc;
-    GNNIS_LAUNCH_CHECK();
-    return 0;
-  }
   const size_t smem = fwd_tc_smem(c);
   const uint32_t gb = (uint32_t)group_bytes(c, 2);
   const int grid = tc_grid(c);
