@@ -55,6 +55,7 @@ struct StageTimer {
 
 template <typename T>
 static int dev_alloc(Ctx* c, T** p, size_t count) {
+  c->graph_gen++;   // a buffer moves: captured evaluations are stale
   if (*p) {
     cudaFree(*p);
     *p = nullptr;
@@ -139,8 +140,84 @@ static int check_ready(Ctx* c, bool need_weights) {
   return 0;
 }
 
+static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* force, uint32_t flags, cudaStream_t st,
+                               StageTimer* tm);
+
+static void graph_entry_clear(Ctx::GraphEntry& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  g = Ctx::GraphEntry();
+}
+
+// One evaluation.  The launches of an evaluation depend only on (positions / energy / force pointers, flags, the
+// minimiser's skip list, the handle state counted by graph_gen), so a combination seen for the second time is captured
+// into a CUDA graph (on the handle's own stream; nothing is enqueued by the capture) and from then on replayed with one
+// cudaGraphLaunch on the caller's stream: the ~2 us launch gaps between the 23 dependent kernels go away (0.23 -> 0.20 ms
+// at N = 13 x R = 128, 6.43 -> 6.38 ms at C2).  Calls inside a caller's own stream capture, profiling calls and
+// first sightings use plain stream launches.
 int energy_force_impl(Ctx* c, const float* pos, float* e_rep, float* force, uint32_t flags, cudaStream_t st,
                       StageTimer* tm) {
+  if (tm || !c->use_graphs) return energy_force_direct(c, pos, e_rep, force, flags, st, tm);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return energy_force_direct(c, pos, e_rep, force, flags, st, tm);
+  }
+  const uint64_t tick = ++c->graph_tick;
+  Ctx::GraphEntry* hit = nullptr;
+  Ctx::GraphEntry* victim = &c->gcache[0];
+  for (Ctx::GraphEntry& g : c->gcache) {
+    if (g.used && g.gen != c->graph_gen) graph_entry_clear(g);
+    if (g.used && g.pos == pos && g.e == e_rep && g.f == force && g.flags == flags && g.skip == c->skip_state) hit = &g;
+    if (!g.used || (victim->used && g.last_use < victim->last_use)) victim = &g;
+  }
+  if (!hit) {   // first sighting: remember the combination, launch directly
+    graph_entry_clear(*victim);
+    victim->used = true;
+    victim->pos = pos;
+    victim->e = e_rep;
+    victim->f = force;
+    victim->flags = flags;
+    victim->skip = c->skip_state;
+    victim->gen = c->graph_gen;
+    victim->last_use = tick;
+    return energy_force_direct(c, pos, e_rep, force, flags, st, tm);
+  }
+  hit->last_use = tick;
+  if (!hit->exec) {   // second sighting: capture
+    GNNIS_CUDA_OK(cudaSetDevice(c->device));
+    const int64_t l0 = c->launches;
+    if (cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      return energy_force_direct(c, pos, e_rep, force, flags, st, tm);
+    }
+    const int rc = energy_force_direct(c, pos, e_rep, force, flags, c->own_stream, nullptr);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ec = cudaStreamEndCapture(c->own_stream, &graph);
+    const int n_launch = (int)(c->launches - l0);
+    c->launches = l0;
+    if (rc || ec != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc) return rc;      // argument / state error: reported as without graphs
+      graph_entry_clear(*hit);
+      return energy_force_direct(c, pos, e_rep, force, flags, st, tm);
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&hit->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+      cudaGetLastError();
+      graph_entry_clear(*hit);
+      return energy_force_direct(c, pos, e_rep, force, flags, st, tm);
+    }
+    hit->launches = n_launch;
+  }
+  GNNIS_CUDA_OK(cudaGraphLaunch(hit->exec, st));
+  c->launches += hit->launches;
+  return 0;
+}
+
+static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* force, uint32_t flags, cudaStream_t st,
+                               StageTimer* tm) {
   const bool gb_only = flags & GNNIS_FLAG_GB_ONLY;
   const bool want_grad = !(flags & GNNIS_FLAG_NO_FORCES);
   if (flags & GNNIS_FLAG_VACUUM_ONLY) {
@@ -257,6 +334,7 @@ int gnnis_create(gnnis_handle* out, int device) {
     delete c;
     return -1;
   }
+  if (const char* e = getenv("GNNIS_GRAPHS")) c->use_graphs = atoi(e);   // debug: 0 = no CUDA-graph replay of evaluations
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;
@@ -267,6 +345,7 @@ int gnnis_destroy(gnnis_handle h) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  for (Ctx::GraphEntry& g : c->gcache) graph_entry_clear(g);
   dev_free(&c->wblob);
   dev_free(&c->img);
   float** f[] = {&c->q, &c->rho, &c->s, &c->alpha, &c->beta, &c->gamma, &c->d0, &c->m0, &c->pref, &c->r_e, &c->born,
@@ -327,6 +406,7 @@ const char* gnnis_last_error(gnnis_handle h) {
 
 int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (c) c->graph_gen++;
   if (!c || !w) return -1;
   if (w->hidden != kH || w->hidden_token != kT || w->n_rbf != kRbf || w->num_solvents < 1) {
     c->err = "unsupported architecture: this build is specialised for hidden=64, hidden_token=128, 20 RBFs "
@@ -453,6 +533,7 @@ int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w) {
 int gnnis_set_system(gnnis_handle h, int32_t n_atoms, const float* params7, const float* d0, const float* m0,
                      int32_t n_unique) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (c) c->graph_gen++;
   if (!c) return -1;
   if (n_atoms < 1 || !params7 || !d0 || !m0 || n_unique < 1) {
     c->err = "gnnis_set_system: bad arguments";
@@ -492,6 +573,7 @@ int gnnis_set_system(gnnis_handle h, int32_t n_atoms, const float* params7, cons
 
 int gnnis_set_replicas(gnnis_handle h, int32_t n_rep, const int32_t* solvent_id, const float* dielectric) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (c) c->graph_gen++;
   if (!c) return -1;
   if (n_rep < 1 || !solvent_id || !dielectric) {
     c->err = "gnnis_set_replicas: bad arguments";
@@ -517,6 +599,7 @@ int gnnis_set_replicas(gnnis_handle h, int32_t n_rep, const int32_t* solvent_id,
 
 int gnnis_set_model_constants(gnnis_handle h, float fraction, float scaling_factor, float cutoff) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (c) c->graph_gen++;
   if (!c) return -1;
   if (!(cutoff > 0.0f)) {
     c->err = "cutoff must be positive";

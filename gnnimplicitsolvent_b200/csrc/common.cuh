@@ -61,6 +61,23 @@ struct Ctx {
   int device = 0;
   std::string err;
   int64_t launches = 0;
+  // CUDA-graph cache of whole evaluations (api.cu): an evaluation whose buffers, flags and handle state have been seen
+  // before is replayed as one graph launch instead of 23 stream launches
+  struct GraphEntry {
+    const float* pos = nullptr;
+    float *e = nullptr, *f = nullptr;
+    uint32_t flags = 0;
+    const int* skip = nullptr;
+    uint64_t gen = 0, last_use = 0;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    bool used = false;
+  };
+  static constexpr int kGraphEntries = 8;
+  GraphEntry gcache[kGraphEntries];
+  uint64_t graph_gen = 1;    // bumped by every call that changes what an evaluation launches (setters, reallocation)
+  uint64_t graph_tick = 0;
+  int use_graphs = 1;        // GNNIS_GRAPHS=0: plain stream launches only
   int num_sms = 148;
   int tc_mask = 7;   // tcgen05 kernels in use: bit0 edge forward, bit1 edge adjoint, bit2 node MLPs (else fp32 CUDA cores)
   // model

@@ -530,6 +530,7 @@ extern "C" {
 
 int gnnis_set_bonds(gnnis_handle h, int32_t n_bonds, const int32_t* idx, const float* r0, const float* k) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (c) c->graph_gen++;
   if (!c) return -1;
   if (c->N <= 0) {
     c->err = "gnnis_set_bonds: call gnnis_set_system first";
@@ -557,6 +558,7 @@ int gnnis_set_bonds(gnnis_handle h, int32_t n_bonds, const int32_t* idx, const f
 
 int gnnis_set_constraints(gnnis_handle h, int32_t n_con, const int32_t* idx, const float* dist, float tolerance) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (c) c->graph_gen++;
   if (!c) return -1;
   if (c->N <= 0) {
     c->err = "gnnis_set_constraints: call gnnis_set_system first";

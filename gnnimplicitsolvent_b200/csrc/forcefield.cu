@@ -256,6 +256,7 @@ using namespace gnnis;
 
 extern "C" int gnnis_set_forcefield(gnnis_handle h, const gnnis_forcefield* ff) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (c) c->graph_gen++;
   if (!c) return -1;
   if (c->N <= 0) {
     c->err = "gnnis_set_forcefield: call gnnis_set_system first";

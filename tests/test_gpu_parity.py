@@ -174,6 +174,54 @@ def test_host_api_matches_device_api(weights):
     assert torch.equal(e.cpu(), e_h) and torch.equal(f.cpu(), f_h)
 
 
+def test_graph_replay_and_invalidation(weights, monkeypatch):
+    """Evaluations with recurring buffers are replayed from a CUDA graph inside the library: results must be bit-equal
+    to plain stream launches (GNNIS_GRAPHS=0), more buffer sets than cache entries must work, and every setter must
+    invalidate what was captured (here: other solvents / dielectrics, then another replica count)."""
+    from gnnimplicitsolvent_b200.engine import Engine
+    c = load_case("mixed_n21")
+    R = c["pos"].shape[0]
+    monkeypatch.setenv("GNNIS_GRAPHS", "0")
+    plain = Engine(c["params"], weights, device=0)
+    monkeypatch.setenv("GNNIS_GRAPHS", "1")
+    eng = Engine(c["params"], weights, device=0)
+    for e_ in (plain, eng):
+        e_.set_replicas(R, c["solvent_ids"], c["dielectrics"])
+    g = torch.Generator().manual_seed(11)
+    sets = [(torch.from_numpy(c["pos"]) + 0.001 * k * torch.randn(c["pos"].shape, generator=g)).float().cuda() for k in range(11)]
+    outs = [(torch.empty(R, device="cuda"), torch.empty(c["pos"].shape, device="cuda")) for _ in sets]
+    for rnd in range(4):                       # round 0: first sighting, round 1: capture, rounds 2-3: replay
+        for k, p in enumerate(sets):           # 11 buffer sets > 8 cache entries: least-recently-used replacement
+            eng.energy_force(p, out_energy=outs[k][0], out_force=outs[k][1])
+            e_ref, f_ref = plain.energy_force(p)
+            assert torch.equal(outs[k][0], e_ref) and torch.equal(outs[k][1], f_ref), (rnd, k)
+    for rnd in range(3):                       # three buffer sets only: these are replayed
+        for k in range(3):
+            outs[k][0].zero_()
+            eng.energy_force(sets[k], out_energy=outs[k][0], out_force=outs[k][1])
+            e_ref, f_ref = plain.energy_force(sets[k])
+            assert torch.equal(outs[k][0], e_ref) and torch.equal(outs[k][1], f_ref)
+    # same buffers, new per-replica solvents: the captured graph must not be reused
+    sid2 = [(int(x) + 5) % 39 for x in c["solvent_ids"]]
+    die2 = [float(x) * 0.5 + 2.0 for x in c["dielectrics"]]
+    for e_ in (plain, eng):
+        e_.set_replicas(R, sid2, die2)
+    for rnd in range(3):
+        eng.energy_force(sets[0], out_energy=outs[0][0], out_force=outs[0][1])
+        e_ref, f_ref = plain.energy_force(sets[0])
+        assert torch.equal(outs[0][0], e_ref) and torch.equal(outs[0][1], f_ref)
+    # fewer replicas through the same buffers
+    R2 = R - 1
+    for e_ in (plain, eng):
+        e_.set_replicas(R2, sid2[:R2], die2[:R2])
+    p2 = sets[0][:R2].contiguous()
+    for rnd in range(3):
+        e2, f2 = torch.empty(R2, device="cuda"), torch.empty(R2, *c["pos"].shape[1:], device="cuda")
+        eng.energy_force(p2, out_energy=e2, out_force=f2)
+        e_ref, f_ref = plain.energy_force(p2)
+        assert torch.equal(e2, e_ref) and torch.equal(f2, f_ref)
+
+
 def test_pipelined_host_api(weights):
     """submit / wait: results of a stream of batches equal the blocking host call bit for bit, arrive in submission
     order, a third submission in flight is refused (-4) and a wait with nothing in flight is refused."""
