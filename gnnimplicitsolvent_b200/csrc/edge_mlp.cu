@@ -586,9 +586,16 @@ __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, in
       for (int c = 0; c < 4; ++c) {
         const bool valid = key[c] >= 0;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
+        // lanes with the same 7-bit key, from one ballot per key bit (MATCH.ANY costs ~130 cycles per call and SM here:
+        // the kernel spent 90 us of a C2 evaluation waiting for it)
+        unsigned peers = act;
+#pragma unroll
+        for (int b = 0; b < 7; ++b) {
+          const unsigned m = __ballot_sync(0xffffffffu, (key[c] >> b) & 1);
+          peers &= ((key[c] >> b) & 1) ? m : ~m;
+        }
         in_bin[c] = 0;
         if (valid) {
-          const unsigned peers = __match_any_sync(act, key[c]);
           const int leader = __ffs(peers) - 1;
           int base = 0;
           if (lane == leader) {
