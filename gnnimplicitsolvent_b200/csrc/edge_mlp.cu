@@ -559,7 +559,7 @@ static EdgeArgs make_args(Ctx* c, int l) {
 
 // Same permutation by a counting sort over the (<= 128) unit-local source indices.  One WARP per tile (no block
 // barriers; the warps of a CTA share a unit and take its tiles round-robin): the warp walks its rows 32 at a time in
-// order, __match_any_sync groups equal sources, so the rank inside a bin follows the edge order; the bins live in
+// order, lanes with equal sources are grouped (ballots), so the rank inside a bin follows the edge order; the bins live in
 // the warp's own shared-memory slice.
 __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, int G, int N, int R,
                                                                  const int* __restrict__ row_ptr,
