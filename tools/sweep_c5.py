@@ -1,5 +1,10 @@
 """C5-style sweep: atoms x replicas -> ms per evaluation, atoms*evals/s, parity vs the CPU oracle
-on the first replicas.  One GPU."""
+on the first replicas.  One GPU, or under torchrun: the R replicas of every point are sharded over the ranks
+(contiguous blocks, sharding.shard_bounds), time = max over ranks, rank 0 prints.
+
+    python tools/sweep_c5.py
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep_c5.py
+"""
 import json
 import os
 import sys
@@ -9,10 +14,18 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from gnnimplicitsolvent_b200 import synth  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from gnnimplicitsolvent_b200 import sharding, synth  # noqa: E402
 from gnnimplicitsolvent_b200.engine import Engine  # noqa: E402
 from oracle import gnn_oracle as O  # noqa: E402
 
+rank = int(os.environ.get("RANK", 0))
+world = int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 z = np.load(os.path.join(ROOT, "tests", "golden", "gnn_weights.npz"))
 sd = {k: torch.from_numpy(z[k]) for k in z.files}
 rows = []
@@ -21,10 +34,14 @@ for N in (10, 20, 50, 100, 200):
     for R in (64, 1024, 4096, 16384):
         if N * R > 1_700_000:
             continue
-        pos = synth.conformers(mol["pos"], R, 0.01, seed=N + R)
-        sids = [r % 39 for r in range(R)]
+        R_total = R
+        pos_all = synth.conformers(mol["pos"], R_total, 0.01, seed=N + R_total)
+        lo, hi = sharding.shard_bounds(R_total, world, rank)
+        R = hi - lo
+        pos = np.ascontiguousarray(pos_all[lo:hi])
+        sids = [r % 39 for r in range(lo, hi)]
         diel = [synth.SOLVENT_DIELECTRICS[s] for s in sids]
-        eng = Engine(mol["params"], sd)
+        eng = Engine(mol["params"], sd, device=local)
         eng.set_replicas(R, sids, diel)
         p = torch.from_numpy(pos).cuda()
         e = torch.empty(R, device="cuda")
@@ -32,6 +49,8 @@ for N in (10, 20, 50, 100, 200):
         for _ in range(3):
             eng.energy_force(p, out_energy=e, out_force=f)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         n_it = 10
         ev[0].record()
@@ -40,14 +59,25 @@ for N in (10, 20, 50, 100, 200):
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / n_it
-        k = min(R, 4 if N >= 100 else 8)
-        o = O.evaluate(mol["params"], pos[:k], sids[:k], diel[:k], sd)
-        e_err = float(((e[:k].cpu() - o["energy_rep"]).abs() / o["energy_rep"].abs()).max())
-        f_err = float(((f[:k].cpu() - o["forces"]) ** 2).sum().sqrt() / (o["forces"] ** 2).sum().sqrt())
-        rows.append({"atoms": N, "replicas": R, "edges": eng.last_edge_count(), "ms_per_eval": ms,
-                     "atoms_evals_per_s": N * R / (ms * 1e-3), "energy_max_rel": e_err, "force_rel_rms": f_err})
-        print(json.dumps(rows[-1]), flush=True)
+        n_edges = eng.last_edge_count()
+        if world > 1:
+            t = torch.tensor([ms, float(n_edges)], dtype=torch.float64, device="cuda")
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, n_edges = float(tmax[0]), int(t[1])
+        e_err = f_err = None
+        if rank == 0:      # parity of this rank's first replicas against the CPU oracle
+            k = min(R, 4 if N >= 100 else 8)
+            o = O.evaluate(mol["params"], pos[:k], sids[:k], diel[:k], sd)
+            e_err = float(((e[:k].cpu() - o["energy_rep"]).abs() / o["energy_rep"].abs()).max())
+            f_err = float(((f[:k].cpu() - o["forces"]) ** 2).sum().sqrt() / (o["forces"] ** 2).sum().sqrt())
+        rows.append({"atoms": N, "replicas": R_total, "gpus": world, "edges": n_edges, "ms_per_eval": ms,
+                     "atoms_evals_per_s": N * R_total / (ms * 1e-3), "energy_max_rel": e_err, "force_rel_rms": f_err})
+        if rank == 0:
+            print(json.dumps(rows[-1]), flush=True)
         eng.close()
         del p, e, f
         torch.cuda.empty_cache()
-print(json.dumps({"sweep": rows}))
+if world > 1:
+    dist.destroy_process_group()
