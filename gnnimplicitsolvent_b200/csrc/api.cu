@@ -90,6 +90,16 @@ static int ensure_workspace(Ctx* c) {
     c->smem_tables = false;
   }
   c->n_units = (c->R + c->G - 1) / c->G;
+  // sub-units per replica for small batches (Ctx::split): enough to give every warp group (2 per SM) a unit, at least
+  // ~6 target atoms (one to two edge tiles) per part, at most split_max parts
+  c->split = 1;
+  if (c->G == 1) {
+    const int groups = 2 * (c->num_sms > 0 ? c->num_sms : 148);
+    int s_ = groups / c->R;
+    if (s_ > c->N / 6) s_ = c->N / 6;
+    if (s_ > c->split_max) s_ = c->split_max;
+    if (s_ > 1) c->split = s_;
+  }
   size_t n = (size_t)c->R * c->N;
   int64_t cap = (int64_t)n * (c->N - 1);
   if (cap > 2147483000LL) {
@@ -97,7 +107,7 @@ static int ensure_workspace(Ctx* c) {
     return -1;
   }
   if (cap < 1) cap = 1;
-  if (n == c->ws_atoms && cap == c->edge_cap) return 0;
+  if (n == c->ws_atoms && cap == c->edge_cap && c->split <= c->ws_split) return 0;
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   int nblk = (int)((n + kPairThreads - 1) / kPairThreads);
   if (dev_alloc(c, &c->deg, n) || dev_alloc(c, &c->row_ptr, n + 1) || dev_alloc(c, &c->blk_sum, (size_t)nblk + 1) ||
@@ -112,7 +122,7 @@ static int ensure_workspace(Ctx* c) {
       return -1;
   }
   if (dev_alloc(c, &c->gbar, n * 128)) return -1;
-  if (dev_alloc(c, &c->abar, n * 64) || dev_alloc(c, &c->Pbar, n * 64) || dev_alloc(c, &c->Qbar, n * 64) ||
+  if (dev_alloc(c, &c->abar, n * 64) || dev_alloc(c, &c->Pbar, n * 64) || dev_alloc(c, &c->Qbar, n * 64 * (size_t)c->split) ||
       dev_alloc(c, &c->rbar, n * (size_t)c->N))
     return -1;
   if (dev_alloc(c, &c->h_pos_dev, n * 3) || dev_alloc(c, &c->h_f_dev, n * 3) || dev_alloc(c, &c->h_e_dev, (size_t)c->R))
@@ -120,6 +130,7 @@ static int ensure_workspace(Ctx* c) {
   if (!c->n_edges_dev && dev_alloc(c, &c->n_edges_dev, 1)) return -1;
   GNNIS_CUDA_OK(cudaMemset(c->sa_atom, 0, n * sizeof(float)));
   c->ws_atoms = n;
+  c->ws_split = c->split;
   c->edge_cap = cap;
   return 0;
 }
@@ -252,6 +263,7 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
   const bool tc_ok = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && tc_path_fits(c);
   const bool tc_fwd = tc_ok && (c->tc_mask & 1), tc_bwd = tc_ok && (c->tc_mask & 2);
   const bool node_tc = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && (c->tc_mask & 4);
+  c->split_eff = (tc_fwd && tc_bwd && c->G == 1) ? c->split : 1;   // the CUDA-core edge kernels do not split replicas
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
   if (tm) tm->mark(kStNeighborBorn);
@@ -335,6 +347,7 @@ int gnnis_create(gnnis_handle* out, int device) {
     return -1;
   }
   if (const char* e = getenv("GNNIS_GRAPHS")) c->use_graphs = atoi(e);   // debug: 0 = no CUDA-graph replay of evaluations
+  if (const char* e = getenv("GNNIS_SPLIT")) c->split_max = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;

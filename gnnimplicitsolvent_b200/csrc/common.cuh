@@ -107,8 +107,16 @@ struct Ctx {
   int G = 1;          // replicas per unit
   int n_units = 0;
   bool smem_tables = true;
+  // Small batches: with one replica per unit and fewer units than warp groups (2 per SM), a replica is split into
+  // `split` sub-units = disjoint ranges of TARGET atoms (each with its own run of CSR rows / tiles), so that the serial
+  // tile chain of a warp group is `split` times shorter.  Target-side results (a, Pbar, rbar) are disjoint; the
+  // source-side adjoint Qbar is produced as `split` partial tables that sum_qbar_parts_kernel adds in fixed order.
+  int split_max = 16;   // GNNIS_SPLIT=1 disables the split (debug / A-B)
+  int split = 1;        // chosen by gnnis_set_replicas
+  int split_eff = 1;    // used by the current evaluation (1 unless all edge kernels run on the tensor-core path)
   // workspace (sized for R*N atoms, edge capacity grows on demand)
   size_t ws_atoms = 0;
+  int ws_split = 0;   // split the workspace (Qbar parts) was sized for
   int64_t edge_cap = 0;
   int *deg = nullptr, *row_ptr = nullptr, *blk_sum = nullptr, *col = nullptr;
   uint32_t* pair = nullptr;
@@ -167,6 +175,31 @@ struct Ctx {
   int2* cl_con = nullptr;
   float* cl_con_d = nullptr;
 };
+
+// Rows of the node tables a unit needs ([atom_base, atom_base + n_tab) of the flat atom index) and the unit-local target
+// range [a0, a1) it owns; S > 1 only with one replica per unit (see Ctx::split).
+struct UnitSpan {
+  int atom_base, n_tab, a0, a1, part;
+};
+__device__ __forceinline__ UnitSpan unit_span(int unit, int G, int N, int R, int S) {
+  UnitSpan u;
+  if (S <= 1) {
+    const int rep0 = unit * G, rep1 = min(R, rep0 + G);
+    u.atom_base = rep0 * N;
+    u.n_tab = (rep1 - rep0) * N;
+    u.a0 = 0;
+    u.a1 = u.n_tab;
+    u.part = 0;
+  } else {
+    const int rep = unit / S;
+    u.part = unit - rep * S;
+    u.atom_base = rep * N;
+    u.n_tab = N;
+    u.a0 = (u.part * N) / S;
+    u.a1 = ((u.part + 1) * N) / S;
+  }
+  return u;
+}
 
 #define GNNIS_CUDA_OK(call)                                                                   \
   do {                                                                                        \

@@ -59,6 +59,8 @@ struct EdgeTcArgs {
   int rbar_accumulate;
   const uint8_t* perm;
   int unit_atoms;
+  int S;                  // sub-units per replica (Ctx::split_eff)
+  size_t qbar_stride;     // floats between the partial Qbar tables of consecutive parts
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
@@ -292,7 +294,9 @@ static size_t bwd_tc_smem(const Ctx* c) { return kBwdWeights + 256 + kGroups * g
 // ---------------------------------------------------------------------------------------------- launchers
 static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   EdgeTcArgs g{};
-  g.n_units = c->n_units;
+  g.n_units = c->n_units * c->split_eff;
+  g.S = c->split_eff;
+  g.qbar_stride = (size_t)c->R * c->N * 64;
   g.G = c->G;
   g.N = c->N;
   g.R = c->R;
@@ -329,7 +333,10 @@ bool tc_path_fits(const Ctx* c) { return fwd_tc_smem(c) <= 227 * 1024 && bwd_tc_
 
 // Units are dealt out CTA-first (unit u -> CTA u % grid, group (u / grid) % 2), so that with fewer units than
 // 2 x #SM every unit gets an SM of its own before any SM runs two groups.
-static int tc_grid(const Ctx* c) { return c->n_units < c->num_sms ? c->n_units : c->num_sms; }
+static int tc_grid(const Ctx* c) {
+  const int nu = c->n_units * c->split_eff;
+  return nu < c->num_sms ? nu : c->num_sms;
+}
 
 // ================================================================================================================
 // 16-warp variant (default): 2 groups x 8 warps per CTA, no group-wide barrier on the MMA hand-off.
@@ -539,8 +546,8 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
       x.done = true;
       return;
     }
-    const int rep0 = x.unit * g.G, rep1 = min(g.R, rep0 + g.G);
-    const int e_begin = g.row_ptr[rep0 * g.N], e_end = g.row_ptr[rep1 * g.N];
+    const UnitSpan us = unit_span(x.unit, g.G, g.N, g.R, g.S);
+    const int e_begin = g.row_ptr[us.atom_base + us.a0], e_end = g.row_ptr[us.atom_base + us.a1];
     if (e_begin < e_end) {
       x.t0 = e_begin;
       x.e_end = e_end;
@@ -645,9 +652,9 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
-      const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
-      const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
-      const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
+      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, g.S);
+      const int atom0 = us.atom_base, natoms = us.n_tab;
+      const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
       float* gA = g.a_out + (size_t)atom0 * 64;
       const float *tQ, *gP;   // gP: the P rows of the unit (shared-memory copy when the tables fit)
       int ld;
@@ -662,7 +669,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         tQ = g.Q + (size_t)atom0 * 64;
         gP = g.P + (size_t)atom0 * 64;
       }
-      zero_rows_n(gA, 64, natoms, gt, kWsGroupThreads);
+      zero_rows_n(gA + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
       if (e_begin >= e_end) {
         ws_group_sync(grp);
         continue;
@@ -868,12 +875,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
-      const int rep0 = unit * g.G, rep1 = min(g.R, rep0 + g.G);
-      const int atom0 = rep0 * g.N, natoms = (rep1 - rep0) * g.N;
-      const int e_begin = g.row_ptr[atom0], e_end = g.row_ptr[atom0 + natoms];
+      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, g.S);
+      const int atom0 = us.atom_base, natoms = us.n_tab;
+      const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
       const float* gP = g.P + (size_t)atom0 * 64;
       const float* gAb = g.abar + (size_t)atom0 * 64;
       float* gPb = g.Pbar + (size_t)atom0 * 64;
+      float* gQb = g.Qbar + (size_t)us.part * g.qbar_stride + (size_t)atom0 * 64;   // this part's (partial) Qbar rows
       const float* tQ;
       float* tQb;
       int ld;
@@ -885,14 +893,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       } else {
         ld = 64;
         tQ = g.Q + (size_t)atom0 * 64;
-        tQb = g.Qbar + (size_t)atom0 * 64;
+        tQb = gQb;
       }
-      zero_rows_n(gPb, 64, natoms, gt, kWsGroupThreads);
+      zero_rows_n(gPb + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
       zero_rows_n(tQb, ld, natoms, gt, kWsGroupThreads);
       if (e_begin >= e_end) {
         ws_group_sync(grp);
         if (SMEM_TABLES) {
-          copy_rows_n(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt, kWsGroupThreads);
+          copy_rows_n(gQb, 64, tQb, ld, natoms, gt, kWsGroupThreads);
           ws_group_sync(grp);
         }
         continue;
@@ -1113,7 +1121,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       reduce_sources_table_256(sU, keys + (kidx + 2) % 3, tQb, ld, gt);
       ws_group_sync(grp);
       if (SMEM_TABLES) {
-        copy_rows_n(g.Qbar + (size_t)atom0 * 64, 64, tQb, ld, natoms, gt, kWsGroupThreads);
+        copy_rows_n(gQb, 64, tQb, ld, natoms, gt, kWsGroupThreads);
         ws_group_sync(grp);
       }
     }
@@ -1121,6 +1129,21 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
+// Qbar = sum over the parts of a split replica, in part order (deterministic)
+__global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t n4, size_t stride4, int S) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = qbar[i];
+    for (int p = 1; p < S; ++p) {
+      const float4 b = qbar[i + (size_t)p * stride4];
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    qbar[i] = a;
+  }
 }
 
 template <bool T, int TERMS>
@@ -1161,6 +1184,12 @@ int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, cudaStream
   else rc = terms == 1 ? launch_bwd_t<false, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<false, 3>(c, g, grid, smem, gb, st);
   if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
+  if (c->split_eff > 1) {
+    const size_t n4 = (size_t)c->R * c->N * 16;
+    const int blocks = (int)((n4 + 255) / 256 < 4 * (size_t)c->num_sms ? (n4 + 255) / 256 : 4 * (size_t)c->num_sms);
+    sum_qbar_parts_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(c->Qbar), n4, n4, c->split_eff);
+    GNNIS_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -1,0 +1,67 @@
+"""Small batches: a replica is split into sub-units (disjoint ranges of target atoms, Ctx::split) so that its edge
+tiles are spread over several warp groups.  Checked against the CPU oracle and against the unsplit evaluation
+(GNNIS_SPLIT=1) of the same inputs; the partial Qbar tables are summed in a fixed order, so results are reproducible
+bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_rms
+
+pytestmark = pytest.mark.gpu
+E_RTOL, F_RRMS = 1e-4, 1e-3
+
+
+def _run(params, sd, pos, sids, diel, monkeypatch, split):
+    from gnnimplicitsolvent_b200.engine import Engine
+    if split is None:
+        monkeypatch.delenv("GNNIS_SPLIT", raising=False)
+    else:
+        monkeypatch.setenv("GNNIS_SPLIT", str(split))
+    eng = Engine(params, sd)
+    eng.set_replicas(pos.shape[0], sids, diel)
+    p = torch.from_numpy(pos).cuda()
+    e, f = eng.energy_force(p)
+    e2, f2 = eng.energy_force(p)
+    assert torch.equal(e, e2) and torch.equal(f, f2)          # deterministic
+    edges = eng.last_edge_count()
+    eng.close()
+    return e.cpu().numpy(), f.cpu().numpy(), edges
+
+
+@pytest.mark.parametrize("N,R", [(50, 1), (37, 3), (100, 2), (200, 1), (24, 5)])
+def test_split_vs_oracle_and_unsplit(N, R, monkeypatch):
+    from gnnimplicitsolvent_b200 import synth
+    from oracle import gnn_oracle as O
+    mol = synth.synth_molecule(N, seed=N + 1)
+    sd = O.random_state_dict(seed=N)
+    pos = synth.conformers(mol["pos"], R, 0.02, seed=R).astype(np.float32)
+    sids = [(3 * r + 1) % 39 for r in range(R)]
+    diel = [synth.SOLVENT_DIELECTRICS[s] for s in sids]
+    o = O.evaluate(mol["params"], pos, sids, diel, sd)
+    e1, f1, n1 = _run(mol["params"], sd, pos, sids, diel, monkeypatch, 1)
+    for split in (None, 2, 16):
+        e, f, n = _run(mol["params"], sd, pos, sids, diel, monkeypatch, split)
+        assert n == n1
+        np.testing.assert_allclose(e, o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
+        assert rel_rms(f, o["forces"].numpy()) < F_RRMS
+        np.testing.assert_allclose(e, e1, rtol=2e-6, atol=1e-4)      # only the summation order differs
+        assert rel_rms(f, f1) < 2e-5
+
+
+def test_split_with_parts_without_edges(monkeypatch):
+    """The first half of the atoms forms a normal molecule, the second half is a line of isolated atoms: whole parts
+    of the split replica have no GNN edge (empty sub-units next to dense ones)."""
+    from gnnimplicitsolvent_b200 import synth
+    from oracle import gnn_oracle as O
+    N = 48
+    mol = synth.synth_molecule(N, seed=9)
+    sd = O.random_state_dict(seed=9)
+    pos0 = mol["pos"].astype(np.float32).copy()
+    pos0[N // 2:] = np.array([[3.0 + 0.9 * i, 0.1 * (i % 2), -2.0] for i in range(N - N // 2)], np.float32)
+    pos = np.stack([pos0, pos0 + 0.01]).astype(np.float32)
+    o = O.evaluate(mol["params"], pos, [0, 5], [78.5, 24.85], sd)
+    for split in (1, None, 16):
+        e, f, n = _run(mol["params"], sd, pos, [0, 5], [78.5, 24.85], monkeypatch, split)
+        np.testing.assert_allclose(e, o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
+        assert rel_rms(f, o["forces"].numpy()) < F_RRMS
