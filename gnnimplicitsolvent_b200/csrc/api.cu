@@ -20,6 +20,7 @@ int launch_edge_fwd_ws(Ctx*, int, int, cudaStream_t);
 int launch_edge_bwd_ws(Ctx*, int, int, int, cudaStream_t);
 int launch_umma_selftest(Ctx*, const float*, const float*, float*, int, int, cudaStream_t);
 bool tc_path_fits(const Ctx*);
+int tc_table_mode(const Ctx*);
 int launch_edge_bwd(Ctx*, int, int, cudaStream_t);
 int launch_node_pre1(Ctx*, cudaStream_t);
 int launch_node_fwd(Ctx*, int, cudaStream_t);
@@ -85,9 +86,11 @@ static int ensure_workspace(Ctx* c) {
     if (c->G > spread) c->G = spread;
     if (c->G < 1) c->G = 1;
     c->smem_tables = true;
+    c->tab_mode = 2;
   } else {
     c->G = 1;
     c->smem_tables = false;
+    c->tab_mode = tc_table_mode(c);   // up to ~128 atoms one table per kernel still fits (forward Q, adjoint Qbar)
   }
   c->n_units = (c->R + c->G - 1) / c->G;
   // sub-units per replica for small batches (Ctx::split): as many as it takes to give every warp group (2 per SM) a

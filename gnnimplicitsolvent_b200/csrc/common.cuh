@@ -106,7 +106,8 @@ struct Ctx {
   // units
   int G = 1;          // replicas per unit
   int n_units = 0;
-  bool smem_tables = true;
+  bool smem_tables = true;   // CUDA-core edge kernels: node tables of the unit in shared memory
+  int tab_mode = 2;          // tensor-core edge kernels: 2 = both tables in shared memory, 1 = one (forward Q, adjoint Qbar), 0 = none
   // Small batches: with one replica per unit and fewer units than warp groups (2 per SM), a replica is split into
   // `split` sub-units = disjoint ranges of TARGET atoms (each with its own run of CSR rows / tiles), so that the serial
   // tile chain of a warp group is `split` times shorter.  Target-side results (a, Pbar, rbar) are disjoint; the

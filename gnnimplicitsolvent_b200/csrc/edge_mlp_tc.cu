@@ -283,13 +283,21 @@ constexpr uint32_t kGrpKeys = kGrpX + kTileE * kTileLd * 4;
 constexpr uint32_t kGrpTab = kGrpKeys + 3 * (uint32_t)sizeof(TileKeys);   // ws kernels rotate three key buffers
 static_assert(sizeof(TileKeys) % 16 == 0, "TileKeys must keep the tables 16-byte aligned");
 
-static size_t group_bytes(const Ctx* c, int ntables) {
-  size_t b = kGrpTab;
-  if (c->smem_tables) b += (size_t)ntables * c->G * c->N * kTabLd * 4;
+// shared-memory tables per group (Ctx::tab_mode): 2 = both tables of the kernel (forward Q, P; adjoint Q, Qbar),
+// 1 = one (forward Q; adjoint Qbar) with the other rows gathered from global memory / L1, 0 = none
+static size_t group_bytes_mode(const Ctx* c, int mode) {
+  size_t b = kGrpTab + (size_t)mode * c->G * c->N * kTabLd * 4;
   return (b + 15) / 16 * 16;
 }
-static size_t fwd_tc_smem(const Ctx* c) { return kFwdWeights + 256 + kGroups * group_bytes(c, 2) + 1024; }
-static size_t bwd_tc_smem(const Ctx* c) { return kBwdWeights + 256 + kGroups * group_bytes(c, 2) + 1024; }
+static size_t group_bytes(const Ctx* c) { return group_bytes_mode(c, c->tab_mode); }
+static size_t fwd_tc_smem(const Ctx* c) { return kFwdWeights + 256 + kGroups * group_bytes(c) + 1024; }
+static size_t bwd_tc_smem(const Ctx* c) { return kBwdWeights + 256 + kGroups * group_bytes(c) + 1024; }
+// largest table mode whose adjoint kernel (the bigger one) fits into 227 KB
+int tc_table_mode(const Ctx* c) {
+  for (int mode = 2; mode >= 1; --mode)
+    if (kBwdWeights + 256 + kGroups * group_bytes_mode(c, mode) + 1024 + 2048 <= 227 * 1024) return mode;   // 2 KB: static smem
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------- launchers
 static EdgeTcArgs make_tc_args(Ctx* c, int l) {
@@ -540,13 +548,14 @@ struct IssueState {
   uint32_t ph_a, ph_u, cur;
   bool done;
 };
+template <bool SPLIT>
 __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs& g) {
   for (;;) {
     if (x.unit >= g.n_units) {
       x.done = true;
       return;
     }
-    const UnitSpan us = unit_span(x.unit, g.G, g.N, g.R, g.S);
+    const UnitSpan us = unit_span(x.unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
     const int e_begin = g.row_ptr[us.atom_base + us.a0], e_end = g.row_ptr[us.atom_base + us.a1];
     if (e_begin < e_end) {
       x.t0 = e_begin;
@@ -558,8 +567,9 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
 }
 
 // ---------------------------------------------------------------------------------------------- forward (ws, dedicated issuer warp)
-template <bool SMEM_TABLES, int TERMS>
+template <int TAB, int TERMS, bool SPLIT>
 __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+  constexpr bool Q_SM = TAB >= 1, P_SM = TAB == 2;   // which node tables of the unit live in shared memory
   extern __shared__ uint8_t smraw[];
   __shared__ WsiBars bars;
   __shared__ uint32_t tmem_slot;
@@ -600,7 +610,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       IssueState st[kGroups];
       for (int i = 0; i < kGroups; ++i) {
         st[i] = IssueState{(int)blockIdx.x + i * (int)gridDim.x, 0, 0, 0, 0u, 0u, 0u, false};
-        issue_next_unit(st[i], g);
+        issue_next_unit<SPLIT>(st[i], g);
       }
       while (!(st[0].done && st[1].done)) {
 #pragma unroll
@@ -632,7 +642,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             x.t0 += kTileE;
             if (x.t0 >= x.e_end) {
               x.unit += gridDim.x * kGroups;
-              issue_next_unit(x, g);
+              issue_next_unit<SPLIT>(x, g);
             }
           }
         }
@@ -652,24 +662,26 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
-      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, g.S);
+      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
       const int atom0 = us.atom_base, natoms = us.n_tab;
       const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
       float* gA = g.a_out + (size_t)atom0 * 64;
       const float *tQ, *gP;   // gP: the P rows of the unit (shared-memory copy when the tables fit)
-      int ld;
-      if (SMEM_TABLES) {
-        ld = kTabLd;
-        copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
-        copy_rows_n(sTab + (size_t)g.unit_atoms * kTabLd, ld, g.P + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
+      constexpr int ldq = Q_SM ? kTabLd : 64, ldp = P_SM ? kTabLd : 64;
+      if (Q_SM) {
+        copy_rows_n(sTab, kTabLd, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
         tQ = sTab;
+      } else {
+        tQ = g.Q + (size_t)atom0 * 64;
+      }
+      if (P_SM) {
+        copy_rows_n(sTab + (size_t)g.unit_atoms * kTabLd, kTabLd, g.P + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
         gP = sTab + (size_t)g.unit_atoms * kTabLd;
       } else {
-        ld = 64;
-        tQ = g.Q + (size_t)atom0 * 64;
         gP = g.P + (size_t)atom0 * 64;
       }
-      zero_rows_n(gA + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
+      if (SPLIT) zero_rows_n(gA + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
+      else zero_rows_n(gA, 64, natoms, gt, kWsGroupThreads);
       if (e_begin >= e_end) {
         ws_group_sync(grp);
         continue;
@@ -688,7 +700,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       }
       TileKeys* tk = keys + kidx;
       if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
-      if (!SMEM_TABLES) prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
+      if (!P_SM) prefetch_l1(gP + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
       warp_arrive_i(u_ok, lane);                       // accumulators are free
       if (ch == 0) {
         float o[32], od[32];
@@ -719,13 +731,13 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           const int col0 = 32 * ch + 16 * c;
           uint32_t ur[16];
           tmem_ld16(lane_addr + cur + col0, ur);
-          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * ld + col0);
-          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
+          const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * ldp + col0);
+          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ldq + col0);
           float4 p[4], q[4];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            p[j4] = SMEM_TABLES ? pp[j4] : __ldg(pp + j4);
-            q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+            p[j4] = P_SM ? pp[j4] : __ldg(pp + j4);
+            q[j4] = Q_SM ? qq[j4] : __ldg(qq + j4);
           }
           tmem_ld_wait();
           float v[16];
@@ -749,7 +761,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         if (has_next) {
           valid_n = t0 + kTileE + row < e_end;
           if (ch == 0) tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
-          if (!SMEM_TABLES) prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
+          if (!P_SM) prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
           if (t0 + 2 * kTileE + row < e_end) {
             pr_nn = g.pair[t0 + 2 * kTileE + row];
             if (ch == 0) r_nn = g.r_e[t0 + 2 * kTileE + row];
@@ -807,8 +819,9 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 }
 
 // ---------------------------------------------------------------------------------------------- adjoint (ws)
-template <bool SMEM_TABLES, int TERMS>
+template <int TAB, int TERMS, bool SPLIT>
 __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+  constexpr bool QB_SM = TAB >= 1, Q_SM = TAB == 2;   // Qbar accumulator / Q rows of the unit in shared memory
   extern __shared__ uint8_t smraw[];
   __shared__ WsBars bars;
   __shared__ uint32_t tmem_slot;
@@ -875,32 +888,32 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
-      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, g.S);
+      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
       const int atom0 = us.atom_base, natoms = us.n_tab;
       const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
       const float* gP = g.P + (size_t)atom0 * 64;
       const float* gAb = g.abar + (size_t)atom0 * 64;
       float* gPb = g.Pbar + (size_t)atom0 * 64;
-      float* gQb = g.Qbar + (size_t)us.part * g.qbar_stride + (size_t)atom0 * 64;   // this part's (partial) Qbar rows
+      // this part's (partial) Qbar rows; recomputed where it is needed instead of kept in registers across the tiles
+      auto qbar_rows = [&]() { return g.Qbar + (SPLIT ? (size_t)(unit % g.S) * g.qbar_stride : (size_t)0) + (size_t)atom0 * 64; };
       const float* tQ;
       float* tQb;
-      int ld;
-      if (SMEM_TABLES) {
-        ld = kTabLd;
+      constexpr int ldq = Q_SM ? kTabLd : 64, ld = QB_SM ? kTabLd : 64;   // ld: row pitch of the Qbar accumulator
+      if (Q_SM) {                      // two tables: Q, then Qbar
         tQb = sTab + g.unit_atoms * kTabLd;
-        copy_rows_n(sTab, ld, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
+        copy_rows_n(sTab, kTabLd, g.Q + (size_t)atom0 * 64, 64, natoms, gt, kWsGroupThreads);
         tQ = sTab;
       } else {
-        ld = 64;
         tQ = g.Q + (size_t)atom0 * 64;
-        tQb = gQb;
+        tQb = QB_SM ? sTab : qbar_rows();
       }
-      zero_rows_n(gPb + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
+      if (SPLIT) zero_rows_n(gPb + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
+      else zero_rows_n(gPb, 64, natoms, gt, kWsGroupThreads);
       zero_rows_n(tQb, ld, natoms, gt, kWsGroupThreads);
       if (e_begin >= e_end) {
         ws_group_sync(grp);
-        if (SMEM_TABLES) {
-          copy_rows_n(gQb, 64, tQb, ld, natoms, gt, kWsGroupThreads);
+        if (QB_SM) {
+          copy_rows_n(qbar_rows(), 64, tQb, ld, natoms, gt, kWsGroupThreads);
           ws_group_sync(grp);
         }
         continue;
@@ -972,12 +985,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           uint32_t ur[16];
           tmem_ld16(lane_addr + ACC + col0, ur);
           const float4* pp = reinterpret_cast<const float4*>(gP + (size_t)tgc * 64 + col0);
-          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ld + col0);
+          const float4* qq = reinterpret_cast<const float4*>(tQ + (size_t)sr * ldq + col0);
           float4 p[4], q[4];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             p[j4] = __ldg(pp + j4);
-            q[j4] = SMEM_TABLES ? qq[j4] : __ldg(qq + j4);
+            q[j4] = Q_SM ? qq[j4] : __ldg(qq + j4);
           }
           tmem_ld_wait();
           float v[16];
@@ -1120,8 +1133,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       reduce_targets_global_256(sU, keys + (kidx + 2) % 3, gPb, gt);          // last tile of the unit
       reduce_sources_table_256(sU, keys + (kidx + 2) % 3, tQb, ld, gt);
       ws_group_sync(grp);
-      if (SMEM_TABLES) {
-        copy_rows_n(gQb, 64, tQb, ld, natoms, gt, kWsGroupThreads);
+      if (QB_SM) {
+        copy_rows_n(qbar_rows(), 64, tQb, ld, natoms, gt, kWsGroupThreads);
         ws_group_sync(grp);
       }
     }
@@ -1146,16 +1159,26 @@ __global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t n4, size
   }
 }
 
-template <bool T, int TERMS>
+template <int T, int TERMS>
 static int launch_fwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
-  GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_fwd_wsi_kernel<T, TERMS><<<grid, kWsiThreads, smem, st>>>(g, gb);
+  if (g.S > 1) {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_wsi_kernel<T, TERMS, true><<<grid, kWsiThreads, smem, st>>>(g, gb);
+  } else {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_wsi_kernel<T, TERMS, false><<<grid, kWsiThreads, smem, st>>>(g, gb);
+  }
   return 0;
 }
-template <bool T, int TERMS>
+template <int T, int TERMS>
 static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
-  GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<T, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_bwd_ws_kernel<T, TERMS><<<grid, kWsThreads, smem, st>>>(g, gb);
+  if (g.S > 1) {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<T, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_bwd_ws_kernel<T, TERMS, true><<<grid, kWsThreads, smem, st>>>(g, gb);
+  } else {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<T, TERMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_bwd_ws_kernel<T, TERMS, false><<<grid, kWsThreads, smem, st>>>(g, gb);
+  }
   return 0;
 }
 
@@ -1163,11 +1186,12 @@ static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint
 int launch_edge_fwd_ws(Ctx* c, int l, int terms, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
   const size_t smem = fwd_tc_smem(c);
-  const uint32_t gb = (uint32_t)group_bytes(c, 2);
+  const uint32_t gb = (uint32_t)group_bytes(c);
   const int grid = tc_grid(c);
   int rc;
-  if (c->smem_tables) rc = terms == 1 ? launch_fwd_t<true, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<true, 3>(c, g, grid, smem, gb, st);
-  else rc = terms == 1 ? launch_fwd_t<false, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<false, 3>(c, g, grid, smem, gb, st);
+  if (c->tab_mode == 2) rc = terms == 1 ? launch_fwd_t<2, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<2, 3>(c, g, grid, smem, gb, st);
+  else if (c->tab_mode == 1) rc = terms == 1 ? launch_fwd_t<1, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<1, 3>(c, g, grid, smem, gb, st);
+  else rc = terms == 1 ? launch_fwd_t<0, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<0, 3>(c, g, grid, smem, gb, st);
   if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
   return 0;
@@ -1177,11 +1201,12 @@ int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, cudaStream
   EdgeTcArgs g = make_tc_args(c, l);
   g.rbar_accumulate = rbar_accumulate;
   const size_t smem = bwd_tc_smem(c);
-  const uint32_t gb = (uint32_t)group_bytes(c, 2);
+  const uint32_t gb = (uint32_t)group_bytes(c);
   const int grid = tc_grid(c);
   int rc;
-  if (c->smem_tables) rc = terms == 1 ? launch_bwd_t<true, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<true, 3>(c, g, grid, smem, gb, st);
-  else rc = terms == 1 ? launch_bwd_t<false, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<false, 3>(c, g, grid, smem, gb, st);
+  if (c->tab_mode == 2) rc = terms == 1 ? launch_bwd_t<2, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<2, 3>(c, g, grid, smem, gb, st);
+  else if (c->tab_mode == 1) rc = terms == 1 ? launch_bwd_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<1, 3>(c, g, grid, smem, gb, st);
+  else rc = terms == 1 ? launch_bwd_t<0, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<0, 3>(c, g, grid, smem, gb, st);
   if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
   if (c->split_eff > 1) {
