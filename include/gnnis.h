@@ -10,7 +10,9 @@
  * no C++ exception crosses the ABI.  Units: nm, kJ/mol, e.  All floating-point buffers are fp32.
  * `*_dev` pointers are device memory owned by the caller; `*_host` pointers are host memory.
  * `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Nothing in
- * gnnis_energy_force synchronises the host; it is CUDA-graph capturable.
+ * gnnis_energy_force synchronises the host; it is CUDA-graph capturable.  Outside a capture, an evaluation whose
+ * buffers, flags and handle state recur is replayed from an internal CUDA graph (bit-identical results; the
+ * environment variable GNNIS_GRAPHS=0, read by gnnis_create, disables this).
  */
 #ifndef GNNIS_H_
 #define GNNIS_H_
