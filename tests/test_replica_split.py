@@ -65,3 +65,32 @@ def test_split_with_parts_without_edges(monkeypatch):
         e, f, n = _run(mol["params"], sd, pos, [0, 5], [78.5, 24.85], monkeypatch, split)
         np.testing.assert_allclose(e, o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
         assert rel_rms(f, o["forces"].numpy()) < F_RRMS
+
+
+@pytest.mark.parametrize("N,R", [(64, 4), (65, 4), (96, 3), (119, 2), (120, 2), (121, 2), (128, 2), (50, 148), (50, 149), (50, 295), (50, 297)])
+def test_table_mode_and_split_boundaries(N, R, monkeypatch):
+    """Molecule sizes around the shared-memory table modes (two tables up to 64 atoms, one up to ~120, none beyond) and
+    batch sizes around the split rule (296 warp groups): the tensor-core path against the independent CUDA-core
+    kernels (which neither split nor use those table modes) on the same inputs."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    from oracle import gnn_oracle as O
+    monkeypatch.delenv("GNNIS_SPLIT", raising=False)
+    mol = synth.synth_molecule(N, seed=N + 7)
+    sd = O.random_state_dict(seed=N + 3)
+    # jitter 0.01 nm: larger displacements of these big synthetic molecules create contacts below 0.05 nm, where the
+    # reference's autograd (and therefore the oracle) returns NaN forces
+    pos = torch.from_numpy(synth.conformers(mol["pos"], R, 0.01, seed=R + 1).astype(np.float32)).cuda()
+    sids = [(5 * r + 2) % 39 for r in range(R)]
+    diel = [synth.SOLVENT_DIELECTRICS[s] for s in sids]
+    eng = Engine(mol["params"], sd)
+    eng.set_replicas(R, sids, diel)
+    e, f = eng.energy_force(pos)
+    e_cc, f_cc = eng.energy_force(pos, cuda_cores=True)
+    np.testing.assert_allclose(e.cpu().numpy(), e_cc.cpu().numpy(), rtol=2e-5, atol=1e-3)
+    assert rel_rms(f.cpu().numpy(), f_cc.cpu().numpy()) < 5e-4      # two fp32 implementations, both inside the 1e-3 gate
+    k = 2
+    o = O.evaluate(mol["params"], pos[:k].cpu().numpy(), sids[:k], diel[:k], sd)
+    assert bool(torch.isfinite(o["forces"]).all()) and bool(torch.isfinite(f).all())
+    np.testing.assert_allclose(e[:k].cpu().numpy(), o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
+    assert rel_rms(f[:k].cpu().numpy(), o["forces"].numpy()) < F_RRMS
