@@ -133,6 +133,7 @@ static int ensure_workspace(Ctx* c) {
   if (dev_alloc(c, &c->h_pos_dev, n * 3) || dev_alloc(c, &c->h_f_dev, n * 3) || dev_alloc(c, &c->h_e_dev, (size_t)c->R))
     return -1;
   if (!c->n_edges_dev && dev_alloc(c, &c->n_edges_dev, 1)) return -1;
+  if (!c->unit_ctr && dev_alloc(c, &c->unit_ctr, 8)) return -1;
   GNNIS_CUDA_OK(cudaMemset(c->sa_atom, 0, n * sizeof(float)));
   c->ws_atoms = n;
   c->ws_split = c->split;
@@ -271,6 +272,7 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
   c->split_eff = (tc_fwd && tc_bwd && c->G == 1) ? c->split : 1;   // the CUDA-core edge kernels do not split replicas
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
+  if (want_grad) GNNIS_CUDA_OK(cudaMemsetAsync(c->unit_ctr, 0, 8 * sizeof(unsigned), st));
   if (tm) tm->mark(kStNeighborBorn);
   if (launch_born_count(c, pos, predicate, st)) return -1;
   if (!gb_only) {
@@ -402,6 +404,7 @@ int gnnis_destroy(gnnis_handle h) {
   dev_free(&c->pair);
   dev_free(&c->perm);
   dev_free(&c->n_edges_dev);
+  dev_free(&c->unit_ctr);
   for (Ctx::HostSlot& s : c->hs) {
     dev_free(&s.pos);
     dev_free(&s.e);

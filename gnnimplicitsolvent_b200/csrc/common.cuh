@@ -60,6 +60,7 @@ struct LayerW {
 struct Ctx {
   int device = 0;
   std::string err;
+  unsigned* unit_ctr = nullptr;   // [8] unit hand-out counters of the edge kernels, zeroed at the start of an evaluation
   int64_t launches = 0;
   // CUDA-graph cache of whole evaluations (api.cu): an evaluation whose buffers, flags and handle state have been seen
   // before is replayed as one graph launch instead of 23 stream launches

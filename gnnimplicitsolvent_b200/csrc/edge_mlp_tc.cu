@@ -59,6 +59,7 @@ struct EdgeTcArgs {
   int rbar_accumulate;
   const uint8_t* perm;
   int unit_atoms;
+  unsigned* unit_counter; // dynamic unit hand-out of the adjoint, zeroed at the start of every evaluation
   int S;                  // sub-units per replica (Ctx::split_eff)
   size_t qbar_stride;     // floats between the partial Qbar tables of consecutive parts
 };
@@ -304,6 +305,7 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   EdgeTcArgs g{};
   g.n_units = c->n_units * c->split_eff;
   g.S = c->split_eff;
+  g.unit_counter = c->unit_ctr ? c->unit_ctr + l : nullptr;
   g.qbar_stride = (size_t)c->R * c->N * 64;
   g.G = c->G;
   g.N = c->N;
@@ -887,7 +889,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     uint32_t ph_d = 0;
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
-    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
+    // the first unit of a group is fixed, the following ones are handed out by a global counter: groups that got
+    // lighter units take more of them (units are independent, so results do not depend on who computes them;
+    // adjoint 3.59 -> 3.57 ms at C2)
+    __shared__ int s_next[kGroups];
+    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit = s_next[grp]) {
       const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
       const int atom0 = us.atom_base, natoms = us.n_tab;
       const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
@@ -911,6 +917,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       else zero_rows_n(gPb, 64, natoms, gt, kWsGroupThreads);
       zero_rows_n(tQb, ld, natoms, gt, kWsGroupThreads);
       if (e_begin >= e_end) {
+        ws_group_sync(grp);
+        if (gt == 0) s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
         ws_group_sync(grp);
         if (QB_SM) {
           copy_rows_n(qbar_rows(), 64, tQb, ld, natoms, gt, kWsGroupThreads);
@@ -956,6 +964,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
       }
       if (warp_arrive_last(cnt_u, 8, lane)) issue_u_du();
       ws_group_sync(grp);
+      // every thread of the group has read the previous hand-out before this barrier; the new one is read after the
+      // barriers that close the unit
+      if (gt == 0) s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
 
       for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
         const bool has_next = t0 + kTileE < e_end;
