@@ -12,12 +12,14 @@ namespace gnnis {
 int launch_born_count(Ctx*, const float*, int, cudaStream_t);
 int launch_fill_edges(Ctx*, const float*, int, int*, int*, uint32_t*, float*, int64_t, cudaStream_t);
 int launch_gb_energy(Ctx*, const float*, const float*, int, int, float*, cudaStream_t);
-int launch_born_adjoint(Ctx*, const float*, int, float*, cudaStream_t);
+int launch_born_adjoint(Ctx*, const float*, int, int, float*, cudaStream_t);
 int launch_reduce_energy(Ctx*, const float*, float*, cudaStream_t);
 int launch_edge_fwd(Ctx*, int, cudaStream_t);
 int launch_tile_perm(Ctx*, cudaStream_t);
-int launch_edge_fwd_ws(Ctx*, int, int, cudaStream_t);
-int launch_edge_bwd_ws(Ctx*, int, int, int, cudaStream_t);
+int launch_edge_fwd_ws(Ctx*, int, int, int, cudaStream_t);
+int launch_edge_bwd_ws(Ctx*, int, int, int, int, cudaStream_t);
+int st_fwd_tables(const Ctx*);
+int st_bwd_tables(const Ctx*);
 int launch_umma_selftest(Ctx*, const float*, const float*, float*, int, int, cudaStream_t);
 bool tc_path_fits(const Ctx*);
 int tc_table_mode(const Ctx*);
@@ -132,6 +134,25 @@ static int ensure_workspace(Ctx* c) {
     return -1;
   if (dev_alloc(c, &c->h_pos_dev, n * 3) || dev_alloc(c, &c->h_f_dev, n * 3) || dev_alloc(c, &c->h_e_dev, (size_t)c->R))
     return -1;
+  // activation stash: 2 x 128 bytes per edge of capacity and layer (+ one tile of slack: partial tiles are addressed,
+  // never written, past their last row)
+  {
+    dev_free(&c->stash);
+    c->stash_on = false;
+    const size_t per_arr = ((size_t)cap + kTileE) * 128;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    double budget = 0.45 * (double)free_b;
+    if (c->stash_max_gb >= 0 && c->stash_max_gb * 1e9 < budget) budget = c->stash_max_gb * 1e9;
+    if (c->use_stash && (double)(6 * per_arr) <= budget && st_fwd_tables(c) >= 0 && st_bwd_tables(c) >= 0) {
+      if (dev_alloc(c, &c->stash, 6 * per_arr)) return -1;
+      for (int l = 0; l < 3; ++l) {
+        c->st_u[l] = c->stash + (size_t)(2 * l) * per_arr;
+        c->st_w[l] = c->stash + (size_t)(2 * l + 1) * per_arr;
+      }
+      c->stash_on = true;
+    }
+  }
   if (!c->n_edges_dev && dev_alloc(c, &c->n_edges_dev, 1)) return -1;
   if (!c->unit_ctr && dev_alloc(c, &c->unit_ctr, 8)) return -1;
   GNNIS_CUDA_OK(cudaMemset(c->sa_atom, 0, n * sizeof(float)));
@@ -272,6 +293,9 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
   c->split_eff = (tc_fwd && tc_bwd && c->G == 1) ? c->split : 1;   // the CUDA-core edge kernels do not split replicas
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
+  // the adjoint reads the activations that the forward leaves behind when both edge stages run on tensor cores and the
+  // stash fits the memory budget (Ctx::stash_on); otherwise it recomputes them (edge_bwd_ws_kernel)
+  const int stash = (want_grad && tc_fwd && tc_bwd && c->stash_on) ? 1 : 0;
   if (want_grad) GNNIS_CUDA_OK(cudaMemsetAsync(c->unit_ctr, 0, 8 * sizeof(unsigned), st));
   if (tm) tm->mark(kStNeighborBorn);
   if (launch_born_count(c, pos, predicate, st)) return -1;
@@ -282,7 +306,7 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
     if (launch_node_pre1(c, st)) return -1;
     for (int l = 0; l < 3; ++l) {
       if (tm) tm->mark(kStEdgeFwd);
-      if (tc_fwd ? launch_edge_fwd_ws(c, l, terms, st) : launch_edge_fwd(c, l, st)) return -1;
+      if (tc_fwd ? launch_edge_fwd_ws(c, l, terms, stash, st) : launch_edge_fwd(c, l, st)) return -1;
       if (tm) tm->mark(kStNodeFwd);
       if ((node_tc ? launch_node_fwd_tc(c, l, st) : launch_node_fwd(c, l, st))) return -1;
     }
@@ -300,13 +324,13 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
         if (tm) tm->mark(kStNodeBwd);
         if ((node_tc ? launch_node_bwd_tc(c, l, st) : launch_node_bwd(c, l, st))) return -1;
         if (tm) tm->mark(kStEdgeBwd);
-        if (tc_bwd ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, terms, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
+        if (tc_bwd ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, terms, stash, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
       }
       if (tm) tm->mark(kStNodeBwd);
       if (launch_node_pre1_bwd(c, st)) return -1;
     }
     if (tm) tm->mark(kStBornAdjoint);
-    if (launch_born_adjoint(c, pos, gb_only ? 0 : 1, force, st)) return -1;
+    if (launch_born_adjoint(c, pos, gb_only ? 0 : 1, predicate, force, st)) return -1;
     if (c->n_bonds > 0 && launch_bond_forces(c, pos, e_rep, force, st)) return -1;
     if (c->have_ff && launch_mm_forces(c, pos, e_rep, force, 1, st)) return -1;
   } else {
@@ -355,6 +379,8 @@ int gnnis_create(gnnis_handle* out, int device) {
   }
   if (const char* e = getenv("GNNIS_GRAPHS")) c->use_graphs = atoi(e);   // debug: 0 = no CUDA-graph replay of evaluations
   if (const char* e = getenv("GNNIS_SPLIT")) c->split_max = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
+  if (const char* e = getenv("GNNIS_STASH")) c->use_stash = atoi(e);      // 0: the edge adjoint always recomputes its activations
+  if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;
@@ -405,6 +431,7 @@ int gnnis_destroy(gnnis_handle h) {
   dev_free(&c->perm);
   dev_free(&c->n_edges_dev);
   dev_free(&c->unit_ctr);
+  dev_free(&c->stash);
   for (Ctx::HostSlot& s : c->hs) {
     dev_free(&s.pos);
     dev_free(&s.e);

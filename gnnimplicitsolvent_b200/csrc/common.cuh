@@ -130,6 +130,14 @@ struct Ctx {
   float *abar = nullptr, *Pbar = nullptr, *Qbar = nullptr, *obar3 = nullptr;
   float* gbar = nullptr;   // [n][128] adjoint of silu(p), scratch between the two tensor-core node adjoint kernels
   float *rbar = nullptr;
+  // activation stash of the edge MLPs (edge_mlp_tc.cu): 16-bit codes of silu'(u), silu'(w) per edge, channel and layer,
+  // written by the forward edge kernels of an evaluation with forces and consumed by edge_bwd_st_kernel.  768 bytes per
+  // edge of CAPACITY; used when that fits the memory budget (ensure_workspace), otherwise the adjoint recomputes.
+  uint8_t* stash = nullptr;
+  uint8_t *st_u[3] = {nullptr, nullptr, nullptr}, *st_w[3] = {nullptr, nullptr, nullptr};
+  bool stash_on = false;
+  int use_stash = 1;          // GNNIS_STASH=0: always recompute (A/B, debug)
+  double stash_max_gb = -1;   // GNNIS_STASH_GB: upper bound of the stash allocation (default: 45 % of the free memory)
   float *e_atom = nullptr, *sa_atom = nullptr;
   int64_t* n_edges_dev = nullptr;
   // host-staging for gnnis_energy_force_host

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
   if (state == LB_INIT) {
     if (!finite) {
       if (threadIdx.x == 0) {
+        a.e[r] = et;               // reported as it is (NaN / inf): status 2 says the start point was not finite
         a.state[r] = LB_DONE;
         a.status[r] = 2;
         atomicSub(a.n_active, 1);
@@ -182,29 +183,29 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
       g[t] = gt;
       gg += gt * gt;
     }
+    // stagnation: the energy surface is discontinuous at graph-cutoff crossings, so a replica can keep accepting
+    // steps that gain nothing; 20 accepted steps without a gain above the fp32 resolution end it.  Every thread
+    // reads the reference energy / stall count BEFORE the barriers of block_sum; thread 0 writes them after, so all
+    // warps take the same branch below.
+    const float eref = state == LB_INIT ? et : a.eref[r];
+    const int st = state == LB_INIT ? 0 : a.stall[r];
     gg = block_sum(gg, red);
     __syncthreads();
     float grms = sqrtf(gg / D);
-    // stagnation: the energy surface is discontinuous at graph-cutoff crossings, so a replica can keep accepting
-    // steps that gain nothing; 20 accepted steps without a gain above the fp32 resolution end it
     bool stalled = false;
     if (state == LB_INIT) {
       if (threadIdx.x == 0) {
         a.eref[r] = et;
         a.stall[r] = 0;
       }
-    } else {
-      const float eref = a.eref[r];
-      const int st = a.stall[r];
-      if (et < eref - (1e-6f * fabsf(eref) + 1e-3f)) {
-        if (threadIdx.x == 0) {
-          a.eref[r] = et;
-          a.stall[r] = 0;
-        }
-      } else {
-        stalled = st + 1 >= 20;
-        if (threadIdx.x == 0) a.stall[r] = st + 1;
+    } else if (et < eref - (1e-6f * fabsf(eref) + 1e-3f)) {
+      if (threadIdx.x == 0) {
+        a.eref[r] = et;
+        a.stall[r] = 0;
       }
+    } else {
+      stalled = st + 1 >= 20;
+      if (threadIdx.x == 0) a.stall[r] = st + 1;
     }
     __syncthreads();
     if (stalled && grms >= a.grad_tol) {

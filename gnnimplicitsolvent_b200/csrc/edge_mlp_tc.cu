@@ -62,6 +62,9 @@ struct EdgeTcArgs {
   unsigned* unit_counter; // dynamic unit hand-out of the adjoint, zeroed at the start of every evaluation
   int S;                  // sub-units per replica (Ctx::split_eff)
   size_t qbar_stride;     // floats between the partial Qbar tables of consecutive parts
+  // activation stash (forward with forces -> adjoint): 16-bit codes of silu'(u) and silu'(w), [E][64] each, row e =
+  // 128 bytes whose 16-byte chunks are XOR-swizzled with (row in tile & 7) -- the shared-memory image of a tile
+  uint8_t *st_u, *st_w;
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
@@ -280,9 +283,12 @@ __global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __re
 //   adjoint tables  : Q, Qbar    [unit_atoms][68] each
 constexpr uint32_t kFwdWeights = 49152, kBwdWeights = 81920;
 constexpr uint32_t kGrpX = 0;
-constexpr uint32_t kGrpKeys = kGrpX + kTileE * kTileLd * 4;
+constexpr uint32_t kGrpStage = kGrpX + kTileE * kTileLd * 4;              // stash kernels: two 16 KB tile images
+constexpr uint32_t kStageBytes = 2 * kTileE * 128;
+constexpr uint32_t kGrpKeys = kGrpStage;                                  // (+ kStageBytes in the stash kernels)
 constexpr uint32_t kGrpTab = kGrpKeys + 3 * (uint32_t)sizeof(TileKeys);   // ws kernels rotate three key buffers
 static_assert(sizeof(TileKeys) % 16 == 0, "TileKeys must keep the tables 16-byte aligned");
+static_assert(kGrpStage % 128 == 0, "tile images must be 128-byte aligned");
 
 // shared-memory tables per group (Ctx::tab_mode): 2 = both tables of the kernel (forward Q, P; adjoint Q, Qbar),
 // 1 = one (forward Q; adjoint Qbar) with the other rows gathered from global memory / L1, 0 = none
@@ -298,6 +304,25 @@ int tc_table_mode(const Ctx* c) {
   for (int mode = 2; mode >= 1; --mode)
     if (kBwdWeights + 256 + kGroups * group_bytes_mode(c, mode) + 1024 + 2048 <= 227 * 1024) return mode;   // 2 KB: static smem
   return 0;
+}
+
+// stash kernels: X | two tile images | keys | tables (forward: Q [, P]; adjoint: Qbar); group size a multiple of 128
+static size_t st_group_bytes(const Ctx* c, int tables) {
+  size_t b = kGrpTab + kStageBytes + (size_t)tables * c->G * c->N * kTabLd * 4;
+  return (b + 127) / 128 * 128;
+}
+constexpr size_t kDynSmemMax = 227 * 1024 - 2048;   // 2 KB: static shared memory of the kernels
+static size_t st_fwd_smem(const Ctx* c, int tables) { return kFwdWeights + 256 + kGroups * st_group_bytes(c, tables) + 1024; }
+static size_t st_bwd_smem(const Ctx* c, int tables) { return 49152 + 256 + kGroups * st_group_bytes(c, tables) + 1024; }
+int st_fwd_tables(const Ctx* c) {
+  for (int t = 2; t >= 0; --t)
+    if (st_fwd_smem(c, t) <= kDynSmemMax) return t;
+  return -1;
+}
+int st_bwd_tables(const Ctx* c) {
+  for (int t = 1; t >= 0; --t)
+    if (st_bwd_smem(c, t) <= kDynSmemMax) return t;
+  return -1;
 }
 
 // ---------------------------------------------------------------------------------------------- launchers
@@ -325,6 +350,8 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   g.rbar = c->rbar;
   g.perm = c->perm;
   g.unit_atoms = c->G * c->N;
+  g.st_u = c->st_u[l];
+  g.st_w = c->st_w[l];
   return g;
 }
 
@@ -569,9 +596,14 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
 }
 
 // ---------------------------------------------------------------------------------------------- forward (ws, dedicated issuer warp)
-template <int TAB, int TERMS, bool SPLIT>
+// STASH: the evaluation wants forces and the activation stash is in use -- the two epilogues also produce silu'(u) and
+// silu'(w), pack them as 16-bit codes into a swizzled 16 KB image of the tile in shared memory, and one thread sends
+// each image to global memory with one bulk store (TMA engine); the adjoint (edge_bwd_st_kernel) then neither
+// recomputes u and w nor evaluates a single sigmoid.
+template <int TAB, int TERMS, bool SPLIT, bool STASH>
 __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   constexpr bool Q_SM = TAB >= 1, P_SM = TAB == 2;   // which node tables of the unit live in shared memory
+  constexpr uint32_t kStg = STASH ? kStageBytes : 0u;
   extern __shared__ uint8_t smraw[];
   __shared__ WsiBars bars;
   __shared__ uint32_t tmem_slot;
@@ -655,8 +687,11 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
     uint8_t* gsm = sm + kFwdWeights + 256 + (size_t)grp * grp_bytes;
     float* sZ = reinterpret_cast<float*>(gsm + kGrpX);
-    TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys);
-    float* sTab = reinterpret_cast<float*>(gsm + kGrpTab);
+    uint8_t* sStU = gsm + kGrpStage;                  // STASH: tile images of the silu'(u) / silu'(w) codes
+    uint8_t* sStW = gsm + kGrpStage + kStageBytes / 2;
+    TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys + kStg);
+    float* sTab = reinterpret_cast<float*>(gsm + kGrpTab + kStg);
+    const uint32_t swz = (uint32_t)(row & 7);         // chunk swizzle of this thread's image row
     const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
     const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
     uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp];
@@ -743,17 +778,33 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           }
           tmem_ld_wait();
           float v[16];
+          if (STASH) {
+            uint32_t code[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 y = silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
-            v[4 * j4 + 0] = y.x;
-            v[4 * j4 + 1] = y.y;
-            v[4 * j4 + 2] = y.z;
-            v[4 * j4 + 3] = y.w;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              float d[4];
+              silu_fd4_sum3(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], d);
+              code[2 * j4] = stash_enc2(d[0], d[1]);
+              code[2 * j4 + 1] = stash_enc2(d[2], d[3]);
+            }
+            const uint32_t q0 = (uint32_t)(4 * ch + 2 * c);
+            uint8_t* img = sStU + row * 128;
+            *reinterpret_cast<uint4*>(img + ((q0 ^ swz) << 4)) = make_uint4(code[0], code[1], code[2], code[3]);
+            *reinterpret_cast<uint4*>(img + (((q0 + 1u) ^ swz) << 4)) = make_uint4(code[4], code[5], code[6], code[7]);
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 y = silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
+              v[4 * j4 + 0] = y.x;
+              v[4 * j4 + 1] = y.y;
+              v[4 * j4 + 2] = y.z;
+              v[4 * j4 + 3] = y.w;
+            }
           }
           st_split16<TERMS>(lane_addr + VH + col0, lane_addr + VL + col0, v);
         }
         tmem_st_wait();
+        if (STASH) fence_proxy_async_smem();           // the image rows are read by the bulk store below
         warp_arrive_i(a_full, lane);
         // ---- look ahead: keys / radial basis of the next tile while w runs
         TileKeys* tkn = keys + (kidx + 1) % 3;
@@ -773,10 +824,15 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             rbf_regs<false>(r_n, g.inv_cutoff, o, od);
             mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
             __syncwarp();
+            if (STASH && gt == 0) bulk_store(g.st_u + (size_t)t0 * 128, sStU, (uint32_t)min(kTileE, e_end - t0) * 128u);
             st_split24<TERMS>(lane_addr + cur, lane_addr + cur + 32, o);
             tmem_st_wait();
             warp_arrive_i(u_ok, lane);
           }
+        } else if (STASH && w8 == 0) {
+          mbar_wait(a_full, ph_a);                   // all eight warps have written their rows of the silu'(u) image
+          __syncwarp();
+          if (gt == 0) bulk_store(g.st_u + (size_t)t0 * 128, sStU, (uint32_t)min(kTileE, e_end - t0) * 128u);
         }
         ph_a ^= 1u;
         // ---- a[tgt] += z of the PREVIOUS tile while the tensor pipe works on w of this one
@@ -790,18 +846,36 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         tmem_ld32(lane_addr + (cur ^ 64u) + 32 * ch, wr);
         tmem_ld_wait();
         if (has_next) warp_arrive_i(u_ok, lane);
+        if (STASH && gt == 0) bulk_store_wait_read();   // the silu'(w) image of the previous tile has left shared memory
         ws_group_sync(grp);                          // (A) the reduction of the previous tile is complete
         {
           const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * ch);
           float* zrow = sZ + row * kTileLd + 32 * ch;
+          if (STASH) {
+            uint8_t* img = sStW + row * 128;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = bb[j4];
-            const float4 z = silu4_sum2(&wr[4 * j4], b);
-            *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
+            for (int j8 = 0; j8 < 4; ++j8) {
+              float z[8], d[8];
+              silu_fd4_sum2(&wr[8 * j8], bb[2 * j8], z, d);
+              silu_fd4_sum2(&wr[8 * j8 + 4], bb[2 * j8 + 1], z + 4, d + 4);
+              *reinterpret_cast<float4*>(zrow + 8 * j8) = make_float4(z[0], z[1], z[2], z[3]);
+              *reinterpret_cast<float4*>(zrow + 8 * j8 + 4) = make_float4(z[4], z[5], z[6], z[7]);
+              *reinterpret_cast<uint4*>(img + ((((uint32_t)(4 * ch + j8)) ^ swz) << 4)) =
+                  make_uint4(stash_enc2(d[0], d[1]), stash_enc2(d[2], d[3]), stash_enc2(d[4], d[5]), stash_enc2(d[6], d[7]));
+            }
+            fence_proxy_async_smem();
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = bb[j4];
+              const float4 z = silu4_sum2(&wr[4 * j4], b);
+              *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
+            }
           }
         }
+        if (STASH && gt == 0) bulk_store_wait_read();   // the silu'(u) image of this tile has left shared memory
         ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
+        if (STASH && gt == 0) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
         pr = pr_n;
         r = r_n;
         valid = valid_n;
@@ -814,6 +888,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);   // last tile of the unit
       ws_group_sync(grp);   // all rows of the unit written before its tables are replaced
     }
+    if (STASH && gt == 0) bulk_store_wait_all();     // every image has reached global memory before the CTA retires
   }
   fence_before_sync();
   __syncthreads();
@@ -1155,6 +1230,361 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
+// ---------------------------------------------------------------------------------------------- adjoint from the stash
+// The adjoint when the forward kernels have left silu'(u), silu'(w) behind (EdgeTcArgs::st_u / st_w): per tile
+//     wbar = abar[i] * silu'(w);  vbar = wbar W2 (tcgen05);  ubar = vbar * silu'(u)
+//     Pbar[i] += ubar;  Qbar[j] += ubar;  rbar_e = ubar . (drbf Wr^T)      (du = drbf Wr^T: second tcgen05 product)
+// i.e. two of the four products of edge_bwd_ws_kernel, no P / Q gathers and no sigmoid.  The 16 KB code images of a
+// tile arrive by bulk copies (TMA engine, mbarrier completion) that are issued one tile ahead by whichever warp is
+// the last to have consumed the previous image; all hand-offs inside a group are arrival counters / mbarriers:
+//     d_full  tcgen05.commit            cnt_a / cnt_u  operand written (last arriving warp issues the product)
+//     ldw/ldu image landed              cnt_w / cnt_s  image consumed  (last arriving warp requests the next one)
+//     tileB   ubar tile of this tile complete in shared memory (8 warp arrivals; waited for before it is reduced)
+//     redR    reductions of the previous tile finished         (8 warp arrivals; waited for before the tile buffer is rewritten)
+// so a warp only ever waits for data it is about to touch.  TMEM per group: vbar 64 | du 64 | X hi 64 | X lo 64 columns;
+// X holds drbf (24 columns) for the du product and wbar for the vbar product in turn.
+constexpr uint32_t kStWeights = 49152;   // WrH 8K | WrL 8K | W2tH 16K | W2tL 16K
+struct StBars {
+  uint64_t d_full[kGroups], ldw[kGroups], ldu[kGroups], tileB[kGroups], redR[kGroups];
+  int cnt_a[kGroups], cnt_u[kGroups], cnt_w[kGroups], cnt_s[kGroups];
+};
+// one arrival per warp on a counter in shared memory; true (warp-uniform) in the warp that completes the count
+__device__ __forceinline__ bool warp_arrive_last_plain(int* cnt, int expected, int lane) {
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    int old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+    if (old == expected - 1) {
+      asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(cnt)), "r"(0) : "memory");
+      last = 1;
+    }
+  }
+  return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+__device__ __forceinline__ void warp_arrive_bar(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+template <int TAB, int TERMS, bool SPLIT>
+__global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+  constexpr bool QB_SM = TAB >= 1;   // Qbar accumulator of the unit in shared memory
+  extern __shared__ uint8_t smraw[];
+  __shared__ StBars bars;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float sPart[kGroups][kTileE];
+  __shared__ int s_next[kGroups];
+  __shared__ uint64_t ibar;
+  uint32_t base = smem_u32(smraw);
+  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
+  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2tH = sm + 16384, *sW2tL = sm + 32768;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) {
+      mbar_init(&bars.d_full[i], 1);
+      mbar_init(&bars.ldw[i], 1);
+      mbar_init(&bars.ldu[i], 1);
+      mbar_init(&bars.tileB[i], 8);
+      mbar_init(&bars.redR[i], 8);
+      bars.cnt_a[i] = 0;
+      bars.cnt_u[i] = 0;
+      bars.cnt_w[i] = 0;
+      bars.cnt_s[i] = 0;
+    }
+    mbar_init(&ibar, 1);
+    // operand image (build_edge_images): Wr hi | lo at 0, W2^T hi | lo at 48 KB
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&ibar)), "r"(kStWeights) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm)),
+                 "l"(g.img), "r"(16384u), "r"(smem_u32(&ibar))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sm + 16384)),
+                 "l"(g.img + 49152), "r"(32768u), "r"(smem_u32(&ibar))
+                 : "memory");
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  mbar_wait(&ibar, 0);
+  __syncwarp();
+  constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
+  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+
+  const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
+  uint8_t* gsm = sm + kStWeights + 256 + (size_t)grp * grp_bytes;
+  float* sU = reinterpret_cast<float*>(gsm + kGrpX);
+  uint8_t* sLW = gsm + kGrpStage;                       // image of the silu'(w) codes of the current tile
+  uint8_t* sLU = gsm + kGrpStage + kStageBytes / 2;     // ... silu'(u)
+  TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys + kStageBytes);
+  float* sTab = reinterpret_cast<float*>(gsm + kGrpTab + kStageBytes);
+  const uint32_t swz = (uint32_t)(row & 7);
+  const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
+  const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
+  uint64_t *d_full = &bars.d_full[grp], *ldw = &bars.ldw[grp], *ldu = &bars.ldu[grp], *tileB = &bars.tileB[grp],
+           *redR = &bars.redR[grp];
+  int *cnt_a = &bars.cnt_a[grp], *cnt_u = &bars.cnt_u[grp], *cnt_w = &bars.cnt_w[grp], *cnt_s = &bars.cnt_s[grp];
+  const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
+  auto issue_du = [&]() {      // du = drbf . Wr^T
+    if (elect_one()) {
+      issue_gemm_3xtf32<0, 3, TERMS>(tm + DU, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
+      mma_commit(d_full);
+    }
+    __syncwarp();
+  };
+  auto issue_vbar = [&]() {    // vbar = wbar . W2
+    if (elect_one()) {
+      issue_gemm_3xtf32<0, 8, TERMS>(tm + ACC, tm + XH, tm + XL, aW2tH, aW2tL, 64, idesc64, 0u);
+      mma_commit(d_full);
+    }
+    __syncwarp();
+  };
+  uint32_t ph_d = 0, ph_w = 0, ph_u = 0, ph_b = 0, ph_r = 0;
+  int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
+
+  // the first unit of a group is fixed, the following ones come from a global counter (see edge_bwd_ws_kernel)
+  for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit = s_next[grp]) {
+    const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
+    const int atom0 = us.atom_base, natoms = us.n_tab;
+    const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
+    const float* gAb = g.abar + (size_t)atom0 * 64;
+    float* gPb = g.Pbar + (size_t)atom0 * 64;
+    auto qbar_rows = [&]() { return g.Qbar + (SPLIT ? (size_t)(unit % g.S) * g.qbar_stride : (size_t)0) + (size_t)atom0 * 64; };
+    constexpr int ld = QB_SM ? kTabLd : 64;   // row pitch of the Qbar accumulator
+    float* tQb = QB_SM ? sTab : qbar_rows();
+    if (SPLIT) zero_rows_n(gPb + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
+    else zero_rows_n(gPb, 64, natoms, gt, kWsGroupThreads);
+    zero_rows_n(tQb, ld, natoms, gt, kWsGroupThreads);
+    if (e_begin >= e_end) {
+      ws_group_sync(grp);
+      if (gt == 0) s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
+      ws_group_sync(grp);
+      if (QB_SM) {
+        copy_rows_n(qbar_rows(), 64, tQb, ld, natoms, gt, kWsGroupThreads);
+        ws_group_sync(grp);
+      }
+      continue;
+    }
+    // ---- prologue: images and keys of the first tile, edge data of the second tile, first du product
+    if (gt == 0) {
+      const uint32_t nb = (uint32_t)min(kTileE, e_end - e_begin) * 128u;
+      bulk_load(sLW, g.st_w + (size_t)e_begin * 128, nb, ldw);
+      bulk_load(sLU, g.st_u + (size_t)e_begin * 128, nb, ldu);
+    }
+    uint32_t pr = 0u, pr_n = 0u;
+    float r = 0.3f, r_n = 0.3f;
+    uint8_t pm = (uint8_t)row, pm_n = (uint8_t)row;
+    bool valid = e_begin + row < e_end;
+    if (valid) {
+      pr = g.pair[e_begin + row];
+      if (ch == 0) {
+        r = g.r_e[e_begin + row];
+        pm = g.perm[e_begin + row];
+      }
+    }
+    if (e_begin + kTileE + row < e_end) {
+      pr_n = g.pair[e_begin + kTileE + row];
+      if (ch == 0) {
+        r_n = g.r_e[e_begin + kTileE + row];
+        pm_n = g.perm[e_begin + kTileE + row];
+      }
+    }
+    TileKeys* tk = keys + kidx;
+    if (ch == 0) {
+      tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
+      tk->src[row] = valid ? (int)(pr & 0xFFFFu) : -1;
+      tk->perm[row] = pm;
+    }
+    prefetch_l1(gAb + (size_t)(valid ? (pr >> 16) : 0u) * 64 + 32 * ch);
+    if (ch == 0) {
+      float o[32], od[32];
+      rbf_regs<true>(r, g.inv_cutoff, o, od);
+      st_split24<TERMS>(lane_addr + XH, lane_addr + XL, od);
+      tmem_st_wait();
+    }
+    if (warp_arrive_last(cnt_u, 8, lane)) issue_du();
+    ws_group_sync(grp);
+    // every thread of the group has read the previous hand-out before this barrier; the new one is read after the
+    // barriers that close the unit
+    if (gt == 0) s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
+
+    // pair-adjoint slot / previous value / partial sum of this thread's row in the tile that is reduced next
+    size_t rslot_p = 0;
+    float rold_p = 0.0f, racc_p = 0.0f;
+    bool valid_p = false;
+
+    for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
+      const bool has_next = t0 + kTileE < e_end;
+      const int tg = valid ? (int)(pr >> 16) : -1, tgc = valid ? tg : 0, sr = valid ? (int)(pr & 0xFFFFu) : 0;
+      // ---- du of this tile is complete: the X columns are free
+      mbar_wait(d_full, ph_d);
+      __syncwarp();
+      ph_d ^= 1u;
+      fence_after_sync();
+      // ---- wbar = abar[tgt] * silu'(w) -> TMEM
+      mbar_wait(ldw, ph_w);
+      ph_w ^= 1u;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = 32 * ch + 16 * c;
+        const uint32_t q0 = (uint32_t)(4 * ch + 2 * c);
+        const uint4 c0 = *reinterpret_cast<const uint4*>(sLW + row * 128 + ((q0 ^ swz) << 4));
+        const uint4 c1 = *reinterpret_cast<const uint4*>(sLW + row * 128 + (((q0 + 1u) ^ swz) << 4));
+        const float4* ab = reinterpret_cast<const float4*>(gAb + (size_t)tgc * 64 + col0);
+        const float4 a0 = __ldg(ab), a1 = __ldg(ab + 1), a2 = __ldg(ab + 2), a3 = __ldg(ab + 3);
+        float wb[16];
+        upk(mul2(stash_dec2(c0.x), pk(a0.x, a0.y)), wb[0], wb[1]);
+        upk(mul2(stash_dec2(c0.y), pk(a0.z, a0.w)), wb[2], wb[3]);
+        upk(mul2(stash_dec2(c0.z), pk(a1.x, a1.y)), wb[4], wb[5]);
+        upk(mul2(stash_dec2(c0.w), pk(a1.z, a1.w)), wb[6], wb[7]);
+        upk(mul2(stash_dec2(c1.x), pk(a2.x, a2.y)), wb[8], wb[9]);
+        upk(mul2(stash_dec2(c1.y), pk(a2.z, a2.w)), wb[10], wb[11]);
+        upk(mul2(stash_dec2(c1.z), pk(a3.x, a3.y)), wb[12], wb[13]);
+        upk(mul2(stash_dec2(c1.w), pk(a3.z, a3.w)), wb[14], wb[15]);
+        st_split16<TERMS>(lane_addr + XH + col0, lane_addr + XL + col0, wb);
+      }
+      tmem_st_wait();
+      if (warp_arrive_last(cnt_a, 8, lane)) issue_vbar();
+      if (has_next && warp_arrive_last_plain(cnt_w, 8, lane) && lane == 0)   // the image is consumed: fetch the next one
+        bulk_load(sLW, g.st_w + (size_t)(t0 + kTileE) * 128, (uint32_t)min(kTileE, e_end - t0 - kTileE) * 128u, ldw);
+      // ---- the previous tile: pair adjoint of its rows, Pbar[tgt] += ubar, Qbar[src] += ubar (under the vbar product)
+      if (t0 > e_begin) {
+        mbar_wait(tileB, ph_b);
+        ph_b ^= 1u;
+        const TileKeys* tkp = keys + (kidx + 2) % 3;
+        if (ch == 0 && valid_p) g.rbar[rslot_p] = rold_p + (racc_p + sPart[grp][row]);   // channels 0..31 + 32..63
+        reduce_targets_global_256(sU, tkp, gPb, gt);
+        reduce_sources_table_256(sU, tkp, tQb, ld, gt);
+      }
+      warp_arrive_bar(redR, lane);
+      // ---- segment lists of this tile (its keys are visible: written before the previous tile was closed)
+      if (w8 == 4) {
+        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - t0), lane);
+        if (lane == 0) {
+          tk->n_seg_t = ns;
+          tk->cont_prev = (t0 > e_begin && keys[(kidx + 2) % 3].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
+        }
+      } else if (w8 == 5) {
+        const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, min(kTileE, e_end - t0), lane);
+        if (lane == 0) tk->n_seg_s = ns;
+      }
+      // ---- edge data of the following tiles
+      TileKeys* tkn = keys + (kidx + 1) % 3;
+      bool valid_n = false;
+      uint32_t pr_nn = 0u;
+      float r_nn = 0.3f;
+      uint8_t pm_nn = (uint8_t)row;
+      if (has_next) {
+        valid_n = t0 + kTileE + row < e_end;
+        if (ch == 0) {
+          tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
+          tkn->src[row] = valid_n ? (int)(pr_n & 0xFFFFu) : -1;
+          tkn->perm[row] = valid_n ? pm_n : (uint8_t)row;
+        }
+        prefetch_l1(gAb + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
+        if (t0 + 2 * kTileE + row < e_end) {
+          pr_nn = g.pair[t0 + 2 * kTileE + row];
+          if (ch == 0) {
+            r_nn = g.r_e[t0 + 2 * kTileE + row];
+            pm_nn = g.perm[t0 + 2 * kTileE + row];
+          }
+        }
+      }
+      // radial derivative operand of the next tile: computed now (registers), stored once vbar has left the X columns
+      float o_n[32], od_n[32];
+      if (has_next && ch == 0) {
+        rbf_regs<true>(r_n, g.inv_cutoff, o_n, od_n);
+#pragma unroll
+        for (int k = 0; k < kRbf; ++k) asm volatile("" : "+f"(od_n[k]));   // keep the work above the wait
+      }
+      // slot of this edge in the dense pair-adjoint array; its previous value is fetched early (layers 2, 1 add)
+      size_t rslot = 0;
+      float rold = 0.0f;
+      if (ch == 0 && valid) {
+        rslot = ((size_t)atom0 + tg) * g.N + (sr - (tg / g.N) * g.N);
+        if (g.rbar_accumulate) rold = g.rbar[rslot];
+      }
+      mbar_wait(d_full, ph_d);
+      __syncwarp();
+      ph_d ^= 1u;
+      fence_after_sync();
+      if (has_next && ch == 0) st_split24<TERMS>(lane_addr + XH, lane_addr + XL, od_n);
+      // ---- ubar = vbar * silu'(u) -> shared tile ; rbar = ubar . du (this thread's 32 channels)
+      mbar_wait(ldu, ph_u);
+      ph_u ^= 1u;
+      mbar_wait(redR, ph_r);       // every warp has finished reducing the previous tile: the tile buffer is free
+      ph_r ^= 1u;
+      float racc = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = 32 * ch + 16 * c;
+        const uint32_t q0 = (uint32_t)(4 * ch + 2 * c);
+        uint32_t vr[16], dr[16];
+        tmem_ld16(lane_addr + ACC + col0, vr);
+        tmem_ld16(lane_addr + DU + col0, dr);
+        const uint4 c0 = *reinterpret_cast<const uint4*>(sLU + row * 128 + ((q0 ^ swz) << 4));
+        const uint4 c1 = *reinterpret_cast<const uint4*>(sLU + row * 128 + (((q0 + 1u) ^ swz) << 4));
+        const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        tmem_ld_wait();
+        float* urow = sU + row * kTileLd + col0;
+        f2_t rab = pk(0.0f, 0.0f);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const f2_t u01 = mul2(pk(__uint_as_float(vr[4 * j4 + 0]), __uint_as_float(vr[4 * j4 + 1])), stash_dec2(cw[2 * j4]));
+          const f2_t u23 = mul2(pk(__uint_as_float(vr[4 * j4 + 2]), __uint_as_float(vr[4 * j4 + 3])), stash_dec2(cw[2 * j4 + 1]));
+          rab = fma2(u01, pk(__uint_as_float(dr[4 * j4 + 0]), __uint_as_float(dr[4 * j4 + 1])), rab);
+          rab = fma2(u23, pk(__uint_as_float(dr[4 * j4 + 2]), __uint_as_float(dr[4 * j4 + 3])), rab);
+          float4 ub;
+          upk(u01, ub.x, ub.y);
+          upk(u23, ub.z, ub.w);
+          *reinterpret_cast<float4*>(urow + 4 * j4) = ub;
+        }
+        float ra, rb;
+        upk(rab, ra, rb);
+        racc += ra + rb;
+      }
+      if (has_next) {
+        if (ch == 0) tmem_st_wait();
+        if (warp_arrive_last(cnt_u, 8, lane)) issue_du();   // vbar / du drained, next radial operand in place
+        if (warp_arrive_last_plain(cnt_s, 8, lane) && lane == 0)
+          bulk_load(sLU, g.st_u + (size_t)(t0 + kTileE) * 128, (uint32_t)min(kTileE, e_end - t0 - kTileE) * 128u, ldu);
+      }
+      if (ch == 1) sPart[grp][row] = racc;
+      warp_arrive_bar(tileB, lane);                  // this warp's part of the ubar tile is in shared memory
+      rslot_p = rslot;
+      rold_p = rold;
+      racc_p = racc;
+      valid_p = valid;
+      pr = pr_n;
+      r = r_n;
+      pm = pm_n;
+      valid = valid_n;
+      pr_n = pr_nn;
+      r_n = r_nn;
+      pm_n = pm_nn;
+      tk = tkn;
+      kidx = (kidx + 1) % 3;
+    }
+    // ---- last tile of the unit
+    mbar_wait(tileB, ph_b);
+    ph_b ^= 1u;
+    if (ch == 0 && valid_p) g.rbar[rslot_p] = rold_p + (racc_p + sPart[grp][row]);
+    reduce_targets_global_256(sU, keys + (kidx + 2) % 3, gPb, gt);
+    reduce_sources_table_256(sU, keys + (kidx + 2) % 3, tQb, ld, gt);
+    ws_group_sync(grp);
+    if (QB_SM) {
+      copy_rows_n(qbar_rows(), 64, tQb, ld, natoms, gt, kWsGroupThreads);
+      ws_group_sync(grp);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
 // Qbar = sum over the parts of a split replica, in part order (deterministic)
 __global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t n4, size_t stride4, int S) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -1170,14 +1600,14 @@ __global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t n4, size
   }
 }
 
-template <int T, int TERMS>
+template <int T, int TERMS, bool STASH>
 static int launch_fwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
   if (g.S > 1) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_wsi_kernel<T, TERMS, true><<<grid, kWsiThreads, smem, st>>>(g, gb);
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, true, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_wsi_kernel<T, TERMS, true, STASH><<<grid, kWsiThreads, smem, st>>>(g, gb);
   } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_wsi_kernel<T, TERMS, false><<<grid, kWsiThreads, smem, st>>>(g, gb);
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, false, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_fwd_wsi_kernel<T, TERMS, false, STASH><<<grid, kWsiThreads, smem, st>>>(g, gb);
   }
   return 0;
 }
@@ -1192,32 +1622,69 @@ static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint
   }
   return 0;
 }
+template <int T, int TERMS>
+static int launch_bwd_st_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
+  if (g.S > 1) {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_st_kernel<T, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_bwd_st_kernel<T, TERMS, true><<<grid, kWsThreads, smem, st>>>(g, gb);
+  } else {
+    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_st_kernel<T, TERMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_bwd_st_kernel<T, TERMS, false><<<grid, kWsThreads, smem, st>>>(g, gb);
+  }
+  return 0;
+}
 
-// terms = 3: 3xTF32 (fp32-accurate, default); terms = 1: one TF32 product per contraction (GNNIS_FLAG_MLP_TF32X1)
-int launch_edge_fwd_ws(Ctx* c, int l, int terms, cudaStream_t st) {
+// terms = 3: 3xTF32 (fp32-accurate, default); terms = 1: one TF32 product per contraction (GNNIS_FLAG_MLP_TF32X1).
+// stash = 1: also leave silu'(u), silu'(w) for edge_bwd_st_kernel (evaluations with forces, Ctx::stash_on).
+int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
-  const size_t smem = fwd_tc_smem(c);
-  const uint32_t gb = (uint32_t)group_bytes(c);
   const int grid = tc_grid(c);
   int rc;
-  if (c->tab_mode == 2) rc = terms == 1 ? launch_fwd_t<2, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<2, 3>(c, g, grid, smem, gb, st);
-  else if (c->tab_mode == 1) rc = terms == 1 ? launch_fwd_t<1, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<1, 3>(c, g, grid, smem, gb, st);
-  else rc = terms == 1 ? launch_fwd_t<0, 1>(c, g, grid, smem, gb, st) : launch_fwd_t<0, 3>(c, g, grid, smem, gb, st);
+  if (stash) {
+    const int tab = st_fwd_tables(c);
+    if (tab < 0) {
+      c->err = "edge forward (stash): shared memory does not fit";
+      return -1;
+    }
+    const size_t smem = st_fwd_smem(c, tab);
+    const uint32_t gb = (uint32_t)st_group_bytes(c, tab);
+    if (tab == 2) rc = terms == 1 ? launch_fwd_t<2, 1, true>(c, g, grid, smem, gb, st) : launch_fwd_t<2, 3, true>(c, g, grid, smem, gb, st);
+    else if (tab == 1) rc = terms == 1 ? launch_fwd_t<1, 1, true>(c, g, grid, smem, gb, st) : launch_fwd_t<1, 3, true>(c, g, grid, smem, gb, st);
+    else rc = terms == 1 ? launch_fwd_t<0, 1, true>(c, g, grid, smem, gb, st) : launch_fwd_t<0, 3, true>(c, g, grid, smem, gb, st);
+  } else {
+    const size_t smem = fwd_tc_smem(c);
+    const uint32_t gb = (uint32_t)group_bytes(c);
+    if (c->tab_mode == 2) rc = terms == 1 ? launch_fwd_t<2, 1, false>(c, g, grid, smem, gb, st) : launch_fwd_t<2, 3, false>(c, g, grid, smem, gb, st);
+    else if (c->tab_mode == 1) rc = terms == 1 ? launch_fwd_t<1, 1, false>(c, g, grid, smem, gb, st) : launch_fwd_t<1, 3, false>(c, g, grid, smem, gb, st);
+    else rc = terms == 1 ? launch_fwd_t<0, 1, false>(c, g, grid, smem, gb, st) : launch_fwd_t<0, 3, false>(c, g, grid, smem, gb, st);
+  }
   if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, cudaStream_t st) {
+int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, int stash, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l);
   g.rbar_accumulate = rbar_accumulate;
-  const size_t smem = bwd_tc_smem(c);
-  const uint32_t gb = (uint32_t)group_bytes(c);
   const int grid = tc_grid(c);
   int rc;
-  if (c->tab_mode == 2) rc = terms == 1 ? launch_bwd_t<2, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<2, 3>(c, g, grid, smem, gb, st);
-  else if (c->tab_mode == 1) rc = terms == 1 ? launch_bwd_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<1, 3>(c, g, grid, smem, gb, st);
-  else rc = terms == 1 ? launch_bwd_t<0, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<0, 3>(c, g, grid, smem, gb, st);
+  if (stash) {
+    const int tab = st_bwd_tables(c);
+    if (tab < 0) {
+      c->err = "edge adjoint (stash): shared memory does not fit";
+      return -1;
+    }
+    const size_t smem = st_bwd_smem(c, tab);
+    const uint32_t gb = (uint32_t)st_group_bytes(c, tab);
+    if (tab == 1) rc = terms == 1 ? launch_bwd_st_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_st_t<1, 3>(c, g, grid, smem, gb, st);
+    else rc = terms == 1 ? launch_bwd_st_t<0, 1>(c, g, grid, smem, gb, st) : launch_bwd_st_t<0, 3>(c, g, grid, smem, gb, st);
+  } else {
+    const size_t smem = bwd_tc_smem(c);
+    const uint32_t gb = (uint32_t)group_bytes(c);
+    if (c->tab_mode == 2) rc = terms == 1 ? launch_bwd_t<2, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<2, 3>(c, g, grid, smem, gb, st);
+    else if (c->tab_mode == 1) rc = terms == 1 ? launch_bwd_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<1, 3>(c, g, grid, smem, gb, st);
+    else rc = terms == 1 ? launch_bwd_t<0, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<0, 3>(c, g, grid, smem, gb, st);
+  }
   if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
   if (c->split_eff > 1) {

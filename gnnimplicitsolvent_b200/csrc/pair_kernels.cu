@@ -383,7 +383,7 @@ template <int LANES>
 __global__ void __launch_bounds__(kPairThreads * LANES)
 born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos, int n, int N, int U, const float* __restrict__ rho,
                     const float* __restrict__ s, const int* __restrict__ radidx, const float* __restrict__ d0,
-                    const float* __restrict__ m0, float cutoff, const float* __restrict__ Bbar,
+                    const float* __restrict__ m0, float cutoff, int predicate, const float* __restrict__ Bbar,
                     const float* __restrict__ dBdI, const float* __restrict__ rbar, int use_rbar,
                     float* __restrict__ force) {
   extern __shared__ float sm[];
@@ -433,8 +433,10 @@ born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos,
     float g1 = Ibar_i * born_integral_dr(r1, rho_i, rho_j, ss[j], U * rj + ri, sd0, sm0);
     float g2 = sIbar[lo + j] * born_integral_dr(r2, rho_j, rho_i, s_i, U * ri + rj, sd0, sm0);
     if (use_rbar) {
-      if (r1 < cutoff) g1 += rbar_row[j];
-      if (r2 < cutoff) g2 += rbar_col[(size_t)j * N];
+      // the same edge test as fill_edges_kernel (run path: eps-distance, data path: radius_graph's squared distance):
+      // only slots that an edge adjoint kernel has written in this evaluation are read
+      if (in_cutoff(predicate, r1, sx, sy, sz, tx, ty, tz, cutoff)) g1 += rbar_row[j];
+      if (in_cutoff(predicate, r2, tx, ty, tz, sx, sy, sz, cutoff)) g2 += rbar_col[(size_t)j * N];
     }
     g1 *= rcp_fast(r1);
     g2 *= rcp_fast(r2);
@@ -521,18 +523,18 @@ int launch_gb_energy(Ctx* c, const float* pos, const float* born_s, int delta, i
   return 0;
 }
 
-int launch_born_adjoint(Ctx* c, const float* pos, int use_rbar, float* force, cudaStream_t st) {
+int launch_born_adjoint(Ctx* c, const float* pos, int use_rbar, int predicate, float* force, cudaStream_t st) {
   int n = c->R * c->N;
   int nblk = (n + kPairThreads - 1) / kPairThreads;
   size_t smem = (4 * stage_atoms_max(c->N) + 3 * (size_t)c->N + 2 * (size_t)c->U * c->U) * sizeof(float);
   if (pair_lanes(c) == 4) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(born_adjoint_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     born_adjoint_kernel<4><<<nblk, 4 * kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->d0,
-                                                                c->m0, c->cutoff, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
+                                                                c->m0, c->cutoff, predicate, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(born_adjoint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     born_adjoint_kernel<1><<<nblk, kPairThreads, smem, st>>>(c->skip_state, pos, n, c->N, c->U, c->rho, c->s, c->radidx, c->d0,
-                                                            c->m0, c->cutoff, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
+                                                            c->m0, c->cutoff, predicate, c->Bbar, c->dBdI, c->rbar, use_rbar, force);
   }
   GNNIS_LAUNCH_CHECK();
   return 0;

@@ -180,7 +180,8 @@ class Engine:
 
     # ------------------------------------------------------------------ hot path
     def energy_force(self, positions: torch.Tensor, *, delta=False, forces=True, gb_only=False, cuda_cores=False,
-                     data_predicate=False, vacuum_only=False, tf32x1=False, out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
+                     data_predicate=False, vacuum_only=False, tf32x1=False, bf16=False, extra_flags: int = 0,
+                     out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
         """positions [R,N,3] (or [R*N,3]) fp32 on the engine's device -> (E[R], F[R,N,3] or None)."""
         p = self._pos(positions)
         e = out_energy if out_energy is not None else torch.empty(self.n_rep, dtype=torch.float32, device=self.device)
@@ -190,7 +191,7 @@ class Engine:
         flags = ((_lib.FLAG_DELTA if delta else 0) | (0 if forces else _lib.FLAG_NO_FORCES)
                  | (_lib.FLAG_GB_ONLY if gb_only else 0) | (_lib.FLAG_MLP_CUDA_CORES if cuda_cores else 0)
                  | (_lib.FLAG_DATA_PREDICATE if data_predicate else 0) | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0)
-                 | (_lib.FLAG_MLP_TF32X1 if tf32x1 else 0))
+                 | (_lib.FLAG_MLP_TF32X1 if tf32x1 else 0) | (_lib.FLAG_MLP_BF16 if bf16 else 0) | int(extra_flags))
         self._check(self.lib.gnnis_energy_force(self._h, p.data_ptr(), e.data_ptr(), f.data_ptr() if forces else None,
                                                 flags, self._stream()))
         return e, f
@@ -292,12 +293,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gnnis_launch_count(self._h))
 
-    def profile_eval(self, positions: torch.Tensor, *, delta=False):
+    def profile_eval(self, positions: torch.Tensor, *, delta=False, extra_flags: int = 0):
         p = self._pos(positions)
         e = torch.empty(self.n_rep, dtype=torch.float32, device=self.device)
         f = torch.empty_like(p)
         ns = self.lib.gnnis_num_stages()
         ms = (C.c_float * ns)()
         self._check(self.lib.gnnis_profile_eval(self._h, p.data_ptr(), e.data_ptr(), f.data_ptr(),
-                                                _lib.FLAG_DELTA if delta else 0, self._stream(), ms, ns))
+                                                (_lib.FLAG_DELTA if delta else 0) | int(extra_flags), self._stream(), ms, ns))
         return {self.lib.gnnis_stage_name(i).decode(): float(ms[i]) for i in range(ns)}
