@@ -381,6 +381,7 @@ int gnnis_create(gnnis_handle* out, int device) {
   if (const char* e = getenv("GNNIS_SPLIT")) c->split_max = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
   if (const char* e = getenv("GNNIS_STASH")) c->use_stash = atoi(e);      // 0: the edge adjoint always recomputes its activations
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
+  if (const char* e = getenv("GNNIS_BWD_HELPERS")) c->bwd_helpers = atoi(e);
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;

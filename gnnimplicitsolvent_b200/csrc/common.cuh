@@ -137,6 +137,7 @@ struct Ctx {
   uint8_t *st_u[3] = {nullptr, nullptr, nullptr}, *st_w[3] = {nullptr, nullptr, nullptr};
   bool stash_on = false;
   int use_stash = 1;          // GNNIS_STASH=0: always recompute (A/B, debug)
+  int bwd_helpers = 4;        // GNNIS_BWD_HELPERS: helper warps per group of the stash adjoint (0 = edge_bwd_st_kernel, 4, 6, 8)
   double stash_max_gb = -1;   // GNNIS_STASH_GB: upper bound of the stash allocation (default: 45 % of the free memory)
   float *e_atom = nullptr, *sa_atom = nullptr;
   int64_t* n_edges_dev = nullptr;

@@ -36,7 +36,10 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef GNNIS_DEBUG_WAIT
+#include <cstdio>
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int site = 0) {
   uint32_t addr = smem_u32(bar);
   uint64_t t0 = 0;
   for (uint32_t it = 0;; ++it) {
@@ -52,7 +55,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((it & 255u) == 255u) {
       uint64_t t = globaltimer_ns();
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) __trap();
+      else if (t - t0 > 2000000000ull) {
+#ifdef GNNIS_DEBUG_WAIT
+        if ((threadIdx.x & 31) == 0)
+          printf("mbar_wait timeout: site %d block %d warp %d parity %u\n", site, (int)blockIdx.x, (int)(threadIdx.x >> 5), parity);
+#endif
+        __trap();
+      }
     }
   }
 }

@@ -260,23 +260,25 @@ class Engine:
         return row_ptr, col[:e], r[:e]
 
     def minimize(self, positions: torch.Tensor, grad_tol: float = 1.0, max_iter: int = 500, history: int = 8,
-                 delta=False, gb_only=False):
+                 delta=False, gb_only=False, vacuum_only=False):
         """Batched per-replica L-BFGS; returns (positions[R,N,3], E[R], status[R] int32, n_rounds)."""
         p = self._pos(positions).clone()
         e = torch.empty(self.n_rep, dtype=torch.float32, device=self.device)
         status = torch.empty(self.n_rep, dtype=torch.int32, device=self.device)
         nit = C.c_int32(0)
-        flags = (_lib.FLAG_DELTA if delta else 0) | (_lib.FLAG_GB_ONLY if gb_only else 0)
+        flags = ((_lib.FLAG_DELTA if delta else 0) | (_lib.FLAG_GB_ONLY if gb_only else 0)
+                 | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0))
         self._check(self.lib.gnnis_minimize(self._h, p.data_ptr(), e.data_ptr(), status.data_ptr(), C.byref(nit),
                                             float(grad_tol), int(max_iter), int(history), flags, self._stream()))
         return p, e, status, int(nit.value)
 
     def langevin(self, positions: torch.Tensor, velocities: torch.Tensor, masses, n_steps: int, *, temperature=300.0,
-                 friction=1.0, dt=0.002, seed=0, first_step=0, delta=False, gb_only=False):
+                 friction=1.0, dt=0.002, seed=0, first_step=0, delta=False, gb_only=False, vacuum_only=False):
         """LangevinMiddle steps in place on (positions, velocities) [R,N,3]."""
         assert positions.is_cuda and velocities.is_cuda and positions.is_contiguous() and velocities.is_contiguous()
         m = _f32(masses).reshape(-1)
-        flags = (_lib.FLAG_DELTA if delta else 0) | (_lib.FLAG_GB_ONLY if gb_only else 0)
+        flags = ((_lib.FLAG_DELTA if delta else 0) | (_lib.FLAG_GB_ONLY if gb_only else 0)
+                 | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0))
         self._check(self.lib.gnnis_langevin(self._h, positions.data_ptr(), velocities.data_ptr(), _fp(m),
                                             float(temperature), float(friction), float(dt), int(n_steps), int(seed),
                                             int(first_step), flags, self._stream()))

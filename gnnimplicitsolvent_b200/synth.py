@@ -249,3 +249,14 @@ def synth_forcefield(mol, coulomb14=1.0 / 1.2, lj14=0.5):
         "exceptions": {"idx": np.array(x_idx, dtype=np.int32).reshape(-1, 2), "chargeprod": f32(x_qq), "sigma": f32(x_s),
                        "epsilon": f32(x_e)},
     }
+
+
+def synth_mol_object(n_atoms: int, n_conformers: int, seed: int = 0, sigma: float = 0.01, with_forcefield: bool = True):
+    """A `Simulator.Molecule` (the stand-in for an RDKit molecule with embedded conformers) of a synthetic molecule:
+    conformers = jittered copies of the base geometry, parameters and vacuum force field as above."""
+    from .Simulator import Molecule  # noqa: PLC0415
+
+    mol = synth_molecule(n_atoms, seed=seed)
+    conf = conformers(mol["pos"], n_conformers, sigma, seed=seed + 1)
+    return Molecule(mol["elements"], conf, mol["params"], synth_forcefield(mol) if with_forcefield else None,
+                    masses=mol["masses"], smiles=f"SYNTH{n_atoms}")

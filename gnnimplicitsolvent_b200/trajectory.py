@@ -131,7 +131,7 @@ def run_simulation(engine, positions: torch.Tensor, velocities: torch.Tensor, ma
                    n_interval: int = 1000, minimize: bool = True, prefix: Optional[str] = None, *,
                    temperature: float = 300.0, friction: float = 1.0, dt: float = 0.002, seed: int = 0,
                    elements: Optional[Sequence[str]] = None, n_constraints: int = 0, grad_tol: float = 10.0,
-                   max_minimize_rounds: int = 500):
+                   max_minimize_rounds: int = 500, first_step: int = 0, eval_flags: Optional[dict] = None):
     """`Simulator.run_simulation` for the resident batched system: optional minimisation, then n_steps of
     LangevinMiddle in blocks of n_interval steps; after every block the frame is copied to the host on a side stream
     (into the memory-mapped file, overlapping the next block) and one log line is written.
@@ -139,8 +139,9 @@ def run_simulation(engine, positions: torch.Tensor, velocities: torch.Tensor, ma
     positions / velocities: CUDA [R, N, 3], advanced in place.  Returns the TrajectoryWriter prefix (or None)."""
     assert positions.is_cuda and velocities.is_cuda
     R, N = positions.shape[0], positions.shape[1]
+    eval_flags = dict(eval_flags or {})     # Hamiltonian switches of the engine (gb_only= / vacuum_only=)
     if minimize:
-        pmin, _, _, _ = engine.minimize(positions, grad_tol=grad_tol, max_iter=max_minimize_rounds)
+        pmin, _, _, _ = engine.minimize(positions, grad_tol=grad_tol, max_iter=max_minimize_rounds, **eval_flags)
         positions.copy_(pmin)
     n_frames = n_steps // n_interval
     writer = TrajectoryWriter(prefix, n_frames, R, N, elements) if prefix is not None else None
@@ -149,7 +150,7 @@ def run_simulation(engine, positions: torch.Tensor, velocities: torch.Tensor, ma
     snaps = [torch.empty_like(positions) for _ in range(2)] if writer is not None else []
     staging = [torch.empty((R, N, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)] if writer is not None else []
     pending = None   # (frame index, staging slot, event, meta)
-    done = 0
+    done = int(first_step)   # the random stream is keyed by the absolute step number: continuing runs do not repeat it
     t_wall = time.perf_counter()
 
     def flush(p):
@@ -160,12 +161,12 @@ def run_simulation(engine, positions: torch.Tensor, velocities: torch.Tensor, ma
 
     for i in range(n_frames):
         engine.langevin(positions, velocities, masses, n_interval, temperature=temperature, friction=friction, dt=dt,
-                        seed=seed, first_step=done)
+                        seed=seed, first_step=done, **eval_flags)
         done += n_interval
         if writer is None:
             continue
         slot = i & 1   # its previous user (frame i - 2) was flushed in iteration i - 1
-        e, _ = engine.energy_force(positions, forces=False)
+        e, _ = engine.energy_force(positions, forces=False, **eval_flags)
         temp = kinetic_temperature(velocities, masses, n_constraints)
         snaps[slot].copy_(positions)
         ready = torch.cuda.Event()
