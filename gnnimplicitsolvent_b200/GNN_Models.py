@@ -279,6 +279,9 @@ class GNN3_Multisolvent_embedding_run_multiple(GNN3_Multisolvent_embedding):
         return 0
 
     def _select_solvents(self, solvent_model, solvent_dielectric):
+        # solvent_model != -1 puts every replica into that solvent for THIS call (GNN_Models.py:780-786).  Intentional
+        # divergence: the reference overwrites its per-replica buffers, so its override sticks for later calls with -1;
+        # here a later call with -1 evaluates the set_num_reps configuration again.
         sm = int(solvent_model) if solvent_model is not None else -1
         if sm != -1:
             self._set_replica_config(self._num_reps, [sm] * self._num_reps, [float(solvent_dielectric)] * self._num_reps)

@@ -190,8 +190,8 @@ class Simulator:
         """`simulation.minimizeEnergy(tolerance, maxIterations)` (helper_functions.py:614-624).  OpenMM's tolerance
         is a gradient-RMS bound in kJ mol^-1 nm^-1 that the reference sets far below the fp32 noise floor (1e-4):
         every replica then runs until its line search stalls, which is what the batched L-BFGS does for
-        grad_tol <= 1.  Returns per-replica status (0 converged / stalled inside 20x grad_tol, 1 iteration limit,
-        2 non-finite)."""
+        grad_tol <= 1.  Returns per-replica status (0 gradient RMS below grad_tol, 1 iteration limit, 2 non-finite,
+        3 line search exhausted at fp32 resolution above grad_tol -- the reference's normal way to stop)."""
         grad_tol = max(float(tolerance), 1.0)
         max_iter = int(max_iterations) if max_iterations and max_iterations > 0 else 2000
         p, e, status, rounds = self._engine.minimize(self._positions, grad_tol=grad_tol, max_iter=max_iter, **self._flags())

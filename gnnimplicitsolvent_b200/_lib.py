@@ -63,6 +63,7 @@ SIGNATURES = {
                                  C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "gnnis_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "gnnis_launch_count": (C.c_int64, [C.c_void_p]),
+    "gnnis_describe": (C.c_char_p, [C.c_void_p]),
     "gnnis_profile_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                      c_float_p, C.c_int32]),
     "gnnis_num_stages": (C.c_int32, []),

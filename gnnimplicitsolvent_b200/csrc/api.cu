@@ -75,8 +75,8 @@ static void dev_free(T** p) {
 
 static int ensure_workspace(Ctx* c) {
   if (c->N <= 0 || c->R <= 0) return 0;
-  if (c->N > 65535) {
-    c->err = "n_atoms per replica must be <= 65535";
+  if (c->N > kMaxAtoms) {
+    c->err = "n_atoms per replica must be <= 1024: the pair kernels keep all pairs of a replica in shared memory (DESIGN.md 4)";
     return -1;
   }
   if (c->N <= kUnitAtomsMax) {
@@ -381,7 +381,6 @@ int gnnis_create(gnnis_handle* out, int device) {
   if (const char* e = getenv("GNNIS_SPLIT")) c->split_max = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
   if (const char* e = getenv("GNNIS_STASH")) c->use_stash = atoi(e);      // 0: the edge adjoint always recomputes its activations
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
-  if (const char* e = getenv("GNNIS_BWD_HELPERS")) c->bwd_helpers = atoi(e);
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;
@@ -570,12 +569,17 @@ int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w) {
     if (build_edge_images(c, 0) || build_node_images(c, 0)) return -1;
     GNNIS_CUDA_OK(cudaDeviceSynchronize());
   }
-  // gamma table is a view into the blob; keep a separate pointer that destroy() must not free twice
-  c->gamma_emb = nullptr;
-  if (dev_alloc(c, &c->gamma_emb, (size_t)S)) return -1;
+  if (dev_alloc(c, &c->gamma_emb, (size_t)S)) return -1;   // (dev_alloc releases the table of a previous load)
   GNNIS_CUDA_OK(cudaMemcpy(c->gamma_emb, w->gamma_embedding, S * sizeof(float), cudaMemcpyHostToDevice));
   c->S = S;
   c->have_weights = true;
+  for (int sid : c->solvent_host)
+    if (sid >= S) {   // replicas configured before the weights were (re)loaded must fit the new embedding table
+      c->err = "gnnis_load_weights: a replica uses solvent id " + std::to_string(sid) + " but the checkpoint has " +
+               std::to_string(S) + " solvents; call gnnis_set_replicas again";
+      c->R = 0;
+      return -1;
+    }
   return 0;
 }
 
@@ -586,6 +590,12 @@ int gnnis_set_system(gnnis_handle h, int32_t n_atoms, const float* params7, cons
   if (!c) return -1;
   if (n_atoms < 1 || !params7 || !d0 || !m0 || n_unique < 1) {
     c->err = "gnnis_set_system: bad arguments";
+    return -1;
+  }
+  if (n_atoms > kMaxAtoms) {
+    c->err = "gnnis_set_system: " + std::to_string(n_atoms) + " atoms per replica; this library supports at most " +
+             std::to_string(kMaxAtoms) + " (all pairs of a replica are processed in shared memory; there is no cell-list "
+             "path for larger systems, see INTEGRATION.md 'Size limits')";
     return -1;
   }
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
@@ -643,6 +653,7 @@ int gnnis_set_replicas(gnnis_handle h, int32_t n_rep, const int32_t* solvent_id,
   GNNIS_CUDA_OK(cudaMemcpy(c->solvent_id, solvent_id, n_rep * sizeof(int), cudaMemcpyHostToDevice));
   GNNIS_CUDA_OK(cudaMemcpy(c->pref, pref.data(), n_rep * sizeof(float), cudaMemcpyHostToDevice));
   c->R = n_rep;
+  c->solvent_host.assign(solvent_id, solvent_id + n_rep);
   return ensure_workspace(c);
 }
 
@@ -822,6 +833,22 @@ int gnnis_umma_selftest(gnnis_handle h, const float* a_dev, const float* b_dev, 
 }
 
 int64_t gnnis_launch_count(gnnis_handle h) { return h ? reinterpret_cast<Ctx*>(h)->launches : 0; }
+
+const char* gnnis_describe(gnnis_handle h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return "";
+  const bool tc = tc_path_fits(c);
+  std::string d = "N=" + std::to_string(c->N) + " R=" + std::to_string(c->R) + " replicas_per_unit=" + std::to_string(c->G) +
+                  " units=" + std::to_string(c->n_units) + " split=" + std::to_string(c->split);
+  d += std::string(" edge_kernels=") + (tc ? "tcgen05" : "cuda-cores (unit tables do not fit next to the operand images)");
+  if (tc) {
+    d += std::string(" adjoint=") + (c->stash_on ? "stash" : (c->use_stash ? "recompute (stash exceeds the memory budget)" : "recompute (GNNIS_STASH=0)"));
+    d += " tables=" + std::to_string(c->stash_on ? st_fwd_tables(c) : c->tab_mode);
+  }
+  d += " stash_bytes=" + std::to_string(c->stash_on ? (size_t)6 * ((size_t)c->edge_cap + kTileE) * 128 : (size_t)0);
+  c->desc = d;
+  return c->desc.c_str();
+}
 
 int32_t gnnis_num_stages(void) { return kNumStages; }
 const char* gnnis_stage_name(int32_t i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }

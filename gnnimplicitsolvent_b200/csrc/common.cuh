@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/gnnis.h"
 
@@ -31,6 +32,7 @@ constexpr int kRbf = 20;                  // _NUM_KERNELS (GNN_Layers.py:2153)
 constexpr int kRbfLd = 24;                // padded row of the rbf tile
 constexpr int kTileE = 128;               // edges per tile
 constexpr int kTileLd = 68;               // padded row (floats) of a [128][64] tile
+constexpr int kMaxAtoms = 1024;             // atoms per replica: all pairs of a replica are processed in shared memory
 constexpr int kUnitAtomsMax = 64;         // atoms per work unit held in shared-memory tables
 constexpr int kEdgeThreads = 256;
 constexpr int kNodeRows = 64;
@@ -59,7 +61,8 @@ struct LayerW {
 
 struct Ctx {
   int device = 0;
-  std::string err;
+  std::string err, desc;
+  std::vector<int> solvent_host;   // solvent ids of the replicas (re-validated when weights are loaded later)
   unsigned* unit_ctr = nullptr;   // [8] unit hand-out counters of the edge kernels, zeroed at the start of an evaluation
   int64_t launches = 0;
   // CUDA-graph cache of whole evaluations (api.cu): an evaluation whose buffers, flags and handle state have been seen
@@ -137,7 +140,6 @@ struct Ctx {
   uint8_t *st_u[3] = {nullptr, nullptr, nullptr}, *st_w[3] = {nullptr, nullptr, nullptr};
   bool stash_on = false;
   int use_stash = 1;          // GNNIS_STASH=0: always recompute (A/B, debug)
-  int bwd_helpers = 4;        // GNNIS_BWD_HELPERS: helper warps per group of the stash adjoint (0 = edge_bwd_st_kernel, 4, 6, 8)
   double stash_max_gb = -1;   // GNNIS_STASH_GB: upper bound of the stash allocation (default: 45 % of the free memory)
   float *e_atom = nullptr, *sa_atom = nullptr;
   int64_t* n_edges_dev = nullptr;

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
       if (threadIdx.x == 0) {
         a.e[r] = et;
         a.state[r] = LB_DONE;
-        a.status[r] = grms < 20.f * a.grad_tol ? 0 : 1;
+        a.status[r] = 3;   // stalled above the threshold (grms >= grad_tol here)
         a.hist[r] = (head << 16) | cnt;
         atomicSub(a.n_active, 1);
       }
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
         // rule (tolerance=1e-4 is below the fp32 force noise floor)
         if (threadIdx.x == 0) {
           a.state[r] = LB_DONE;
-          a.status[r] = finite ? (sqrtf(gg / D) < 20.f * a.grad_tol ? 0 : 1) : 2;
+          a.status[r] = finite ? (sqrtf(gg / D) < a.grad_tol ? 0 : 3) : 2;
           a.hist[r] = 0;
           atomicSub(a.n_active, 1);
         }

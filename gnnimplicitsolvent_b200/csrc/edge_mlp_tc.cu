@@ -1585,471 +1585,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
-// ---------------------------------------------------------------------------------------------- adjoint from the stash, helper warps
-// Same arithmetic as edge_bwd_st_kernel, other division of labour.  The per-tile instruction stream of an epilogue
-// warp is what bounds these kernels (about 8.5 cycles per instruction and warp, four warps per scheduler), so
-// everything that does not need this warp's TMEM lanes moves to H helper warps per group that run alongside:
-//     epilogue warps (8 per group): wbar -> TMEM, vbar / du -> ubar tile in shared memory, partial pair adjoints
-//     helper warps   (H per group): edge keys, segment lists, radial derivative operand (-> TMEM X columns), the two
-//                                   segmented reductions of the ubar tile, the pair-adjoint read-modify-write, table
-//                                   zeroing / copy-out, the first bulk loads of a unit
-// The helpers reduce tile t while the epilogue warps already work on tile t + 1.  Hand-offs: cnt_u has 12 arrivals
-// (8 epilogue warps have drained vbar / du, 4 helper warps have stored the next radial operand), tileB 8 (ubar tile
-// written), redR H (tile reduced); the rest as in edge_bwd_st_kernel.
-template <int NW>
-__device__ __forceinline__ void reduce_targets_global_n(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
-                                                        float* __restrict__ out, int ht) {
-  const int lane = ht & 31, cq = lane & 15, half = lane >> 4, w = ht >> 5;
-  const int nseg = tk->n_seg_t;
-  for (int s = w; s < nseg; s += NW) {
-    const int p0 = tk->seg_t[s], p1 = tk->seg_t[s + 1];
-    const int mid = p0 + ((p1 - p0 + 1) >> 1);
-    const int a0 = half ? mid : p0, a1 = half ? p1 : mid;
-    float4 run = make_float4(0.f, 0.f, 0.f, 0.f), run2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int p = a0;
-#pragma unroll 2
-    for (; p + 1 < a1; p += 2) {   // two interleaved partial sums, fixed order
-      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
-      const float4 u = *reinterpret_cast<const float4*>(sX + (p + 1) * kTileLd + 4 * cq);
-      run.x += v.x;
-      run.y += v.y;
-      run.z += v.z;
-      run.w += v.w;
-      run2.x += u.x;
-      run2.y += u.y;
-      run2.z += u.z;
-      run2.w += u.w;
-    }
-    if (p < a1) {
-      const float4 v = *reinterpret_cast<const float4*>(sX + p * kTileLd + 4 * cq);
-      run.x += v.x;
-      run.y += v.y;
-      run.z += v.z;
-      run.w += v.w;
-    }
-    run.x += run2.x;
-    run.y += run2.y;
-    run.z += run2.z;
-    run.w += run2.w;
-    const float ox = __shfl_xor_sync(0xffffffffu, run.x, 16), oy = __shfl_xor_sync(0xffffffffu, run.y, 16);
-    const float oz = __shfl_xor_sync(0xffffffffu, run.z, 16), ow = __shfl_xor_sync(0xffffffffu, run.w, 16);
-    if (half == 0) {
-      run.x += ox;
-      run.y += oy;
-      run.z += oz;
-      run.w += ow;
-      float4* dst = reinterpret_cast<float4*>(out + (size_t)tk->tgt[p0] * 64 + 4 * cq);
-      if (s == 0 && tk->cont_prev) {
-        float4 t = *dst;
-        run.x += t.x;
-        run.y += t.y;
-        run.z += t.z;
-        run.w += t.w;
-      }
-      *dst = run;
-    }
-  }
-}
-template <int NW>
-__device__ __forceinline__ void reduce_sources_table_n(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
-                                                       float* __restrict__ table, int ld, int ht) {
-  const int cq = ht & 15, slot = ht >> 4;
-  const int nseg = tk->n_seg_s;
-  for (int s = slot; s < nseg; s += 2 * NW) {
-    const int p0 = tk->seg_s[s], p1 = tk->seg_s[s + 1];
-    const int row0 = tk->perm[p0];
-    float4* dst = reinterpret_cast<float4*>(table + (size_t)tk->src[row0] * ld + 4 * cq);
-    float4 t = *dst;
-    for (int p = p0; p < p1; p += 4) {
-      const int r0 = tk->perm[p], r1 = tk->perm[min(p + 1, p1 - 1)], r2 = tk->perm[min(p + 2, p1 - 1)],
-                r3 = tk->perm[min(p + 3, p1 - 1)];
-      const float4 v0 = *reinterpret_cast<const float4*>(sX + r0 * kTileLd + 4 * cq);
-      const float4 v1 = *reinterpret_cast<const float4*>(sX + r1 * kTileLd + 4 * cq);
-      const float4 v2 = *reinterpret_cast<const float4*>(sX + r2 * kTileLd + 4 * cq);
-      const float4 v3 = *reinterpret_cast<const float4*>(sX + r3 * kTileLd + 4 * cq);
-      const bool b1 = p + 1 < p1, b2 = p + 2 < p1, b3 = p + 3 < p1;
-      t.x += v0.x;
-      t.y += v0.y;
-      t.z += v0.z;
-      t.w += v0.w;
-      if (b1) {
-        t.x += v1.x;
-        t.y += v1.y;
-        t.z += v1.z;
-        t.w += v1.w;
-      }
-      if (b2) {
-        t.x += v2.x;
-        t.y += v2.y;
-        t.z += v2.z;
-        t.w += v2.w;
-      }
-      if (b3) {
-        t.x += v3.x;
-        t.y += v3.y;
-        t.z += v3.z;
-        t.w += v3.w;
-      }
-    }
-    *dst = t;
-  }
-}
-
-template <int H>
-__device__ __forceinline__ void sth_group_sync(int grp) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(256 + 32 * H) : "memory");
-}
-template <int H>
-__device__ __forceinline__ void sth_helper_sync(int grp) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 3), "n"(32 * H) : "memory");
-}
-
-template <int TAB, int TERMS, bool SPLIT, int H>
-__global__ void __launch_bounds__(kGroups * (256 + 32 * H), 1) edge_bwd_sth_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
-  constexpr bool QB_SM = TAB >= 1;   // Qbar accumulator of the unit in shared memory
-  constexpr int kHT = 32 * H;        // helper threads per group
-  extern __shared__ uint8_t smraw[];
-  __shared__ StBars bars;
-  __shared__ uint32_t tmem_slot;
-  __shared__ float sPart[kGroups][2][kTileE];
-  __shared__ int s_next[kGroups];
-  __shared__ uint64_t ibar;
-  uint32_t base = smem_u32(smraw);
-  uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
-  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2tH = sm + 16384, *sW2tL = sm + 32768;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) {
-    for (int i = 0; i < kGroups; ++i) {
-      mbar_init(&bars.d_full[i], 1);
-      mbar_init(&bars.ldw[i], 1);
-      mbar_init(&bars.ldu[i], 1);
-      mbar_init(&bars.tileB[i], 8);
-      mbar_init(&bars.redR[i], H);
-      bars.cnt_a[i] = 0;
-      bars.cnt_u[i] = 0;
-      bars.cnt_w[i] = 0;
-      bars.cnt_s[i] = 0;
-    }
-    mbar_init(&ibar, 1);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&ibar)), "r"(kStWeights) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm)),
-                 "l"(g.img), "r"(16384u), "r"(smem_u32(&ibar))
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(sm + 16384)),
-                 "l"(g.img + 49152), "r"(32768u), "r"(smem_u32(&ibar))
-                 : "memory");
-  }
-  fence_proxy_async_smem();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  mbar_wait(&ibar, 0);
-  __syncwarp();
-  constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
-
-  const bool helper = warp >= 2 * 8;
-  const int grp = helper ? (warp - 16) / H : warp >> 3;
-  uint8_t* gsm = sm + kStWeights + 256 + (size_t)grp * grp_bytes;
-  float* sU = reinterpret_cast<float*>(gsm + kGrpX);
-  uint8_t* sLW = gsm + kGrpStage;
-  uint8_t* sLU = gsm + kGrpStage + kStageBytes / 2;
-  TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys + kStageBytes);
-  float* sTab = reinterpret_cast<float*>(gsm + kGrpTab + kStageBytes);
-  const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
-  uint64_t *d_full = &bars.d_full[grp], *ldw = &bars.ldw[grp], *ldu = &bars.ldu[grp], *tileB = &bars.tileB[grp],
-           *redR = &bars.redR[grp];
-  int *cnt_a = &bars.cnt_a[grp], *cnt_u = &bars.cnt_u[grp], *cnt_w = &bars.cnt_w[grp], *cnt_s = &bars.cnt_s[grp];
-  const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2tH = smem_u32(sW2tH), aW2tL = smem_u32(sW2tL);
-  auto issue_du = [&]() {      // du = drbf . Wr^T
-    if (elect_one()) {
-      issue_gemm_3xtf32<0, 3, TERMS>(tm + DU, tm + XH, tm + XL, aWrH, aWrL, 64, idesc64, 0u);
-      mma_commit(d_full);
-    }
-    __syncwarp();
-  };
-  auto issue_vbar = [&]() {    // vbar = wbar . W2
-    if (elect_one()) {
-      issue_gemm_3xtf32<0, 8, TERMS>(tm + ACC, tm + XH, tm + XL, aW2tH, aW2tL, 64, idesc64, 0u);
-      mma_commit(d_full);
-    }
-    __syncwarp();
-  };
-  constexpr int ld = QB_SM ? kTabLd : 64;   // row pitch of the Qbar accumulator
-
-  if (!helper) {
-    // =========================================== epilogue warps ===========================================
-    const int gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
-    const uint32_t swz = (uint32_t)(row & 7);
-    const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-    uint32_t ph_d = 0, ph_w = 0, ph_u = 0, ph_r = 0;
-    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit = s_next[grp]) {
-      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
-      const int atom0 = us.atom_base;
-      const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
-      const float* gAb = g.abar + (size_t)atom0 * 64;
-      if (e_begin >= e_end) {
-        sth_group_sync<H>(grp);
-        sth_group_sync<H>(grp);
-        continue;
-      }
-      uint32_t pr = 0u, pr_n = 0u;
-      if (e_begin + row < e_end) pr = g.pair[e_begin + row];                       // invalid rows use target 0
-      if (e_begin + kTileE + row < e_end) pr_n = g.pair[e_begin + kTileE + row];
-      prefetch_l1(gAb + (size_t)(pr >> 16) * 64 + 32 * ch);
-      if (warp_arrive_last(cnt_u, 12, lane)) issue_du();
-      sth_group_sync<H>(grp);
-      for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-        const bool has_next = t0 + kTileE < e_end;
-        const int tgc = (int)(pr >> 16);
-        // ---- du of this tile is complete: the X columns are free
-        mbar_wait(d_full, ph_d, 1);
-        __syncwarp();
-        ph_d ^= 1u;
-        fence_after_sync();
-        // ---- wbar = abar[tgt] * silu'(w) -> TMEM
-        mbar_wait(ldw, ph_w, 2);
-        ph_w ^= 1u;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = 32 * ch + 16 * c;
-          const uint32_t q0 = (uint32_t)(4 * ch + 2 * c);
-          const uint4 c0 = *reinterpret_cast<const uint4*>(sLW + row * 128 + ((q0 ^ swz) << 4));
-          const uint4 c1 = *reinterpret_cast<const uint4*>(sLW + row * 128 + (((q0 + 1u) ^ swz) << 4));
-          const float4* ab = reinterpret_cast<const float4*>(gAb + (size_t)tgc * 64 + col0);
-          const float4 a0 = __ldg(ab), a1 = __ldg(ab + 1), a2 = __ldg(ab + 2), a3 = __ldg(ab + 3);
-          float wb[16];
-          upk(mul2(stash_dec2(c0.x), pk(a0.x, a0.y)), wb[0], wb[1]);
-          upk(mul2(stash_dec2(c0.y), pk(a0.z, a0.w)), wb[2], wb[3]);
-          upk(mul2(stash_dec2(c0.z), pk(a1.x, a1.y)), wb[4], wb[5]);
-          upk(mul2(stash_dec2(c0.w), pk(a1.z, a1.w)), wb[6], wb[7]);
-          upk(mul2(stash_dec2(c1.x), pk(a2.x, a2.y)), wb[8], wb[9]);
-          upk(mul2(stash_dec2(c1.y), pk(a2.z, a2.w)), wb[10], wb[11]);
-          upk(mul2(stash_dec2(c1.z), pk(a3.x, a3.y)), wb[12], wb[13]);
-          upk(mul2(stash_dec2(c1.w), pk(a3.z, a3.w)), wb[14], wb[15]);
-          st_split16<TERMS>(lane_addr + XH + col0, lane_addr + XL + col0, wb);
-        }
-        tmem_st_wait();
-        if (warp_arrive_last(cnt_a, 8, lane)) issue_vbar();
-        if (has_next && warp_arrive_last_plain(cnt_w, 8, lane) && lane == 0)   // the image is consumed: fetch the next one
-          bulk_load(sLW, g.st_w + (size_t)(t0 + kTileE) * 128, (uint32_t)min(kTileE, e_end - t0 - kTileE) * 128u, ldw);
-        // ---- edge data of the following tiles while vbar runs
-        uint32_t pr_nn = 0u;
-        if (has_next) {
-          prefetch_l1(gAb + (size_t)(pr_n >> 16) * 64 + 32 * ch);
-          if (t0 + 2 * kTileE + row < e_end) pr_nn = g.pair[t0 + 2 * kTileE + row];
-        }
-        mbar_wait(d_full, ph_d, 3);
-        __syncwarp();
-        ph_d ^= 1u;
-        fence_after_sync();
-        // ---- ubar = vbar * silu'(u) -> shared tile ; partial rbar = ubar . du over this thread's 32 channels
-        mbar_wait(ldu, ph_u, 4);
-        ph_u ^= 1u;
-        if (t0 > e_begin) {
-          mbar_wait(redR, ph_r, 5);   // the helpers have reduced the previous tile: the tile buffer is free
-          ph_r ^= 1u;
-        }
-        float racc = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = 32 * ch + 16 * c;
-          const uint32_t q0 = (uint32_t)(4 * ch + 2 * c);
-          uint32_t vr[16], dr[16];
-          tmem_ld16(lane_addr + ACC + col0, vr);
-          tmem_ld16(lane_addr + DU + col0, dr);
-          const uint4 c0 = *reinterpret_cast<const uint4*>(sLU + row * 128 + ((q0 ^ swz) << 4));
-          const uint4 c1 = *reinterpret_cast<const uint4*>(sLU + row * 128 + (((q0 + 1u) ^ swz) << 4));
-          const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          tmem_ld_wait();
-          float* urow = sU + row * kTileLd + col0;
-          f2_t rab = pk(0.0f, 0.0f);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const f2_t u01 = mul2(pk(__uint_as_float(vr[4 * j4 + 0]), __uint_as_float(vr[4 * j4 + 1])), stash_dec2(cw[2 * j4]));
-            const f2_t u23 = mul2(pk(__uint_as_float(vr[4 * j4 + 2]), __uint_as_float(vr[4 * j4 + 3])), stash_dec2(cw[2 * j4 + 1]));
-            rab = fma2(u01, pk(__uint_as_float(dr[4 * j4 + 0]), __uint_as_float(dr[4 * j4 + 1])), rab);
-            rab = fma2(u23, pk(__uint_as_float(dr[4 * j4 + 2]), __uint_as_float(dr[4 * j4 + 3])), rab);
-            float4 ub;
-            upk(u01, ub.x, ub.y);
-            upk(u23, ub.z, ub.w);
-            *reinterpret_cast<float4*>(urow + 4 * j4) = ub;
-          }
-          float ra, rb;
-          upk(rab, ra, rb);
-          racc += ra + rb;
-        }
-        if (has_next) {
-          if (warp_arrive_last(cnt_u, 12, lane)) issue_du();   // vbar / du drained (the helpers add the radial operand)
-          if (warp_arrive_last_plain(cnt_s, 8, lane) && lane == 0)
-            bulk_load(sLU, g.st_u + (size_t)(t0 + kTileE) * 128, (uint32_t)min(kTileE, e_end - t0 - kTileE) * 128u, ldu);
-        }
-        sPart[grp][ch][row] = racc;
-        warp_arrive_bar(tileB, lane);                  // this warp's part of the ubar tile is in shared memory
-        pr = pr_n;
-        pr_n = pr_nn;
-      }
-      mbar_wait(redR, ph_r, 6);                           // last tile reduced
-      ph_r ^= 1u;
-      sth_group_sync<H>(grp);
-    }
-  } else {
-    // =========================================== helper warps ===========================================
-    const int hw = (warp - 16) % H, ht = 32 * hw + lane;
-    // the four helper warps that prepare rows (keys, radial operand, pair adjoint) cover the four TMEM lane quarters
-    const bool prep = hw < 4;
-    const int wq = warp & 3, row = 32 * wq + lane;
-    const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-    uint32_t ph_b = 0;
-    int kidx = 0;
-    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit = s_next[grp]) {
-      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
-      const int atom0 = us.atom_base, natoms = us.n_tab;
-      const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
-      float* gPb = g.Pbar + (size_t)atom0 * 64;
-      auto qbar_rows = [&]() { return g.Qbar + (SPLIT ? (size_t)(unit % g.S) * g.qbar_stride : (size_t)0) + (size_t)atom0 * 64; };
-      float* tQb = QB_SM ? sTab : qbar_rows();
-      if (SPLIT) zero_rows_n(gPb + (size_t)us.a0 * 64, 64, us.a1 - us.a0, ht, kHT);   // the targets this unit owns
-      else zero_rows_n(gPb, 64, natoms, ht, kHT);
-      zero_rows_n(tQb, ld, natoms, ht, kHT);
-      if (e_begin >= e_end) {
-        sth_helper_sync<H>(grp);
-        if (QB_SM) copy_rows_n(qbar_rows(), 64, tQb, ld, natoms, ht, kHT);
-        sth_group_sync<H>(grp);
-        if (ht == 0) s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
-        sth_group_sync<H>(grp);
-        continue;
-      }
-      // ---- prologue: images, keys, segment lists and radial operand of the first tile; edge data of the second
-      if (ht == 0) {
-        const uint32_t nb = (uint32_t)min(kTileE, e_end - e_begin) * 128u;
-        bulk_load(sLW, g.st_w + (size_t)e_begin * 128, nb, ldw);
-        bulk_load(sLU, g.st_u + (size_t)e_begin * 128, nb, ldu);
-      }
-      uint32_t pr = 0u, pr_n = 0u;
-      float r = 0.3f, r_n = 0.3f;
-      uint8_t pm = (uint8_t)row, pm_n = (uint8_t)row;
-      bool valid = false;
-      TileKeys* tk = keys + kidx;
-      if (prep) {
-        valid = e_begin + row < e_end;
-        if (valid) {
-          pr = g.pair[e_begin + row];
-          r = g.r_e[e_begin + row];
-          pm = g.perm[e_begin + row];
-        }
-        if (e_begin + kTileE + row < e_end) {
-          pr_n = g.pair[e_begin + kTileE + row];
-          r_n = g.r_e[e_begin + kTileE + row];
-          pm_n = g.perm[e_begin + kTileE + row];
-        }
-        tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
-        tk->src[row] = valid ? (int)(pr & 0xFFFFu) : -1;
-        tk->perm[row] = pm;
-        float o[32], od[32];
-        rbf_regs<true>(r, g.inv_cutoff, o, od);
-        st_split24<TERMS>(lane_addr + XH, lane_addr + XL, od);   // X is free: the previous unit was closed by a barrier
-        tmem_st_wait();
-        if (warp_arrive_last(cnt_u, 12, lane)) issue_du();
-      }
-      sth_helper_sync<H>(grp);                       // keys of the first tile, zeroed tables
-      if (hw == H - 2) {
-        const int ns = build_segments<false>(tk->tgt, nullptr, tk->seg_t, min(kTileE, e_end - e_begin), lane);
-        if (lane == 0) {
-          tk->n_seg_t = ns;
-          tk->cont_prev = 0;
-        }
-      } else if (hw == H - 1) {
-        const int ns = build_segments<true>(tk->src, tk->perm, tk->seg_s, min(kTileE, e_end - e_begin), lane);
-        if (lane == 0) tk->n_seg_s = ns;
-      }
-      sth_group_sync<H>(grp);
-      if (ht == 0) s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
-
-      for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
-        const bool has_next = t0 + kTileE < e_end;
-        TileKeys* tkn = keys + (kidx + 1) % 3;
-        // ---- rows of the next tile: keys, edge data of the tile after it, radial derivative operand (registers)
-        bool valid_n = false;
-        uint32_t pr_nn = 0u;
-        float r_nn = 0.3f;
-        uint8_t pm_nn = (uint8_t)row;
-        float o_n[32], od_n[32];
-        size_t rslot = 0;
-        float rold = 0.0f;
-        if (prep) {
-          if (has_next) {
-            valid_n = t0 + kTileE + row < e_end;
-            tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
-            tkn->src[row] = valid_n ? (int)(pr_n & 0xFFFFu) : -1;
-            tkn->perm[row] = valid_n ? pm_n : (uint8_t)row;
-            if (t0 + 2 * kTileE + row < e_end) {
-              pr_nn = g.pair[t0 + 2 * kTileE + row];
-              r_nn = g.r_e[t0 + 2 * kTileE + row];
-              pm_nn = g.perm[t0 + 2 * kTileE + row];
-            }
-            rbf_regs<true>(r_n, g.inv_cutoff, o_n, od_n);
-          }
-          // slot of this row's edge in the dense pair-adjoint array; its previous value is fetched early (layers 2, 1 add)
-          if (valid) {
-            const int tg = (int)(pr >> 16), sr = (int)(pr & 0xFFFFu);
-            rslot = ((size_t)atom0 + tg) * g.N + (sr - (tg / g.N) * g.N);
-            if (g.rbar_accumulate) rold = g.rbar[rslot];
-          }
-        }
-        sth_helper_sync<H>(grp);   // keys of the next tile visible; every helper warp has finished the previous reduction
-        if (has_next) {
-          if (hw == H - 2) {
-            const int ns = build_segments<false>(tkn->tgt, nullptr, tkn->seg_t, min(kTileE, e_end - t0 - kTileE), lane);
-            if (lane == 0) {
-              tkn->n_seg_t = ns;
-              tkn->cont_prev = (tk->tgt[kTileE - 1] == tkn->tgt[0]) ? 1 : 0;
-            }
-          } else if (hw == H - 1) {
-            const int ns = build_segments<true>(tkn->src, tkn->perm, tkn->seg_s, min(kTileE, e_end - t0 - kTileE), lane);
-            if (lane == 0) tkn->n_seg_s = ns;
-          }
-          if (prep) {
-            // vbar of this tile is complete (its du completed before it): the X columns take the next radial operand
-            mbar_wait(d_full, 0u, 7);
-            mbar_wait(d_full, 1u, 8);
-            __syncwarp();
-            fence_after_sync();
-            st_split24<TERMS>(lane_addr + XH, lane_addr + XL, od_n);
-            tmem_st_wait();
-            if (warp_arrive_last(cnt_u, 12, lane)) issue_du();
-          }
-        }
-        // ---- this tile: pair adjoint of its rows, Pbar[tgt] += ubar, Qbar[src] += ubar
-        mbar_wait(tileB, ph_b, 9);
-        ph_b ^= 1u;
-        if (prep && valid) g.rbar[rslot] = rold + (sPart[grp][0][row] + sPart[grp][1][row]);   // channels 0..31 + 32..63
-        reduce_targets_global_n<H>(sU, tk, gPb, ht);
-        reduce_sources_table_n<H>(sU, tk, tQb, ld, ht);
-        warp_arrive_bar(redR, lane);
-        pr = pr_n;
-        r = r_n;
-        pm = pm_n;
-        valid = valid_n;
-        pr_n = pr_nn;
-        r_n = r_nn;
-        pm_n = pm_nn;
-        tk = tkn;
-        kidx = (kidx + 1) % 3;
-      }
-      sth_helper_sync<H>(grp);                       // the Qbar accumulator is complete
-      if (QB_SM) copy_rows_n(qbar_rows(), 64, tQb, ld, natoms, ht, kHT);
-      sth_group_sync<H>(grp);
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_slot, 512);
-}
-
 // Qbar = sum over the parts of a split replica, in part order (deterministic)
 __global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t n4, size_t stride4, int S) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -2099,24 +1634,6 @@ static int launch_bwd_st_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, u
   return 0;
 }
 
-template <int T, int TERMS, int H>
-static int launch_bwd_sth_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
-  constexpr int threads = kGroups * (256 + 32 * H);
-  if (g.S > 1) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_sth_kernel<T, TERMS, true, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_sth_kernel<T, TERMS, true, H><<<grid, threads, smem, st>>>(g, gb);
-  } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_sth_kernel<T, TERMS, false, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_sth_kernel<T, TERMS, false, H><<<grid, threads, smem, st>>>(g, gb);
-  }
-  return 0;
-}
-template <int H>
-static int launch_bwd_sth(Ctx* c, const EdgeTcArgs& g, int tab, int terms, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
-  if (tab == 1) return terms == 1 ? launch_bwd_sth_t<1, 1, H>(c, g, grid, smem, gb, st) : launch_bwd_sth_t<1, 3, H>(c, g, grid, smem, gb, st);
-  return terms == 1 ? launch_bwd_sth_t<0, 1, H>(c, g, grid, smem, gb, st) : launch_bwd_sth_t<0, 3, H>(c, g, grid, smem, gb, st);
-}
-
 // terms = 3: 3xTF32 (fp32-accurate, default); terms = 1: one TF32 product per contraction (GNNIS_FLAG_MLP_TF32X1).
 // stash = 1: also leave silu'(u), silu'(w) for edge_bwd_st_kernel (evaluations with forces, Ctx::stash_on).
 int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
@@ -2159,10 +1676,7 @@ int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, int stash,
     }
     const size_t smem = st_bwd_smem(c, tab);
     const uint32_t gb = (uint32_t)st_group_bytes(c, tab);
-    if (c->bwd_helpers == 4) rc = launch_bwd_sth<4>(c, g, tab, terms, grid, smem, gb, st);
-    else if (c->bwd_helpers == 6) rc = launch_bwd_sth<6>(c, g, tab, terms, grid, smem, gb, st);
-    else if (c->bwd_helpers == 8) rc = launch_bwd_sth<8>(c, g, tab, terms, grid, smem, gb, st);
-    else if (tab == 1) rc = terms == 1 ? launch_bwd_st_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_st_t<1, 3>(c, g, grid, smem, gb, st);
+    if (tab == 1) rc = terms == 1 ? launch_bwd_st_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_st_t<1, 3>(c, g, grid, smem, gb, st);
     else rc = terms == 1 ? launch_bwd_st_t<0, 1>(c, g, grid, smem, gb, st) : launch_bwd_st_t<0, 3>(c, g, grid, smem, gb, st);
   } else {
     const size_t smem = bwd_tc_smem(c);

@@ -292,6 +292,10 @@ class Engine:
                                                  self._stream()))
         return d
 
+    def describe(self) -> str:
+        """Which code path the current set-up runs on (tcgen05 / CUDA cores, stash / recompute, tables, split)."""
+        return self.lib.gnnis_describe(self._h).decode()
+
     def launch_count(self) -> int:
         return int(self.lib.gnnis_launch_count(self._h))
 

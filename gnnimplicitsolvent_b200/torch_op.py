@@ -33,8 +33,11 @@ def load() -> str:
 class ScriptableEnergy(torch.nn.Module):
     """forward(positions[, solvent_model, solvent_dielectric]) -> scalar energy (kJ/mol) with d/dpositions = -forces:
     TorchForce's default contract (`energy.backward()`, then `positions.grad`).  The two optional scalars are the
-    global parameters TorchForce appends (`helper_functions.py:784-785`); the solvent of every replica is fixed by
-    `Engine.set_replicas`, so they are accepted and ignored."""
+    global parameters TorchForce appends (`helper_functions.py:784-785`).  The solvent of every replica is fixed by
+    `Engine.set_replicas` when the module is scripted; the reference's run model switches ALL replicas to another
+    solvent when `solvent_model != -1` (GNN_Models.py:780-786) -- the scripted module cannot, so it raises instead of
+    returning energies for the wrong solvent (use the eager model's `forward(positions, solvent_model, dielectric)`
+    or script a model that was set up for that solvent)."""
 
     def __init__(self, handle: int, n_rep: int, flags: int = 0):
         super().__init__()
@@ -44,6 +47,10 @@ class ScriptableEnergy(torch.nn.Module):
 
     def forward(self, positions: torch.Tensor, solvent_model: Optional[torch.Tensor] = None,
                 solvent_dielectric: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if solvent_model is not None:
+            if int(solvent_model.item()) != -1:
+                raise RuntimeError("gnnis scripted module: the solvent_model override (!= -1) is not supported; "
+                                   "the solvents were fixed by set_num_reps when the module was scripted")
         return torch.ops.gnnis.energy(positions, self.handle, self.n_rep, self.flags).sum()
 
 
@@ -58,6 +65,10 @@ class ScriptableEnergyForces(torch.nn.Module):
 
     def forward(self, positions: torch.Tensor, solvent_model: Optional[torch.Tensor] = None,
                 solvent_dielectric: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if solvent_model is not None:
+            if int(solvent_model.item()) != -1:
+                raise RuntimeError("gnnis scripted module: the solvent_model override (!= -1) is not supported; "
+                                   "the solvents were fixed by set_num_reps when the module was scripted")
         e, f = torch.ops.gnnis.energy_force(positions, self.handle, self.n_rep, self.flags)
         return e.sum(), f
 

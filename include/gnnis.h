@@ -155,7 +155,11 @@ int gnnis_set_forcefield(gnnis_handle h, const gnnis_forcefield* ff);
  * OpenMM's LocalEnergyMinimizer, helper_functions.py:614-624; semantics differ by design: one optimiser
  * per replica, SURVEY.md §7 hard part 5).  pos_dev is updated in place.  Stops a replica when its
  * gradient RMS < grad_tol (kJ/mol/nm) or after max_iter iterations (0 = 1000).
- * status_dev [R] int32: 0 converged, 1 iteration limit, 2 non-finite energy/force (positions restored).
+ * status_dev [R] int32: 0 converged (gradient RMS below grad_tol), 1 iteration limit, 2 non-finite energy/force
+ * (positions restored), 3 stopped with a gradient RMS above grad_tol because the line search can no longer lower
+ * the energy at fp32 resolution (20 accepted steps without a gain, or a step below 2e-7 nm) -- the model's energy
+ * surface jumps wherever a pair crosses the 0.6 nm graph cutoff, so a replica can end on such a ledge; this is
+ * where OpenMM's minimizeEnergy(tolerance=1e-4) of the reference stops as well.
  * Optional harmonic bonds k/2 (r-r0)^2 given per molecule (n_bonds, bond_idx_host[2*n_bonds],
  * bond_r0_host, bond_k_host) stand in for the vacuum force field when testing. */
 int gnnis_set_bonds(gnnis_handle h, int32_t n_bonds, const int32_t* bond_idx_host,
@@ -185,6 +189,10 @@ int gnnis_umma_selftest(gnnis_handle h, const float* a_dev, const float* b_dev, 
 
 /* Number of kernels this library launched since the handle was created (bench.py's gpu_launches). */
 int64_t gnnis_launch_count(gnnis_handle h);
+/* One line saying which code path the current system / replica set-up runs on: replicas per unit, sub-unit split,
+ * tcgen05 or CUDA-core edge kernels (and why), adjoint from the activation stash or by recomputation (and why),
+ * shared-memory table mode, stash bytes.  The string belongs to the handle and is valid until the next call. */
+const char* gnnis_describe(gnnis_handle h);
 /* Time of the individual kernel families of the last gnnis_profile_eval call, in ms (order: see gnnis_stage_name) */
 int gnnis_profile_eval(gnnis_handle h, const float* pos_dev, float* e_rep_dev, float* force_dev, uint32_t flags,
                        void* stream, float* stage_ms_host, int32_t n_stages);

