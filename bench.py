@@ -163,6 +163,56 @@ def run_reference_arm(args):
     print(json.dumps(line), file=OUT, flush=True)
 
 
+def strong_scaling_block(eng_c2, mol, sd, world, rank, local_rank, dist, flush, n_eval=5):
+    from gnnimplicitsolvent_b200 import sharding, synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    from gnnimplicitsolvent_b200.helper_functions import SOLVENT_DICT
+    total = 39 * 512
+    lo, hi = sharding.shard_bounds(total, world, rank)
+    r3 = hi - lo
+    die_of = {v["solvent_id"]: v["dielectric"] for v in SOLVENT_DICT.values()}
+    sids = [r % 39 for r in range(lo, hi)]
+    eng = Engine(mol["params"], sd, device=local_rank)
+    eng.set_replicas(r3, sids, [die_of[s_] for s_ in sids])
+    pos = torch.from_numpy(synth.conformers(mol["pos"], total, 0.01, seed=777)[lo:hi].copy()).cuda()
+    e = torch.empty(r3, dtype=torch.float32, device="cuda")
+    f = torch.empty(r3, N_ATOMS, 3, dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        eng.energy_force(pos, out_energy=e, out_force=f)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_eval)]
+    for i in range(n_eval):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        eng.energy_force(pos, out_energy=e, out_force=f)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / n_eval
+    gather_us, checksum = 0.0, float(e.double().sum())
+    if dist:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sharding.gather_energies(e, total, world, rank)          # warm-up of the communicator
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0.record()
+        e_all = sharding.gather_energies(e, total, world, rank)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_us = g0.elapsed_time(g1) * 1e3
+        checksum = float(e_all.double().sum())
+        t = torch.tensor([ms, gather_us], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, gather_us = float(t[0]), float(t[1])
+    path = eng.describe()
+    eng.close()
+    return {"workload": "C3: N=50, 39 solvents x 512 conformers = 19968 replicas, sharded over the ranks (strong scaling)",
+            "replicas_total": total, "replicas_per_rank": r3, "ms_per_eval": ms, "atoms_evals_per_s": total * N_ATOMS / (ms * 1e-3),
+            "gather_us": gather_us, "unit_waves_per_rank": r3 / 296.0,
+            "energy_checksum": checksum, "path": path}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -287,6 +337,14 @@ def main():
     e_check = float(pin_e[(args.steps - 1) % 2].double().sum())
     t_e2e = time.perf_counter() - t0
 
+    # ---- strong scaling record (BASELINE.json configs[2], C3): 39 solvents x 512 conformers = 19 968 replicas sharded
+    # over the ranks, solvent id = replica mod 39; per evaluation max over ranks, plus the one collective of the path
+    strong = None
+    try:
+        strong = strong_scaling_block(eng, mol, sd, world, rank, local_rank, dist, flush)
+    except Exception as exc:  # noqa: BLE001 -- the headline line must not depend on this block
+        strong = {"error": str(exc)[:200]}
+
     t_all = torch.tensor([t_ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
@@ -300,37 +358,48 @@ def main():
         value = atoms_total * args.steps / (t_ms * 1e-3)
         e2e_value = atoms_total * args.steps / (t_e2e_ms * 1e-3)
         peaks, peak_kind = measured_peaks()
-        # dominant kernel family: edge adjoint (3 launches per evaluation, one per interaction layer).
-        # algorithmic FLOPs per launch (reference formulation, input-gradient only, no recompute counted):
-        #   layer l: 2 * E * (K_l*64 + 64*64), K = 26, 148, 148  (DESIGN.md "roofline accounting")
-        dom = max(stage_acc, key=stage_acc.get) if stage_acc else "edge_bwd"
-        e_per_launch = float(n_edges)
-        flops_edge = [2.0 * e_per_launch * (k_ * 64 + 64 * 64) for k_ in (26, 148, 148)]
-        if dom in ("edge_bwd", "edge_fwd"):
-            flops_launch = sum(flops_edge) / 3.0
-            dur_ms = stage_acc[dom] / 3.0
-        else:
-            flops_launch, dur_ms = float("nan"), stage_acc.get(dom, float("nan"))
-        achieved = flops_launch / (dur_ms * 1e-3) / 1e12
-        # the edge kernels issue tcgen05.mma.kind::tf32 (dense tf32 = half the bf16 rate): denominator = measured
-        # sustained bf16 cuBLAS TF/s / 2; the 3xTF32 split triples the executed tensor work on top
-        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))) / 2.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "edge_traffic.json")
+        # ---- roofline of the two edge kernel families (3 launches each per evaluation, one per interaction layer).
+        # Algorithmic work per launch (DESIGN.md 5 "roofline accounting", E = edges, n = atoms of the rank):
+        #   tensor: 2 * E * (K_l*64 + 64*64) FLOPs, K = 26, 148, 148 (reference formulation; the same count for the
+        #           forward and for the input-gradient adjoint; nothing the kernels recompute or triple is counted)
+        #   HBM:    forward 9 E (pair, r, perm) + 512 n (P, Q) read, 256 n (a) + 256 E (activation stash) written;
+        #           adjoint 256 E (stash) + 10 E + 256 n (abar) read, 512 n (Pbar, Qbar) + 4 E (rbar) written, + 4 E rbar read
+        # peak: tensor = measured sustained bf16 cuBLAS TF/s / 2 (dense kind::tf32 rate); HBM = measured copy GB/s
+        e_l, n_l = float(n_edges), float(R * N_ATOMS)
+        flops_launch = sum(2.0 * e_l * (k_ * 64 + 64 * 64) for k_ in (26, 148, 148)) / 3.0
+        stash_on = "adjoint=stash" in eng.describe()
+        bytes_launch = {"edge_fwd": e_l * (9 + (256 if stash_on else 0)) + n_l * 768,
+                        "edge_bwd": e_l * ((256 if stash_on else 0) + 18) + n_l * (1024 if stash_on else 1280)}
+        tpeak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))) / 2.0
+        hpeak = float(peaks.get("hbm_gbs"))
+        traffic_all = {}
+        tpath = os.path.join(ROOT, "profiles", "r2_edge_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if dom in tj and int(tj.get("replicas", 0)) == R:
-                traffic = tj[dom]
-        # explanatory only: tensor work the kernel EXECUTES per launch = 3 TF32 products per contraction; the adjoint
-        # runs u, du (K = 24) and w, vbar (K = 64) per tile, the forward u and w
-        k_exec = {"edge_bwd": 2 * 24 * 64 + 2 * 64 * 64, "edge_fwd": 24 * 64 + 64 * 64}.get(dom)
-        executed = 3 * 2.0 * e_per_launch * k_exec / (dur_ms * 1e-3) / 1e12 if k_exec else None
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic,
-                    "executed_tflops_3xtf32": executed, "executed_frac": executed / peak if executed else None,
-                    "peak_source": f"{peak_kind} bf16 sustained / 2 (kind::tf32 rate); kernel computes in 3xTF32",
-                    "algorithmic_flops_per_launch": flops_launch, "avg_launch_ms": dur_ms, "stage_ms": stage_acc}
+            if int(tj.get("replicas", 0)) == R:
+                traffic_all = tj
+
+        def roof(stage):
+            dur_ms = stage_acc[stage] / 3.0
+            tf = flops_launch / (dur_ms * 1e-3) / 1e12
+            gb = bytes_launch[stage] / (dur_ms * 1e-3) / 1e9
+            # the bound that binds is the one whose minimum time is longer
+            hbm_bound = bytes_launch[stage] / hpeak / 1e9 > flops_launch / tpeak / 1e12
+            r = {"kernel": stage, "bound": "hbm" if hbm_bound else "tensor", "avg_launch_ms": dur_ms,
+                 "achieved": gb if hbm_bound else tf, "peak": hpeak if hbm_bound else tpeak, "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                 "frac": (gb / hpeak) if hbm_bound else (tf / tpeak), "traffic": traffic_all.get(stage),
+                 "tensor_tflops": tf, "tensor_frac": tf / tpeak, "hbm_gbs": gb, "hbm_frac": gb / hpeak,
+                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch[stage]}
+            return r
+
+        dom = max(("edge_fwd", "edge_bwd"), key=lambda k_: stage_acc.get(k_, 0.0))
+        roofline = roof(dom)
+        roofline["peak_source"] = (f"{peak_kind}: HBM copy {hpeak:.0f} GB/s, bf16 sustained / 2 = {tpeak:.0f} TFLOP/s (kind::tf32 rate; "
+                                   "the kernels compute in 3xTF32)")
+        roofline["other"] = [roof("edge_bwd" if dom == "edge_fwd" else "edge_fwd")]
+        roofline["stage_ms"] = stage_acc
+        roofline["path"] = eng.describe()
         cpu_baseline = None
         if not args.no_cpu_baseline:
             import warnings
@@ -350,7 +419,7 @@ def main():
                     "d2h_bytes_per_step": R * N_ATOMS * 12 + R * 4, "ms_per_step": t_e2e_ms / args.steps, "energy_checksum": e_check,
                     "call": "gnnis_energy_force_host_submit / _wait (pinned host buffers, two calls in flight)"},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "parity": parity,
+            "parity": parity, "strong": strong,
         }
         print(json.dumps(line), file=OUT, flush=True)
     if dist:

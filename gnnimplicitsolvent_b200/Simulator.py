@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import os
 import tempfile
-import time
 from typing import Optional, Sequence
 
 import numpy as np
@@ -207,8 +206,10 @@ class Simulator:
 
     @property
     def hdf5_loc(self):
-        """Trajectory location (Simulator.py:405-417).  h5py is absent here: the file set written by
-        trajectory.TrajectoryWriter uses this path as its prefix; trajectory.export_mdtraj_h5 converts it."""
+        """Trajectory location (Simulator.py:405-417).  h5py is absent in this image: run_simulation writes the
+        trajectory as `<stub>_output.coordinates.npy` + `<stub>_output.meta.npz` (trajectory.TrajectoryWriter, same
+        dataset names and units as the MDTraj HDF5 file) and trajectory.export_mdtraj_h5 converts them to this path
+        where h5py exists."""
         return self._work_folder + self._file_stub() + "_output.h5"
 
     @property
@@ -229,27 +230,17 @@ class Simulator:
         elif workfolder == "TMPDIR":
             workfolder = os.environ["TMPDIR"] + "/"
         os.makedirs(workfolder, exist_ok=True)
-        prefix = workfolder + self._file_stub() + "_output.h5"
+        prefix = workfolder + self._file_stub()     # TrajectoryWriter: <prefix>_output.coordinates.npy / .meta.npz, <prefix>_log.txt
         do_min = bool(minimize and self._iteration == 0)
         if do_min:
             self.minimize()
-        t0 = time.perf_counter()
         trajectory.run_simulation(self._engine, self._positions, self._velocities, self._mol.masses, n_steps=n_steps,
                                   n_interval=n_interval, minimize=False, prefix=prefix, temperature=self._temperature,
                                   friction=self._friction, dt=self._dt, seed=self._random_number_seed,
                                   elements=self._mol.elements, n_constraints=self._n_constraints,
                                   first_step=self._steps_done, eval_flags=self._flags())
         self._steps_done += (n_steps // n_interval) * n_interval
-        self._write_log(workfolder + self._file_stub() + "_log.txt", prefix, time.perf_counter() - t0)
         return prefix
-
-    def _write_log(self, path, prefix, wall):
-        _, meta = trajectory.load_trajectory(prefix)
-        with open(path, "w") as f:
-            f.write('#"Step","Potential Energy (kJ/mole)","Temperature (K)","Speed (ns/day)"\n')
-            for i in range(len(meta["time"])):
-                f.write(f"{int(meta['step'][i])},{float(np.nansum(meta['potentialEnergy'][i]))},"
-                        f"{float(np.nanmean(meta['temperature'][i]))},{float(meta['ns_per_day'][i]):.3g}\n")
 
 
 class Multi_simulator(Simulator):

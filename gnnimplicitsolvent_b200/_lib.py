@@ -64,6 +64,7 @@ SIGNATURES = {
     "gnnis_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "gnnis_launch_count": (C.c_int64, [C.c_void_p]),
     "gnnis_describe": (C.c_char_p, [C.c_void_p]),
+    "gnnis_minimize_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnis_profile_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                      c_float_p, C.c_int32]),
     "gnnis_num_stages": (C.c_int32, []),
@@ -72,6 +73,7 @@ SIGNATURES = {
 
 FLAG_DELTA, FLAG_NO_FORCES, FLAG_GB_ONLY, FLAG_MLP_BF16, FLAG_MLP_CUDA_CORES = 0x1, 0x2, 0x4, 0x8, 0x10
 FLAG_MLP_TF32X1 = 0x80
+FLAG_MLP_FP16 = 0x100
 FLAG_DATA_PREDICATE = 0x20
 FLAG_VACUUM_ONLY = 0x40
 

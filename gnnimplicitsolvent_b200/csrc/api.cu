@@ -279,17 +279,18 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
     c->err = "force_dev is NULL but GNNIS_FLAG_NO_FORCES is not set";
     return -1;
   }
-  if (flags & GNNIS_FLAG_MLP_BF16) {
-    c->err = "GNNIS_FLAG_MLP_BF16: no bf16 MLP mode is offered -- already single-pass TF32 (GNNIS_FLAG_MLP_TF32X1) misses "
-             "the fp32 parity gates (DESIGN.md 5.1)";
-    return -3;
-  }
-  const int terms = (flags & GNNIS_FLAG_MLP_TF32X1) ? 1 : 3;
+  // arithmetic of the edge MLPs: 3 = 3xTF32 (default, fp32-accurate), 1 = one TF32 product, 2 = bf16 operands + tanh activations
+  const int terms = (flags & GNNIS_FLAG_MLP_BF16) ? 2 : ((flags & GNNIS_FLAG_MLP_FP16) ? 4 : ((flags & GNNIS_FLAG_MLP_TF32X1) ? 1 : 3));
   // tensor-core (tcgen05, 3xTF32) edge kernels unless the caller forces the CUDA-core path or the unit's tables
   // do not fit next to the staged weight operands
   const bool tc_ok = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && tc_path_fits(c);
   const bool tc_fwd = tc_ok && (c->tc_mask & 1), tc_bwd = tc_ok && (c->tc_mask & 2);
   const bool node_tc = !(flags & GNNIS_FLAG_MLP_CUDA_CORES) && (c->tc_mask & 4);
+  if ((terms == 2 || terms == 4) && !(tc_fwd && tc_bwd)) {
+    c->err = "GNNIS_FLAG_MLP_BF16 / _FP16 need the tensor-core edge kernels (not with GNNIS_FLAG_MLP_CUDA_CORES, GNNIS_TC masks, or "
+             "unit tables that do not fit next to the operand images)";
+    return -3;
+  }
   c->split_eff = (tc_fwd && tc_bwd && c->G == 1) ? c->split : 1;   // the CUDA-core edge kernels do not split replicas
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
@@ -381,6 +382,8 @@ int gnnis_create(gnnis_handle* out, int device) {
   if (const char* e = getenv("GNNIS_SPLIT")) c->split_max = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
   if (const char* e = getenv("GNNIS_STASH")) c->use_stash = atoi(e);      // 0: the edge adjoint always recomputes its activations
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
+  if (const char* e = getenv("GNNIS_LB_STALL")) c->lb_stall_limit = atoi(e) < 1 ? 1 : atoi(e);
+  if (const char* e = getenv("GNNIS_LB_MAXDISP")) c->lb_max_disp = (float)atof(e);
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;
@@ -398,7 +401,7 @@ int gnnis_destroy(gnnis_handle h) {
                  &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->abar, &c->Pbar, &c->Qbar, &c->rbar, &c->e_atom,
                  &c->sa_atom, &c->h_pos_dev, &c->h_e_dev, &c->h_f_dev, &c->bond_r0, &c->bond_k, &c->lb_S, &c->lb_Y,
                  &c->lb_rho, &c->lb_alpha, &c->lb_g, &c->lb_gprev, &c->lb_xprev, &c->lb_d, &c->lb_e, &c->lb_eprev,
-                 &c->lb_step, &c->lb_ftmp, &c->lb_etmp, &c->masses, &c->gamma_emb, &c->gbar, &c->lb_eref};
+                 &c->lb_step, &c->lb_ftmp, &c->lb_etmp, &c->masses, &c->gamma_emb, &c->gbar, &c->lb_eref, &c->lb_grms};
   for (float** p : f) dev_free(p);
   for (int l = 0; l < 3; ++l) {
     dev_free(&c->P[l]);
@@ -425,7 +428,7 @@ int gnnis_destroy(gnnis_handle h) {
   dev_free(&c->ff_term_ptr);
   dev_free(&c->ff_term_ref);
   int** ip[] = {&c->radidx, &c->solvent_id, &c->deg, &c->row_ptr, &c->blk_sum, &c->col, &c->bond_idx, &c->lb_state,
-                &c->lb_count, &c->lb_active, &c->lb_stall};
+                &c->lb_count, &c->lb_active, &c->lb_stall, &c->lb_nevals};
   for (int** p : ip) dev_free(p);
   dev_free(&c->pair);
   dev_free(&c->perm);
@@ -556,7 +559,7 @@ int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w) {
   }
   // tensor-core operand images (zero-filled: the padded K columns of Wr stay zero)
   {
-    const size_t per_layer = 81920 + 196608 + 131072 + 131072;
+    const size_t per_layer = 81920 + 196608 + 131072 + 131072 + 2 * 24576;
     if (dev_alloc(c, &c->img, 3 * per_layer)) return -1;
     GNNIS_CUDA_OK(cudaMemset(c->img, 0, 3 * per_layer));
     for (int l = 0; l < 3; ++l) {
@@ -565,6 +568,7 @@ int gnnis_load_weights(gnnis_handle h, const gnnis_weights* w) {
       c->img_nf[l] = base + 81920;
       c->img_nba[l] = base + 81920 + 196608;
       c->img_nbb[l] = base + 81920 + 196608 + 131072;
+      c->img_edge_bf[l] = base + 81920 + 196608 + 131072 + 131072;
     }
     if (build_edge_images(c, 0) || build_node_images(c, 0)) return -1;
     GNNIS_CUDA_OK(cudaDeviceSynchronize());

@@ -95,6 +95,7 @@ struct Ctx {
   // operands of every tcgen05 kernel, built once when the weights are loaded; kernels fetch them with cp.async.bulk
   uint8_t* img = nullptr;
   uint8_t *img_edge[3] = {nullptr, nullptr, nullptr};   // 80 KB: Wr | W2 | W2^T        (forward uses the first 48 KB)
+  uint8_t *img_edge_bf[3] = {nullptr, nullptr, nullptr};   // 24 KB: the same three operands as bf16 (GNNIS_FLAG_MLP_BF16)
   uint8_t *img_nf[3] = {nullptr, nullptr, nullptr};     // 192 KB: W3a | W4 | [Wi;Wj]    (last layer: first 64 KB)
   uint8_t *img_nba[3] = {nullptr, nullptr, nullptr};    // 128 KB: [Wi;Wj]^T | W4^T      (layers 1, 2)
   uint8_t *img_nbb[3] = {nullptr, nullptr, nullptr};    // 128 KB: W3a | W3a^T
@@ -179,7 +180,10 @@ struct Ctx {
   float *lb_S = nullptr, *lb_Y = nullptr, *lb_rho = nullptr, *lb_alpha = nullptr;
   float *lb_g = nullptr, *lb_gprev = nullptr, *lb_xprev = nullptr, *lb_d = nullptr, *lb_e = nullptr, *lb_eprev = nullptr;
   float *lb_step = nullptr, *lb_ftmp = nullptr, *lb_etmp = nullptr, *lb_eref = nullptr;
-  int *lb_state = nullptr, *lb_count = nullptr, *lb_active = nullptr, *lb_stall = nullptr;
+  int *lb_state = nullptr, *lb_count = nullptr, *lb_active = nullptr, *lb_stall = nullptr, *lb_nevals = nullptr;
+  float* lb_grms = nullptr;
+  float lb_max_disp = 0.03f;   // largest displacement of an atom coordinate per trial step, nm (GNNIS_LB_MAXDISP)
+  int lb_stall_limit = 20;     // accepted steps without an energy gain above the fp32 resolution that end a replica (GNNIS_LB_STALL)
   float* masses = nullptr;
   // distance constraints of the integrator (clusters of constrained atoms)
   int n_clusters = 0;

@@ -98,7 +98,10 @@ struct LbArgs {
   const float* et; // [R]    energies at the trial positions
   float *g, *d, *S, *Y, *rho, *alpha, *e, *step, *gd, *eref;
   int *state, *hist, *status, *n_active, *stall;
+  int* n_evals;     // [R] energy / force evaluations this replica took part in (gnnis_minimize_stats)
+  float* grms_out;  // [R] gradient RMS at the last accepted point
   float grad_tol, max_disp;
+  int stall_limit;
 };
 
 // one CTA per replica: accept / reject the trial point, update the history, build the next direction and trial.
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
   const size_t o = (size_t)r * D;
   int state = a.state[r];
   if (state == LB_DONE) return;
+  if (threadIdx.x == 0) a.n_evals[r] += 1;
   float* x = a.x + o;
   float* xt = a.xt + o;
   const float* ft = a.ft + o;
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
     gg = block_sum(gg, red);
     __syncthreads();
     float grms = sqrtf(gg / D);
+    if (threadIdx.x == 0) a.grms_out[r] = grms;
     bool stalled = false;
     if (state == LB_INIT) {
       if (threadIdx.x == 0) {
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
         a.stall[r] = 0;
       }
     } else {
-      stalled = st + 1 >= 20;
+      stalled = st + 1 >= a.stall_limit;
       if (threadIdx.x == 0) a.stall[r] = st + 1;
     }
     __syncthreads();
@@ -351,12 +356,14 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
   }
 }
 
-__global__ void lbfgs_init_kernel(int R, int* state, int* hist, int* status, int* n_active) {
+__global__ void lbfgs_init_kernel(int R, int* state, int* hist, int* status, int* n_active, int* n_evals, float* grms) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) {
     state[r] = LB_INIT;
     hist[r] = 0;
     status[r] = 1;
+    n_evals[r] = 0;
+    grms[r] = 0.0f;
   }
   if (r == 0) *n_active = R;
 }
@@ -658,7 +665,8 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
         dyn_alloc(c, &c->lb_ftmp, n3) || dyn_alloc(c, &c->lb_etmp, (size_t)R) || dyn_alloc(c, &c->lb_e, (size_t)R) ||
         dyn_alloc(c, &c->lb_step, (size_t)R) || dyn_alloc(c, &c->lb_eprev, (size_t)R) ||
         dyn_alloc(c, &c->lb_state, (size_t)R) || dyn_alloc(c, &c->lb_count, (size_t)R) || dyn_alloc(c, &c->lb_active, 1) ||
-        dyn_alloc(c, &c->lb_eref, (size_t)R) || dyn_alloc(c, &c->lb_stall, (size_t)R))
+        dyn_alloc(c, &c->lb_eref, (size_t)R) || dyn_alloc(c, &c->lb_stall, (size_t)R) ||
+        dyn_alloc(c, &c->lb_nevals, (size_t)R) || dyn_alloc(c, &c->lb_grms, (size_t)R))
       return -1;
     c->dyn_atoms = n3;
     c->dyn_hist = history;
@@ -685,9 +693,12 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
   a.hist = c->lb_count;
   a.status = status_dev;
   a.n_active = c->lb_active;
+  a.n_evals = c->lb_nevals;
+  a.grms_out = c->lb_grms;
   a.grad_tol = grad_tol;
-  a.max_disp = 0.03f;
-  lbfgs_init_kernel<<<(R + 127) / 128, 128, 0, st>>>(R, a.state, a.hist, a.status, a.n_active);
+  a.max_disp = c->lb_max_disp;
+  a.stall_limit = c->lb_stall_limit;
+  lbfgs_init_kernel<<<(R + 127) / 128, 128, 0, st>>>(R, a.state, a.hist, a.status, a.n_active, a.n_evals, a.grms_out);
   GNNIS_LAUNCH_CHECK();
   GNNIS_CUDA_OK(cudaMemcpyAsync(a.xt, pos_dev, n3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   uint32_t eflags = flags & ~GNNIS_FLAG_NO_FORCES;
@@ -714,6 +725,19 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
   GNNIS_CUDA_OK(cudaMemcpyAsync(e_rep_dev, a.e, R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   GNNIS_CUDA_OK(cudaStreamSynchronize(st));
   if (n_iter_host) *n_iter_host = it;
+  return 0;
+}
+
+int gnnis_minimize_stats(gnnis_handle h, int32_t* n_evals_dev, float* grad_rms_dev, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return -1;
+  if (!c->lb_nevals || c->dyn_atoms != (size_t)c->R * 3 * c->N) {
+    c->err = "gnnis_minimize_stats: no minimisation has run for the current replica set-up";
+    return -1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n_evals_dev) GNNIS_CUDA_OK(cudaMemcpyAsync(n_evals_dev, c->lb_nevals, c->R * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (grad_rms_dev) GNNIS_CUDA_OK(cudaMemcpyAsync(grad_rms_dev, c->lb_grms, c->R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

@@ -41,6 +41,15 @@ namespace gnnis {
 
 using namespace umma;
 
+// values of the TERMS template parameter that select the half-precision modes: 16-bit tensor-core operands
+// (tcgen05.mma.kind::f16, fp32 accumulate) and tanh-based activations.  kBf16: GNNIS_FLAG_MLP_BF16; kFp16: the same
+// kernels with fp16 operands (GNNIS_FLAG_MLP_FP16: 3 more mantissa bits; every operand of these MLPs fits fp16's range)
+constexpr int kBf16 = 2, kFp16 = 4;
+__host__ __device__ constexpr bool is_half(int terms) { return terms == kBf16 || terms == kFp16; }
+template <int TERMS>
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  return TERMS == kFp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
+}
 constexpr int kTabLd = 68;        // padded row of the shared-memory node tables (bank spread for row-per-lane gathers)
 constexpr int kGroups = 2;
 
@@ -89,6 +98,14 @@ template <int S0, int S1, int TERMS = 3>
 __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_addr,
                                                   uint32_t b_lo_addr, int b_rows, uint32_t idesc, uint32_t accumulate) {
   uint32_t acc = accumulate;
+  if (is_half(TERMS)) {   // 16-bit operands (kind::f16): K = 8 (S1 - S0) in steps of 16 = 8 TMEM columns / 32 bytes of the B row
+#pragma unroll
+    for (int s = 0; s < (S1 - S0 + 1) / 2; ++s) {
+      mma_bf16_ts(d_tmem, a_hi + 8u * (uint32_t)s, smem_desc_k_sw128(b_hi_addr + 32u * (uint32_t)s), idesc, acc);
+      acc = 1;
+    }
+    return;
+  }
 #pragma unroll
   for (int term = 0; term < TERMS; ++term) {   // TERMS = 1: single TF32 product (opt-in reduced-precision mode)
     const uint32_t a = term == 2 ? a_lo : a_hi;
@@ -167,6 +184,15 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
 // radial operand rows: only the 24 columns that the K = 24 products read (20 basis functions + 4 zeros)
 template <int TERMS = 3>
 __device__ __forceinline__ void st_split24(uint32_t t_hi, uint32_t t_lo, const float (&x)[32]) {
+  if (is_half(TERMS)) {   // 24 values -> 12 words of two bf16 / fp16, padded with zeros to K = 32
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) w[j] = pack_half2<TERMS>(x[2 * j], x[2 * j + 1]);
+#pragma unroll
+    for (int j = 12; j < 16; ++j) w[j] = 0u;
+    tmem_st16(t_hi, w);
+    return;
+  }
   if (TERMS == 1) {   // single-product mode: the raw fp32 words (kind::tf32 reads their top 19 bits), no lo part
     uint32_t h[16], h8[8];
 #pragma unroll
@@ -326,7 +352,7 @@ int st_bwd_tables(const Ctx* c) {
 }
 
 // ---------------------------------------------------------------------------------------------- launchers
-static EdgeTcArgs make_tc_args(Ctx* c, int l) {
+static EdgeTcArgs make_tc_args(Ctx* c, int l, int terms = 3) {
   EdgeTcArgs g{};
   g.n_units = c->n_units * c->split_eff;
   g.S = c->split_eff;
@@ -339,7 +365,7 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   g.pair = c->pair;
   g.r_e = c->r_e;
   g.inv_cutoff = (float)(1.0 / (double)c->cutoff);
-  g.img = c->img_edge[l];
+  g.img = terms == kBf16 ? c->img_edge_bf[l] : (terms == kFp16 ? c->img_edge_bf[l] + 24576 : c->img_edge[l]);
   g.b2 = c->L[l].b2;
   g.P = c->P[l];
   g.Q = c->Q[l];
@@ -355,8 +381,27 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l) {
   return g;
 }
 
+// bf16 image of a K-major operand block (element (n, k) = src[n * ld_n + k], round to nearest even; the image is
+// zero-filled beforehand, so padded K columns stay zero)
+__global__ void build_operand_image_bf16_kernel(uint8_t* __restrict__ img, const float* __restrict__ src, int rows_total,
+                                                int nrows, int kcount, int ld_n, int fp16) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nrows * kcount; t += gridDim.x * blockDim.x) {
+    int n = t / kcount, k = t - n * kcount;
+    const float v = src[(size_t)n * ld_n + k];
+    const uint32_t w = fp16 ? pack_f16x2(v, 0.0f) : pack_bf16x2(v, 0.0f);
+    *reinterpret_cast<uint16_t*>(img + sw128_offset_bf16(n, k, rows_total)) = (uint16_t)(w & 0xFFFFu);
+  }
+}
+
 int build_edge_images(Ctx* c, cudaStream_t st) {
   for (int l = 0; l < 3; ++l) {
+    for (int fp16 = 0; fp16 < 2; ++fp16) {   // half-precision modes: Wr | W2 | W2^T, 8 KB each, as bf16 and as fp16
+      uint8_t* bf = c->img_edge_bf[l] + (size_t)fp16 * 24576;
+      build_operand_image_bf16_kernel<<<32, 256, 0, st>>>(bf, c->L[l].Wr, 64, 64, kRbf, kRbf, fp16);
+      build_operand_image_bf16_kernel<<<32, 256, 0, st>>>(bf + 8192, c->L[l].W2, 64, 64, 64, 64, fp16);
+      build_operand_image_bf16_kernel<<<32, 256, 0, st>>>(bf + 16384, c->L[l].W2_t, 64, 64, 64, 64, fp16);
+      GNNIS_LAUNCH_CHECK();
+    }
     uint8_t* im = c->img_edge[l];
     if (launch_build_operand(c, im, im + 8192, c->L[l].Wr, 64, 0, 64, 0, kRbf, kRbf, st) ||
         launch_build_operand(c, im + 16384, im + 32768, c->L[l].W2, 64, 0, 64, 0, 64, 64, st) ||
@@ -440,6 +485,19 @@ __device__ __forceinline__ void st_split16(uint32_t t_hi, uint32_t t_lo, const f
   }
   tmem_st16(t_hi, h);
   tmem_st16(t_lo, l);
+}
+// 16 channels [col0, col0 + 16) of an A operand row: hi / lo TF32 words at base + col0 (one TMEM column per channel),
+// or 8 words of two bf16 at base + col0 / 2 in the bf16 mode
+template <int TERMS>
+__device__ __forceinline__ void st_operand16(uint32_t lane_addr, uint32_t base_hi, uint32_t base_lo, int col0, const float (&x)[16]) {
+  if (is_half(TERMS)) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_half2<TERMS>(x[2 * j], x[2 * j + 1]);
+    tmem_st8(lane_addr + base_hi + (uint32_t)(col0 >> 1), w);
+  } else {
+    st_split16<TERMS>(lane_addr + base_hi + col0, lane_addr + base_lo + col0, x);
+  }
 }
 __device__ __forceinline__ void copy_rows_n(float* __restrict__ dst, int ld_dst, const float* __restrict__ src,
                                             int ld_src, int nrows, int t0, int nthreads) {
@@ -609,7 +667,9 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   __shared__ uint32_t tmem_slot;
   uint32_t base = smem_u32(smraw);
   uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
-  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + 16384, *sW2L = sm + 32768;
+  // operand images: 3xTF32 / TF32: Wr hi | lo | W2 hi | lo (48 KB); bf16 mode: Wr | W2 (8 KB each, no lo parts)
+  constexpr bool BF = is_half(TERMS);
+  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + (BF ? 8192 : 16384), *sW2L = sm + 32768;
   float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -624,7 +684,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   __shared__ uint64_t ibar;
   if (tid == 0) {
     mbar_init(&ibar, 1);
-    bulk_copy_image(sm, g.img, kFwdWeights, &ibar);   // B[n = c][k] = Wr[c][k] and W2[c][k], hi | lo
+    bulk_copy_image(sm, g.img, BF ? 16384u : kFwdWeights, &ibar);   // B[n = c][k] = Wr[c][k] and W2[c][k], hi | lo
   }
   if (tid < 64) sb2[tid] = g.b2[tid];
   fence_proxy_async_smem();
@@ -634,7 +694,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   mbar_wait(&ibar, 0);
   __syncwarp();
   constexpr uint32_t VH = 128, VL = 192;
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+  constexpr uint32_t idesc64 = TERMS == kFp16 ? idesc_fp16(128, 64) : (BF ? idesc_bf16(128, 64) : idesc_tf32(128, 64));
 
   if (warp == 2 * 8) {
     // ===================================== MMA issuer =====================================
@@ -783,7 +843,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               float d[4];
-              silu_fd4_sum3(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], d);
+              if (BF) silu_fd4_sum3_tanh(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], d);
+              else silu_fd4_sum3(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], d);
               code[2 * j4] = stash_enc2(d[0], d[1]);
               code[2 * j4 + 1] = stash_enc2(d[2], d[3]);
             }
@@ -794,14 +855,14 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           } else {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 y = silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
+              const float4 y = BF ? silu4_sum3_tanh(&ur[4 * j4], p[j4], q[j4]) : silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
               v[4 * j4 + 0] = y.x;
               v[4 * j4 + 1] = y.y;
               v[4 * j4 + 2] = y.z;
               v[4 * j4 + 3] = y.w;
             }
           }
-          st_split16<TERMS>(lane_addr + VH + col0, lane_addr + VL + col0, v);
+          st_operand16<TERMS>(lane_addr, VH, VL, col0, v);
         }
         tmem_st_wait();
         if (STASH) fence_proxy_async_smem();           // the image rows are read by the bulk store below
@@ -856,8 +917,13 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               float z[8], d[8];
-              silu_fd4_sum2(&wr[8 * j8], bb[2 * j8], z, d);
-              silu_fd4_sum2(&wr[8 * j8 + 4], bb[2 * j8 + 1], z + 4, d + 4);
+              if (BF) {
+                silu_fd4_sum2_tanh(&wr[8 * j8], bb[2 * j8], z, d);
+                silu_fd4_sum2_tanh(&wr[8 * j8 + 4], bb[2 * j8 + 1], z + 4, d + 4);
+              } else {
+                silu_fd4_sum2(&wr[8 * j8], bb[2 * j8], z, d);
+                silu_fd4_sum2(&wr[8 * j8 + 4], bb[2 * j8 + 1], z + 4, d + 4);
+              }
               *reinterpret_cast<float4*>(zrow + 8 * j8) = make_float4(z[0], z[1], z[2], z[3]);
               *reinterpret_cast<float4*>(zrow + 8 * j8 + 4) = make_float4(z[4], z[5], z[6], z[7]);
               *reinterpret_cast<uint4*>(img + ((((uint32_t)(4 * ch + j8)) ^ swz) << 4)) =
@@ -868,7 +934,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 b = bb[j4];
-              const float4 z = silu4_sum2(&wr[4 * j4], b);
+              const float4 z = BF ? silu4_sum2_tanh(&wr[4 * j4], b) : silu4_sum2(&wr[4 * j4], b);
               *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
             }
           }
@@ -1084,7 +1150,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
           for (int j4 = 0; j4 < 4; ++j4) {
             silu_fd4_sum3(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], &dsu[16 * c + 4 * j4]);
           }
-          st_split16<TERMS>(lane_addr + XH + col0, lane_addr + XL + col0, v);
+          st_operand16<TERMS>(lane_addr, XH, XL, col0, v);
         }
         tmem_st_wait();
         if (warp_arrive_last(cnt_a, 8, lane)) issue_x(aW2H, aW2L);              // w = v . W2^T
@@ -1117,7 +1183,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
             wb[4 * j4 + 2] = sd.z;
             wb[4 * j4 + 3] = sd.w;
           }
-          st_split16<TERMS>(lane_addr + XH + col0, lane_addr + XL + col0, wb);
+          st_operand16<TERMS>(lane_addr, XH, XL, col0, wb);
         }
         tmem_st_wait();
         if (warp_arrive_last(cnt_a, 8, lane)) issue_x(aW2tH, aW2tL);            // vbar = wbar . W2
@@ -1278,7 +1344,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
   __shared__ uint64_t ibar;
   uint32_t base = smem_u32(smraw);
   uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
-  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2tH = sm + 16384, *sW2tL = sm + 32768;
+  // operand images: Wr hi | lo | W2^T hi | lo (48 KB), or in the bf16 mode Wr | W2^T (8 KB each)
+  constexpr bool BF = is_half(TERMS);
+  uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2tH = sm + (BF ? 8192 : 16384), *sW2tL = sm + 32768;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -1296,13 +1364,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
     }
     mbar_init(&ibar, 1);
     // operand image (build_edge_images): Wr hi | lo at 0, W2^T hi | lo at 48 KB
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&ibar)), "r"(kStWeights) : "memory");
+    // (build_edge_images) 3xTF32 image: Wr at 0 (16 KB), W2^T at 48 KB (32 KB); bf16 image: Wr at 0, W2^T at 16 KB (8 KB each)
+    const uint32_t n_wr = BF ? 8192u : 16384u, n_w2t = BF ? 8192u : 32768u, off_w2t = BF ? 16384u : 49152u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&ibar)), "r"(n_wr + n_w2t) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm)),
-                 "l"(g.img), "r"(16384u), "r"(smem_u32(&ibar))
+                 "l"(g.img), "r"(n_wr), "r"(smem_u32(&ibar))
                  : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(sm + 16384)),
-                 "l"(g.img + 49152), "r"(32768u), "r"(smem_u32(&ibar))
+                     smem_u32(sm + n_wr)),
+                 "l"(g.img + off_w2t), "r"(n_w2t), "r"(smem_u32(&ibar))
                  : "memory");
   }
   fence_proxy_async_smem();
@@ -1312,7 +1382,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
   mbar_wait(&ibar, 0);
   __syncwarp();
   constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
-  constexpr uint32_t idesc64 = idesc_tf32(128, 64);
+  constexpr uint32_t idesc64 = TERMS == kFp16 ? idesc_fp16(128, 64) : (BF ? idesc_bf16(128, 64) : idesc_tf32(128, 64));
 
   const int grp = tid >> 8, gt = tid & 255, w8 = gt >> 5, wq = w8 & 3, ch = w8 >> 2, row = 32 * wq + lane;
   uint8_t* gsm = sm + kStWeights + 256 + (size_t)grp * grp_bytes;
@@ -1444,7 +1514,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
         upk(mul2(stash_dec2(c1.y), pk(a2.z, a2.w)), wb[10], wb[11]);
         upk(mul2(stash_dec2(c1.z), pk(a3.x, a3.y)), wb[12], wb[13]);
         upk(mul2(stash_dec2(c1.w), pk(a3.z, a3.w)), wb[14], wb[15]);
-        st_split16<TERMS>(lane_addr + XH + col0, lane_addr + XL + col0, wb);
+        st_operand16<TERMS>(lane_addr, XH, XL, col0, wb);
       }
       tmem_st_wait();
       if (warp_arrive_last(cnt_a, 8, lane)) issue_vbar();
@@ -1636,8 +1706,24 @@ static int launch_bwd_st_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, u
 
 // terms = 3: 3xTF32 (fp32-accurate, default); terms = 1: one TF32 product per contraction (GNNIS_FLAG_MLP_TF32X1).
 // stash = 1: also leave silu'(u), silu'(w) for edge_bwd_st_kernel (evaluations with forces, Ctx::stash_on).
+// dispatch on the tensor-core arithmetic of the forward kernels: 3 = 3xTF32, 1 = TF32, kBf16 / kFp16 = 16-bit operands + tanh activations
+template <int T, bool STASH>
+static int launch_fwd_terms(Ctx* c, const EdgeTcArgs& g, int terms, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
+  if (terms == kBf16) return launch_fwd_t<T, kBf16, STASH>(c, g, grid, smem, gb, st);
+  if (terms == kFp16) return launch_fwd_t<T, kFp16, STASH>(c, g, grid, smem, gb, st);
+  if (terms == 1) return launch_fwd_t<T, 1, STASH>(c, g, grid, smem, gb, st);
+  return launch_fwd_t<T, 3, STASH>(c, g, grid, smem, gb, st);
+}
+template <int T>
+static int launch_bwd_st_terms(Ctx* c, const EdgeTcArgs& g, int terms, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
+  if (terms == kBf16) return launch_bwd_st_t<T, kBf16>(c, g, grid, smem, gb, st);
+  if (terms == kFp16) return launch_bwd_st_t<T, kFp16>(c, g, grid, smem, gb, st);
+  if (terms == 1) return launch_bwd_st_t<T, 1>(c, g, grid, smem, gb, st);
+  return launch_bwd_st_t<T, 3>(c, g, grid, smem, gb, st);
+}
+
 int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
-  EdgeTcArgs g = make_tc_args(c, l);
+  EdgeTcArgs g = make_tc_args(c, l, terms);
   const int grid = tc_grid(c);
   int rc;
   if (stash) {
@@ -1648,15 +1734,15 @@ int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
     }
     const size_t smem = st_fwd_smem(c, tab);
     const uint32_t gb = (uint32_t)st_group_bytes(c, tab);
-    if (tab == 2) rc = terms == 1 ? launch_fwd_t<2, 1, true>(c, g, grid, smem, gb, st) : launch_fwd_t<2, 3, true>(c, g, grid, smem, gb, st);
-    else if (tab == 1) rc = terms == 1 ? launch_fwd_t<1, 1, true>(c, g, grid, smem, gb, st) : launch_fwd_t<1, 3, true>(c, g, grid, smem, gb, st);
-    else rc = terms == 1 ? launch_fwd_t<0, 1, true>(c, g, grid, smem, gb, st) : launch_fwd_t<0, 3, true>(c, g, grid, smem, gb, st);
+    if (tab == 2) rc = launch_fwd_terms<2, true>(c, g, terms, grid, smem, gb, st);
+    else if (tab == 1) rc = launch_fwd_terms<1, true>(c, g, terms, grid, smem, gb, st);
+    else rc = launch_fwd_terms<0, true>(c, g, terms, grid, smem, gb, st);
   } else {
     const size_t smem = fwd_tc_smem(c);
     const uint32_t gb = (uint32_t)group_bytes(c);
-    if (c->tab_mode == 2) rc = terms == 1 ? launch_fwd_t<2, 1, false>(c, g, grid, smem, gb, st) : launch_fwd_t<2, 3, false>(c, g, grid, smem, gb, st);
-    else if (c->tab_mode == 1) rc = terms == 1 ? launch_fwd_t<1, 1, false>(c, g, grid, smem, gb, st) : launch_fwd_t<1, 3, false>(c, g, grid, smem, gb, st);
-    else rc = terms == 1 ? launch_fwd_t<0, 1, false>(c, g, grid, smem, gb, st) : launch_fwd_t<0, 3, false>(c, g, grid, smem, gb, st);
+    if (c->tab_mode == 2) rc = launch_fwd_terms<2, false>(c, g, terms, grid, smem, gb, st);
+    else if (c->tab_mode == 1) rc = launch_fwd_terms<1, false>(c, g, terms, grid, smem, gb, st);
+    else rc = launch_fwd_terms<0, false>(c, g, terms, grid, smem, gb, st);
   }
   if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
@@ -1664,7 +1750,8 @@ int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
 }
 
 int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, int stash, cudaStream_t st) {
-  EdgeTcArgs g = make_tc_args(c, l);
+  if (!stash && is_half(terms)) terms = 1;   // the recomputing adjoint has no 16-bit form: single-pass TF32 products instead
+  EdgeTcArgs g = make_tc_args(c, l, terms);
   g.rbar_accumulate = rbar_accumulate;
   const int grid = tc_grid(c);
   int rc;
@@ -1676,8 +1763,8 @@ int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, int stash,
     }
     const size_t smem = st_bwd_smem(c, tab);
     const uint32_t gb = (uint32_t)st_group_bytes(c, tab);
-    if (tab == 1) rc = terms == 1 ? launch_bwd_st_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_st_t<1, 3>(c, g, grid, smem, gb, st);
-    else rc = terms == 1 ? launch_bwd_st_t<0, 1>(c, g, grid, smem, gb, st) : launch_bwd_st_t<0, 3>(c, g, grid, smem, gb, st);
+    if (tab == 1) rc = launch_bwd_st_terms<1>(c, g, terms, grid, smem, gb, st);
+    else rc = launch_bwd_st_terms<0>(c, g, terms, grid, smem, gb, st);
   } else {
     const size_t smem = bwd_tc_smem(c);
     const uint32_t gb = (uint32_t)group_bytes(c);

@@ -139,6 +139,19 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with bf16 operands, fp32 accumulate, A and B K-major, M x N tile (K = 16 per instruction)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// the same with fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t idesc_fp16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of bf16 element (row n, k) inside a K-major SW128 operand with `rows` rows (panel = 64 bf16 of K)
+__host__ __device__ __forceinline__ uint32_t sw128_offset_bf16(int n, int k, int rows) {
+  return (uint32_t)(k >> 6) * (uint32_t)rows * 128u + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
+         ((((uint32_t)(k & 63) >> 3) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(k & 7) * 2u;
+}
 // byte offset of element (row n, k) inside a K-major SW128 operand with `rows` rows (panel = 32 fp32 of K)
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int n, int k, int rows) {
   return (uint32_t)(k >> 5) * (uint32_t)rows * 128u + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
@@ -155,6 +168,31 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       :
       : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem] with bf16 operands: A holds two consecutive K elements per 32-bit TMEM column (low
+// half = lower k), 16 K elements = 8 columns per instruction
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// two fp32 -> one word of two bf16 (round to nearest even): low half = a (the lower k / channel), high half = b
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 // ---- TMEM <-> registers: 32 lanes x 32 columns per warp (thread = lane, 32 consecutive columns) -----------------

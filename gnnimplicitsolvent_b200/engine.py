@@ -180,7 +180,7 @@ class Engine:
 
     # ------------------------------------------------------------------ hot path
     def energy_force(self, positions: torch.Tensor, *, delta=False, forces=True, gb_only=False, cuda_cores=False,
-                     data_predicate=False, vacuum_only=False, tf32x1=False, bf16=False, extra_flags: int = 0,
+                     data_predicate=False, vacuum_only=False, tf32x1=False, bf16=False, fp16=False, extra_flags: int = 0,
                      out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
         """positions [R,N,3] (or [R*N,3]) fp32 on the engine's device -> (E[R], F[R,N,3] or None)."""
         p = self._pos(positions)
@@ -191,7 +191,7 @@ class Engine:
         flags = ((_lib.FLAG_DELTA if delta else 0) | (0 if forces else _lib.FLAG_NO_FORCES)
                  | (_lib.FLAG_GB_ONLY if gb_only else 0) | (_lib.FLAG_MLP_CUDA_CORES if cuda_cores else 0)
                  | (_lib.FLAG_DATA_PREDICATE if data_predicate else 0) | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0)
-                 | (_lib.FLAG_MLP_TF32X1 if tf32x1 else 0) | (_lib.FLAG_MLP_BF16 if bf16 else 0) | int(extra_flags))
+                 | (_lib.FLAG_MLP_TF32X1 if tf32x1 else 0) | (_lib.FLAG_MLP_BF16 if bf16 else 0) | (_lib.FLAG_MLP_FP16 if fp16 else 0) | int(extra_flags))
         self._check(self.lib.gnnis_energy_force(self._h, p.data_ptr(), e.data_ptr(), f.data_ptr() if forces else None,
                                                 flags, self._stream()))
         return e, f
@@ -271,6 +271,13 @@ class Engine:
         self._check(self.lib.gnnis_minimize(self._h, p.data_ptr(), e.data_ptr(), status.data_ptr(), C.byref(nit),
                                             float(grad_tol), int(max_iter), int(history), flags, self._stream()))
         return p, e, status, int(nit.value)
+
+    def minimize_stats(self):
+        """(evaluations[R] int32, gradient RMS[R] float32) of the last `minimize` call, per replica."""
+        n = torch.empty(self.n_rep, dtype=torch.int32, device=self.device)
+        g = torch.empty(self.n_rep, dtype=torch.float32, device=self.device)
+        self._check(self.lib.gnnis_minimize_stats(self._h, n.data_ptr(), g.data_ptr(), self._stream()))
+        return n, g
 
     def langevin(self, positions: torch.Tensor, velocities: torch.Tensor, masses, n_steps: int, *, temperature=300.0,
                  friction=1.0, dt=0.002, seed=0, first_step=0, delta=False, gb_only=False, vacuum_only=False):

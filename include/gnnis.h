@@ -30,8 +30,15 @@ typedef struct gnnis_ctx* gnnis_handle;
                                       polar energy = E_GB(B') - E_GB(B)                                    */
 #define GNNIS_FLAG_NO_FORCES 0x2u  /* energy only (skips the adjoint pass)                                */
 #define GNNIS_FLAG_GB_ONLY 0x4u    /* plain GB-Neck2 (GNN_GBNeck_2, GNN_Models.py:173): B' = B, no SA term */
-#define GNNIS_FLAG_MLP_BF16 0x8u   /* reserved, returns -3: no bf16 MLP mode (single-pass TF32 already misses the fp32
-                                      parity gates)                                         */
+#define GNNIS_FLAG_MLP_BF16 0x8u   /* opt-in bf16 mode of the edge MLPs (the "bf16 MLP mode" of the north star): the
+                                      per-edge contractions run as tcgen05.mma.kind::f16 with bf16 operands (fp32
+                                      accumulate) and the SiLU activations come from MUFU.TANH (tanh.approx.f32) instead
+                                      of ex2 + rcp.  Accuracy is stated separately and is NOT inside the fp32 gates
+                                      (tests/test_gpu_parity.py::test_bf16_mode); needs the tensor-core
+                                      edge kernels (-3 otherwise); never used for the benchmark's headline number */
+#define GNNIS_FLAG_MLP_FP16 0x100u  /* the same kernels as GNNIS_FLAG_MLP_BF16 with fp16 operands (three more mantissa bits at
+                                      the same speed; the operands of these MLPs -- activations, radial basis, adjoints,
+                                      weights -- fit fp16's range).  Accuracy stated in test_half_precision_modes           */
 #define GNNIS_FLAG_MLP_TF32X1 0x80u /* opt-in reduced-precision mode of the edge MLPs: ONE TF32 product per contraction
                                       instead of the fp32-accurate 3xTF32 default.  Accuracy is stated separately
                                       (tests/test_gpu_parity.py::test_tf32x1_mode: energies ~1e-3, forces ~1e-2 rel);
@@ -166,6 +173,10 @@ int gnnis_set_bonds(gnnis_handle h, int32_t n_bonds, const int32_t* bond_idx_hos
                     const float* bond_r0_host, const float* bond_k_host);
 int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* status_dev, int32_t* n_iter_host,
                    float grad_tol, int32_t max_iter, int32_t history, uint32_t flags, void* stream);
+
+/* Per-replica record of the last gnnis_minimize call: number of energy / force evaluations the replica took part in
+ * until it stopped, and the gradient RMS (kJ/mol/nm) at its final accepted point.  Either pointer may be NULL. */
+int gnnis_minimize_stats(gnnis_handle h, int32_t* n_evals_dev, float* grad_rms_dev, void* stream);
 
 /* Batched LangevinMiddle integrator (replaces LangevinMiddleIntegrator(T, gamma, dt) + simulation.step,
  * helper_functions.py:787-789, Simulator.py:402).  masses_host [N] (amu), temperature K, friction 1/ps,

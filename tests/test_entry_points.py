@@ -157,7 +157,7 @@ def test_run_simulation_writes_trajectory_and_log(tmp_path):
     assert xyz.shape[0] == 4 and np.all(np.isfinite(np.asarray(xyz)))
     log = open(sim.log_loc).read().strip().splitlines()
     assert len(log) == 5 and log[0].startswith('#"Step"')
-    assert sim.hdf5_loc == prefix
+    assert sim.hdf5_loc == prefix + "_output.h5" and sim.log_loc == prefix + "_log.txt"
 
 
 @pytest.mark.gpu

@@ -96,9 +96,10 @@ def test_minimize_with_forcefield(weights):
     assert bool((e1 < e0).all()) and int((status == 2).sum()) == 0
     g0 = f0.reshape(64, -1).pow(2).mean(1).sqrt()
     g1 = f1.reshape(64, -1).pow(2).mean(1).sqrt()
-    # status 0 = gradient RMS below the threshold, or the line search stalled within 20x of it: the model's energy
-    # surface is discontinuous wherever a pair crosses the 0.6 nm graph cutoff (messages do not vanish there, in the
-    # reference as here), so a replica can end on such a step
-    assert int((status == 0).sum()) >= 48
-    assert bool((g1[status == 0] < 200.0).all()) and float(g0.min()) > 1000.0
+    # status 0 = gradient RMS below the threshold; status 3 = the line search can no longer lower the energy: the model's
+    # energy surface jumps by up to a few kJ/mol wherever a pair crosses the 0.6 nm graph cutoff (messages do not vanish
+    # there, in the reference as here), and a replica whose descent direction crosses such a ledge upwards stops on it
+    assert bool((g1[status == 0] < 10.0).all())
+    assert int(((status == 0) | (status == 3)).sum()) >= 56
+    assert float(g1.median()) < 0.05 * float(g0.median()) and float(g0.min()) > 1000.0
     assert float((e0 - e1).min()) > 100.0

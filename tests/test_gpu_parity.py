@@ -282,8 +282,10 @@ def test_cuda_core_path_vs_golden(name, weights):
     assert abs(float(e.double().sum()) - float(c["energy_total"])) <= E_RTOL * abs(float(c["energy_total"]))
     assert rel_rms(f.cpu().numpy(), c["forces"]) < F_RRMS
     e2, f2 = eng.energy_force(torch.from_numpy(c["pos"]).cuda())
-    # tensor-core (3xTF32) and CUDA-core paths agree to fp32 rounding
-    assert rel_rms(f2.cpu().numpy(), f.cpu().numpy()) < 2e-5
+    # tensor-core (3xTF32) and CUDA-core paths: energies agree to fp32 rounding; the default adjoint reads silu'(u),
+    # silu'(w) back from 16-bit codes (absolute error <= 9.6e-6 per activation derivative), which shows up as a few
+    # 1e-5 relative in the forces -- two decades inside the 1e-3 gate
+    assert rel_rms(f2.cpu().numpy(), f.cpu().numpy()) < 1e-4
     np.testing.assert_allclose(e2.cpu().numpy(), e.cpu().numpy(), rtol=2e-6)
 
 
@@ -332,3 +334,59 @@ def test_tf32x1_mode(name, weights):
     assert 0.0 < e_rel < 2e-3 and 0.0 < f_rel < 2e-2          # different from, and close to, the fp32-accurate result
     e3b, f3b = eng.energy_force(pos)                           # the default mode is bit-reproducible afterwards
     assert torch.equal(e3, e3b) and torch.equal(f3, f3b)
+
+
+# measured on B200 against the reference's goldens (worst of the five cases; printed by the test, quoted in DESIGN.md 5.5)
+HALF_MODE_BOUNDS = {"bf16": (5e-3, 8e-2), "fp16": (2e-3, 2e-2)}
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["c1_n13_dmso", "c2_n50_water", "mixed_n21", "mixed_n50", "n100_mixed"])
+def test_half_precision_modes(name, mode, weights):
+    """The half-precision MLP modes (GNNIS_FLAG_MLP_BF16, the north star's "bf16 MLP mode", and GNNIS_FLAG_MLP_FP16):
+    per-edge contractions as tcgen05.mma.kind::f16 on 16-bit operands (fp32 accumulate), SiLU from MUFU.TANH.
+    north_star asks for the force tolerance of this mode to be stated separately from the fp32 one: against the
+    REFERENCE's goldens the modes are held to HALF_MODE_BOUNDS (energy max rel, force rel-RMS); they must differ from
+    the fp32-accurate default, which stays bit-reproducible afterwards, and be deterministic themselves."""
+    c = load_case(name)
+    eng = _engine(c, weights)
+    pos = torch.from_numpy(c["pos"]).cuda()
+    kw = {mode: True}
+    e3, f3 = eng.energy_force(pos)
+    eb, fb = eng.energy_force(pos, **kw)
+    assert bool(torch.isfinite(eb).all() and torch.isfinite(fb).all())
+    R, N, _ = c["pos"].shape
+    e_ref = (c["e_atom"] + c["sa_atom"]).reshape(R, N).astype(np.float64).sum(1)     # the reference's per-replica energies
+    e_rel = float(np.abs(eb.double().cpu().numpy() - e_ref).max() / np.abs(e_ref).max())
+    f_rel = rel_rms(fb.cpu().numpy(), c["forces"])
+    print(f"{mode} mode vs reference goldens [{name}]: energy max rel {e_rel:.2e}, force rel-RMS {f_rel:.2e}")
+    e_max, f_max = HALF_MODE_BOUNDS[mode]
+    assert 0.0 < e_rel < e_max and 0.0 < f_rel < f_max
+    assert not torch.equal(eb, e3)
+    e3b, f3b = eng.energy_force(pos)
+    assert torch.equal(e3, e3b) and torch.equal(f3, f3b)
+    eb2, fb2 = eng.energy_force(pos, **kw)
+    assert torch.equal(eb, eb2) and torch.equal(fb, fb2)
+
+
+def test_stash_adjoint_vs_recomputing_adjoint(weights, monkeypatch):
+    """Default adjoint (activation stash written by the forward, edge_bwd_st_kernel) against the recomputing one
+    (GNNIS_STASH=0, edge_bwd_ws_kernel): identical energies, forces equal to the stash's 16-bit resolution, both inside
+    the gates against the reference's goldens; gnnis_describe says which one runs."""
+    from gnnimplicitsolvent_b200.engine import Engine
+    for name in ("c2_n50_water", "n100_mixed", "mixed_n21"):
+        c = load_case(name)
+        pos = torch.from_numpy(c["pos"]).cuda()
+        eng_s = _engine(c, weights)
+        assert "adjoint=stash" in eng_s.describe()
+        monkeypatch.setenv("GNNIS_STASH", "0")
+        eng_r = _engine(c, weights)
+        monkeypatch.delenv("GNNIS_STASH")
+        assert "adjoint=recompute" in eng_r.describe()
+        es, fs = eng_s.energy_force(pos)
+        er, fr = eng_r.energy_force(pos)
+        assert torch.equal(es, er)
+        assert rel_rms(fs.cpu().numpy(), fr.cpu().numpy()) < 1e-4
+        assert rel_rms(fs.cpu().numpy(), c["forces"]) < F_RRMS and rel_rms(fr.cpu().numpy(), c["forces"]) < F_RRMS
+        es2, fs2 = eng_s.energy_force(pos)                    # deterministic
+        assert torch.equal(fs, fs2)

@@ -100,3 +100,23 @@ def test_oracle_vs_imported_reference_random_weights():
     o = O.evaluate(mol["params"], pos, sids, diel, sd)
     assert float(e) == float(o["energy_total"])
     assert rel_rms(o["forces"].numpy(), (-p.grad).reshape(3, 17, 3).numpy()) < 2e-6
+
+
+def test_activation_stash_codec_arithmetic():
+    """The 16-bit fixed-point code of silu'(x) used between the forward and adjoint edge kernels (csrc/fastmath.cuh,
+    stash_enc2 / stash_dec2), re-stated in numpy with the same fp32 operations: one FMA whose rounding lands the code in
+    the mantissa of a float in [2^23, 2^24), decode by one FMA with exactly representable constants."""
+    K, ENC_OFF = np.float32(52428.8), np.float32(8395264.0)
+    INV, DEC_OFF = np.float32(1.9073486328125e-05), np.float32(-160.126953125)
+    assert float(INV) == 1.25 / 65536 and float(DEC_OFF) == -(2 ** 23 + 6656) * 1.25 / 65536    # exact constants
+    d = np.linspace(-0.0998, 1.0998, 200001, dtype=np.float32)       # the range of silu'
+    t = (d.astype(np.float64) * np.float64(K) + np.float64(ENC_OFF)).astype(np.float32)          # fma, one rounding
+    bits = t.view(np.uint32)
+    assert np.all((bits >> 23) == (0x4B000000 >> 23))                                             # exponent of [2^23, 2^24)
+    code = bits & 0xFFFF
+    assert code.min() >= 1 and code.max() <= 65534                                                # never wraps
+    f = (np.uint32(0x4B000000) | code).view(np.float32)                                           # PRMT with 0x4B00
+    dec = (f.astype(np.float64) * np.float64(INV) + np.float64(DEC_OFF)).astype(np.float32)
+    err = np.abs(dec.astype(np.float64) - d.astype(np.float64))
+    assert err.max() <= 0.5 * 1.25 / 65536 * 1.01 + 1e-7, err.max()                              # half a code step: 9.6e-6
+    assert abs(float(np.mean(dec.astype(np.float64) - d))) < 2e-7                                 # unbiased
