@@ -325,7 +325,9 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
         if (tm) tm->mark(kStNodeBwd);
         if ((node_tc ? launch_node_bwd_tc(c, l, st) : launch_node_bwd(c, l, st))) return -1;
         if (tm) tm->mark(kStEdgeBwd);
-        if (tc_bwd ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, terms, stash, st) : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st)) return -1;
+        if (tc_bwd ? launch_edge_bwd_ws(c, l, l == 2 ? 0 : 1, (terms == 3 && stash && c->adj_terms) ? c->adj_terms : terms, stash, st)
+                   : launch_edge_bwd(c, l, l == 2 ? 0 : 1, st))
+          return -1;
       }
       if (tm) tm->mark(kStNodeBwd);
       if (launch_node_pre1_bwd(c, st)) return -1;
@@ -384,6 +386,7 @@ int gnnis_create(gnnis_handle* out, int device) {
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
   if (const char* e = getenv("GNNIS_LB_STALL")) c->lb_stall_limit = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("GNNIS_LB_MAXDISP")) c->lb_max_disp = (float)atof(e);
+  if (const char* e = getenv("GNNIS_ADJ")) c->adj_terms = atoi(e);   // experiment: arithmetic of the stash adjoint's products (1, 3, 4)
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);
   return 0;
