@@ -108,3 +108,24 @@ def test_argument_errors_do_not_crash():
     eng.set_replicas(2, [0, 1], [78.5, 47.24])
     with pytest.raises((GnnisError, AssertionError, ValueError, RuntimeError)):
         eng.energy_force(torch.zeros(3, 8, 3, device="cuda"))    # wrong replica count
+
+
+@pytest.mark.gpu
+def test_size_limit_and_path_description(weights):
+    """No silent degradation: more than 1024 atoms per replica is refused with a message that names the limit, and
+    gnnis_describe tells which path a set-up runs on (stash / recomputing adjoint, tcgen05 / CUDA cores)."""
+    from gnnimplicitsolvent_b200.engine import Engine, GnnisError
+    from gnnimplicitsolvent_b200 import synth
+    big = np.zeros((1025, 7), dtype=np.float32)
+    big[:, 1] = 0.15
+    with pytest.raises(GnnisError, match="at most 1024"):
+        Engine(big, weights)
+    mol = synth.synth_molecule(50, seed=50)
+    eng = Engine(mol["params"], weights)
+    eng.set_replicas(64, [0] * 64, [78.5] * 64)
+    d = eng.describe()
+    assert "N=50" in d and "edge_kernels=tcgen05" in d and "adjoint=stash" in d
+    mol = synth.synth_molecule(100, seed=100)
+    eng = Engine(mol["params"], weights)
+    eng.set_replicas(8, [0] * 8, [78.5] * 8)
+    assert "edge_kernels=tcgen05" in eng.describe()
