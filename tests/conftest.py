@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["c1_n13_dmso", "mixed_n21", "c2_n50_water", "mixed_n50", "n100_mixed"]
+CASES = ["c1_n13_dmso", "mixed_n21", "c2_n50_water", "mixed_n50", "n100_mixed", "sulfur_n30", "epsband_n21"]
 
 
 def pytest_configure(config):

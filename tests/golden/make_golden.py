@@ -2,7 +2,7 @@
 (/root/reference/MachineLearning/GNN_Models.py: GNN3_Multisolvent_embedding_run_multiple :700,
  ..._Delta :947, ..._split :1068) on CPU through oracle/ref_harness.py, with the shipped checkpoint
 MachineLearning/trained_models/GNN.pt.  Run on the build box only (the reference tree does not travel):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case names]
 Outputs (committed):
     gnn_weights.npz          the 39-entry state dict of GNN.pt["model"] (weights are data, not source)
     case_<name>.npz          inputs (params, pos, solvent ids, dielectrics) + reference outputs:
@@ -29,16 +29,55 @@ CASES = {
     "c2_n50_water": (50, 4, [0] * 4, 0.01),
     "mixed_n50": (50, 6, [1, 5, 9, 20, 30, 38], 0.02),
     "n100_mixed": (100, 2, [0, 12], 0.01),
+    # round 2: two sulfur atoms (negative GBn2 screening scale: s_j < 0) -- molecule seed 2 instead of N
+    "sulfur_n30": (30, 4, [0, 3, 9, 22], 0.01),
+    # round 2: in every conformer one pair sits inside the 1e-6-wide eps band of the 0.6 nm cutoff, so that exactly ONE
+    # of its two directed edges exists (r(j->i) < 0.6 <= r(i->j)); see eps_band_conformers
+    "epsband_n21": (21, 4, [0, 3, 7, 38], 0.01),
 }
+MOL_SEED = {"sulfur_n30": 2}
+
+
+def eps_band_conformers(pos, cutoff=0.6):
+    """Moves one atom of every conformer along a pair axis until the fp32 eps-distances of the two directions
+    (|x_src - x_tgt + 1e-6|, GNN_Models.py:912) straddle the cutoff: the edge list becomes asymmetric there."""
+    from oracle import gnn_oracle as O
+    pos = pos.copy()
+    R, N, _ = pos.shape
+    for r in range(R):
+        d = np.linalg.norm(pos[r][:, None, :] - pos[r][None, :, :], axis=2)
+        d[np.tril_indices(N)] = 99.0
+        i, j = np.unravel_index(np.argmin(np.abs(d - cutoff)), d.shape)
+        axis = (pos[r, j] - pos[r, i]).astype(np.float64)
+        axis /= np.linalg.norm(axis)
+        found = False
+        for k in range(-4000, 4000):           # steps of 2.5e-8 nm around the cutoff
+            trial = pos[r].copy()
+            trial[j] = (pos[r, i].astype(np.float64) + axis * (cutoff + k * 2.5e-8)).astype(np.float32)
+            rp, col, _ = O.neighbor_list_numpy(trial[None])
+            has_ji = j in col[rp[i]:rp[i + 1]]     # edge j -> i (row of target i)
+            has_ij = i in col[rp[j]:rp[j + 1]]
+            if has_ji != has_ij:
+                pos[r] = trial
+                found = True
+                break
+        assert found, "no asymmetric placement found"
+    return pos
 
 
 def main():
     torch.set_num_threads(1)
     sd = torch.load(H.checkpoint_path(), weights_only=True, map_location="cpu")["model"]
-    np.savez_compressed(os.path.join(HERE, "gnn_weights.npz"), **{k: v.numpy() for k, v in sd.items()})
+    if not sys.argv[1:]:
+        np.savez_compressed(os.path.join(HERE, "gnn_weights.npz"), **{k: v.numpy() for k, v in sd.items()})
+    only = sys.argv[1:]
     for name, (N, R, sids, sigma) in CASES.items():
-        mol = synth.synth_molecule(N, seed=N)
+        if only and name not in only:
+            continue
+        mol = synth.synth_molecule(N, seed=MOL_SEED.get(name, N))
         pos = synth.conformers(mol["pos"], R, sigma, seed=1000 * N + R)
+        if name.startswith("epsband"):
+            pos = eps_band_conformers(pos)
         diel = [synth.SOLVENT_DIELECTRICS[s] for s in sids]
         out = {"params": mol["params"], "pos": pos, "solvent_ids": np.array(sids, dtype=np.int64),
                "dielectrics": np.array(diel, dtype=np.float32)}
