@@ -297,7 +297,7 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
   // the adjoint reads the activations that the forward leaves behind when both edge stages run on tensor cores and the
   // stash fits the memory budget (Ctx::stash_on); otherwise it recomputes them (edge_bwd_ws_kernel)
   const int stash = (want_grad && tc_fwd && tc_bwd && c->stash_on) ? 1 : 0;
-  if (!gb_only) GNNIS_CUDA_OK(cudaMemsetAsync(c->unit_ctr, 0, 8 * sizeof(unsigned), st));   // unit hand-out counters of the edge kernels
+  if (want_grad) GNNIS_CUDA_OK(cudaMemsetAsync(c->unit_ctr, 0, 8 * sizeof(unsigned), st));
   if (tm) tm->mark(kStNeighborBorn);
   if (launch_born_count(c, pos, predicate, st)) return -1;
   if (!gb_only) {

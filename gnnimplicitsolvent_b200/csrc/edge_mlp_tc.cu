@@ -356,7 +356,7 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l, int terms = 3) {
   EdgeTcArgs g{};
   g.n_units = c->n_units * c->split_eff;
   g.S = c->split_eff;
-  g.unit_counter = c->unit_ctr ? c->unit_ctr + l : nullptr;   // adjoint: counters 0..2; the forward launcher uses 3..5
+  g.unit_counter = c->unit_ctr ? c->unit_ctr + l : nullptr;
   g.qbar_stride = (size_t)c->R * c->N * 64;
   g.G = c->G;
   g.N = c->N;
@@ -634,42 +634,12 @@ __device__ __forceinline__ void warp_arrive_i(uint64_t* bar, int lane) {
 }
 // issuer-side walk over the units of one group (must visit exactly the tiles the epilogue warps visit)
 struct IssueState {
-  int unit, t0, e_end, stage, seen;
+  int unit, t0, e_end, stage;
   uint32_t ph_a, ph_u, cur;
   bool done;
 };
-// Unit hand-out of the forward kernel.  The first unit of a group is fixed; every following one is drawn from a
-// global counter by the group's epilogue warps (one atomicAdd per unit) and passed to the issuer warp, which has to
-// walk exactly the same sequence, through a four-entry ring in shared memory: `seq` counts the entries written,
-// `cons` the entries the issuer has taken.  The writer is never more than one entry ahead of the issuer for units that
-// have edges (its first wait on a product needs the issuer to have reached that unit); runs of empty units are held
-// back by the ring's back-pressure.
-struct UnitQueue {
-  int unit[kGroups][4];
-  int seq[kGroups], cons[kGroups];
-};
-__device__ __forceinline__ void unit_queue_push(UnitQueue* q, int grp, int unit) {   // one thread of the group
-  volatile int* cons = &q->cons[grp];
-  const int s = q->seq[grp];
-  while (s - *cons >= 4) {
-  }
-  q->unit[grp][s & 3] = unit;
-  __threadfence_block();
-  *reinterpret_cast<volatile int*>(&q->seq[grp]) = s + 1;
-}
-__device__ __forceinline__ int unit_queue_pop(UnitQueue* q, int grp, int& seen) {     // the (converged) issuer warp
-  volatile int* seq = &q->seq[grp];
-  while (*seq == seen) {
-  }
-  __threadfence_block();
-  const int u = *reinterpret_cast<volatile int*>(&q->unit[grp][seen & 3]);
-  seen += 1;
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) *reinterpret_cast<volatile int*>(&q->cons[grp]) = seen;
-  return u;
-}
 template <bool SPLIT>
-__device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs& g, UnitQueue* q, int grp) {
+__device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs& g) {
   for (;;) {
     if (x.unit >= g.n_units) {
       x.done = true;
@@ -682,7 +652,7 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
       x.e_end = e_end;
       return;
     }
-    x.unit = unit_queue_pop(q, grp, x.seen);
+    x.unit += gridDim.x * kGroups;
   }
 }
 
@@ -697,7 +667,6 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   constexpr uint32_t kStg = STASH ? kStageBytes : 0u;
   extern __shared__ uint8_t smraw[];
   __shared__ WsiBars bars;
-  __shared__ UnitQueue uq;
   __shared__ uint32_t tmem_slot;
   uint32_t base = smem_u32(smraw);
   uint8_t* sm = smraw + ((1024u - (base & 1023u)) & 1023u);
@@ -713,8 +682,6 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       mbar_init(&bars.d_full[i], 1);
       mbar_init(&bars.a_full[i], 8);
       mbar_init(&bars.u_ok[i], 12);
-      uq.seq[i] = 0;
-      uq.cons[i] = 0;
     }
   }
   __shared__ uint64_t ibar;
@@ -739,8 +706,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       const uint32_t aWrH = smem_u32(sWrH), aWrL = smem_u32(sWrL), aW2H = smem_u32(sW2H), aW2L = smem_u32(sW2L);
       IssueState st[kGroups];
       for (int i = 0; i < kGroups; ++i) {
-        st[i] = IssueState{(int)blockIdx.x + i * (int)gridDim.x, 0, 0, 0, 0, 0u, 0u, 0u, false};
-        issue_next_unit<SPLIT>(st[i], g, &uq, i);
+        st[i] = IssueState{(int)blockIdx.x + i * (int)gridDim.x, 0, 0, 0, 0u, 0u, 0u, false};
+        issue_next_unit<SPLIT>(st[i], g);
       }
       while (!(st[0].done && st[1].done)) {
 #pragma unroll
@@ -771,8 +738,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             x.cur ^= 64u;
             x.t0 += kTileE;
             if (x.t0 >= x.e_end) {
-              x.unit = unit_queue_pop(&uq, i, x.seen);
-              issue_next_unit<SPLIT>(x, g, &uq, i);
+              x.unit += gridDim.x * kGroups;
+              issue_next_unit<SPLIT>(x, g);
             }
           }
         }
@@ -794,8 +761,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     uint32_t ph_d = 0, ph_a = 0, cur = 0;
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
-    __shared__ int s_next[kGroups];
-    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit = s_next[grp]) {
+    for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
       const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
       const int atom0 = us.atom_base, natoms = us.n_tab;
       const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
@@ -817,11 +783,6 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       if (SPLIT) zero_rows_n(gA + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
       else zero_rows_n(gA, 64, natoms, gt, kWsGroupThreads);
       if (e_begin >= e_end) {
-        ws_group_sync(grp);
-        if (gt == 0) {
-          s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
-          unit_queue_push(&uq, grp, s_next[grp]);
-        }
         ws_group_sync(grp);
         continue;
       }
@@ -849,12 +810,6 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         warp_arrive_i(u_ok, lane);
       }
       ws_group_sync(grp);                            // tables + keys of the first tile visible
-      // every thread of the group has read the previous hand-out before this barrier; the new one is read after the
-      // barrier that closes the unit.  Groups that drew lighter units take more of them (units are independent).
-      if (gt == 0) {
-        s_next[grp] = (int)atomicAdd(g.unit_counter, 1u) + (int)(gridDim.x * kGroups);
-        unit_queue_push(&uq, grp, s_next[grp]);
-      }
 
       for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
         const bool has_next = t0 + kTileE < e_end;
@@ -1772,7 +1727,6 @@ static int launch_bwd_st_terms(Ctx* c, const EdgeTcArgs& g, int terms, int grid,
 
 int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
   EdgeTcArgs g = make_tc_args(c, l, terms);
-  g.unit_counter = c->unit_ctr + 3 + l;
   const int grid = tc_grid(c);
   int rc;
   if (stash) {
