@@ -75,7 +75,10 @@ if rank == 0:
                  "cpu_cores": torch.get_num_threads(), "speedup_vs_cpu": 1e3 * t_cpu / ms,
                  "energy_max_rel": float((e.cpu() - o["energy_rep"]).abs().max() / o["energy_rep"].abs().max()),
                  "minimize": {"potential": "GNN + synthetic vacuum force field", "grad_tol_kJ_mol_nm": 10.0,
-                              "rounds": rounds, "seconds": t_min, "converged": int((status == 0).sum()),
+                              "rounds": rounds, "seconds": t_min,
+                              "status_counts": {str(k): int((status == k).sum()) for k in range(4)},
+                              "final_grad_rms_median": float(eng.minimize_stats()[1].median()),
+                              "evaluations_per_replica_median": float(eng.minimize_stats()[0].float().median()),
                               "s_per_conformer": t_min / R}}
     eng.close()
 
