@@ -307,7 +307,7 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
     if (launch_node_pre1(c, st)) return -1;
     for (int l = 0; l < 3; ++l) {
       if (tm) tm->mark(kStEdgeFwd);
-      if (tc_fwd ? launch_edge_fwd_ws(c, l, terms, stash, st) : launch_edge_fwd(c, l, st)) return -1;
+      if (tc_fwd ? launch_edge_fwd_ws(c, l, (terms == 3 && c->act_tanh) ? 7 : terms, stash, st) : launch_edge_fwd(c, l, st)) return -1;
       if (tm) tm->mark(kStNodeFwd);
       if ((node_tc ? launch_node_fwd_tc(c, l, st) : launch_node_fwd(c, l, st))) return -1;
     }
@@ -386,6 +386,7 @@ int gnnis_create(gnnis_handle* out, int device) {
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
   if (const char* e = getenv("GNNIS_LB_STALL")) c->lb_stall_limit = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("GNNIS_LB_MAXDISP")) c->lb_max_disp = (float)atof(e);
+  if (const char* e = getenv("GNNIS_ACT")) c->act_tanh = atoi(e);    // experiment: tanh-based activations with the 3xTF32 products
   if (const char* e = getenv("GNNIS_ADJ")) c->adj_terms = atoi(e);   // experiment: arithmetic of the stash adjoint's products (1, 3, 4)
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);

@@ -140,6 +140,7 @@ struct Ctx {
   uint8_t* stash = nullptr;
   uint8_t *st_u[3] = {nullptr, nullptr, nullptr}, *st_w[3] = {nullptr, nullptr, nullptr};
   bool stash_on = false;
+  int act_tanh = 0;           // experiment (GNNIS_ACT=1): MUFU.TANH activations in the default-precision forward
   int adj_terms = 0;          // 0: the adjoint's products follow the mode of the evaluation
   int use_stash = 1;          // GNNIS_STASH=0: always recompute (A/B, debug)
   double stash_max_gb = -1;   // GNNIS_STASH_GB: upper bound of the stash allocation (default: 45 % of the free memory)

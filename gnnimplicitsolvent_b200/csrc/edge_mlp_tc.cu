@@ -45,6 +45,7 @@ using namespace umma;
 // (tcgen05.mma.kind::f16, fp32 accumulate) and tanh-based activations.  kBf16: GNNIS_FLAG_MLP_BF16; kFp16: the same
 // kernels with fp16 operands (GNNIS_FLAG_MLP_FP16: 3 more mantissa bits; every operand of these MLPs fits fp16's range)
 constexpr int kBf16 = 2, kFp16 = 4;
+constexpr int kTanh3 = 7;   // forward only (experiment, GNNIS_ACT=1): 3xTF32 products with the tanh-based activations
 __host__ __device__ constexpr bool is_half(int terms) { return terms == kBf16 || terms == kFp16; }
 template <int TERMS>
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -661,8 +662,10 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
 // silu'(w), pack them as 16-bit codes into a swizzled 16 KB image of the tile in shared memory, and one thread sends
 // each image to global memory with one bulk store (TMA engine); the adjoint (edge_bwd_st_kernel) then neither
 // recomputes u and w nor evaluates a single sigmoid.
-template <int TAB, int TERMS, bool SPLIT, bool STASH>
+template <int TAB, int TM, bool SPLIT, bool STASH>
 __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
+  constexpr int TERMS = TM == kTanh3 ? 3 : TM;                 // arithmetic of the products
+  constexpr bool FAST = is_half(TM) || TM == kTanh3;           // tanh-based activations
   constexpr bool Q_SM = TAB >= 1, P_SM = TAB == 2;   // which node tables of the unit live in shared memory
   constexpr uint32_t kStg = STASH ? kStageBytes : 0u;
   extern __shared__ uint8_t smraw[];
@@ -846,7 +849,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               float d[4];
-              if (BF) silu_fd4_sum3_tanh(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], d);
+              if (FAST) silu_fd4_sum3_tanh(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], d);
               else silu_fd4_sum3(&ur[4 * j4], p[j4], q[j4], &v[4 * j4], d);
               code[2 * j4] = stash_enc2(d[0], d[1]);
               code[2 * j4 + 1] = stash_enc2(d[2], d[3]);
@@ -858,7 +861,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           } else {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 y = BF ? silu4_sum3_tanh(&ur[4 * j4], p[j4], q[j4]) : silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
+              const float4 y = FAST ? silu4_sum3_tanh(&ur[4 * j4], p[j4], q[j4]) : silu4_sum3(&ur[4 * j4], p[j4], q[j4]);
               v[4 * j4 + 0] = y.x;
               v[4 * j4 + 1] = y.y;
               v[4 * j4 + 2] = y.z;
@@ -920,7 +923,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               float z[8], d[8];
-              if (BF) {
+              if (FAST) {
                 silu_fd4_sum2_tanh(&wr[8 * j8], bb[2 * j8], z, d);
                 silu_fd4_sum2_tanh(&wr[8 * j8 + 4], bb[2 * j8 + 1], z + 4, d + 4);
               } else {
@@ -937,7 +940,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 b = bb[j4];
-              const float4 z = BF ? silu4_sum2_tanh(&wr[4 * j4], b) : silu4_sum2(&wr[4 * j4], b);
+              const float4 z = FAST ? silu4_sum2_tanh(&wr[4 * j4], b) : silu4_sum2(&wr[4 * j4], b);
               *reinterpret_cast<float4*>(zrow + 4 * j4) = z;
             }
           }
@@ -1714,6 +1717,7 @@ template <int T, bool STASH>
 static int launch_fwd_terms(Ctx* c, const EdgeTcArgs& g, int terms, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
   if (terms == kBf16) return launch_fwd_t<T, kBf16, STASH>(c, g, grid, smem, gb, st);
   if (terms == kFp16) return launch_fwd_t<T, kFp16, STASH>(c, g, grid, smem, gb, st);
+  if (terms == kTanh3) return launch_fwd_t<T, kTanh3, STASH>(c, g, grid, smem, gb, st);
   if (terms == 1) return launch_fwd_t<T, 1, STASH>(c, g, grid, smem, gb, st);
   return launch_fwd_t<T, 3, STASH>(c, g, grid, smem, gb, st);
 }
