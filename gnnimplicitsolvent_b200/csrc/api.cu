@@ -386,7 +386,7 @@ int gnnis_create(gnnis_handle* out, int device) {
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
   if (const char* e = getenv("GNNIS_LB_STALL")) c->lb_stall_limit = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("GNNIS_LB_MAXDISP")) c->lb_max_disp = (float)atof(e);
-  if (const char* e = getenv("GNNIS_ACT")) c->act_tanh = atoi(e);    // experiment: tanh-based activations with the 3xTF32 products
+  if (const char* e = getenv("GNNIS_ACT")) c->act_tanh = atoi(e);    // 0: exponential-based sigmoid in the forward edge kernels
   if (const char* e = getenv("GNNIS_ADJ")) c->adj_terms = atoi(e);   // experiment: arithmetic of the stash adjoint's products (1, 3, 4)
   if (const char* e = getenv("GNNIS_TC")) c->tc_mask = atoi(e);   // debug: bit0 edge fwd, bit1 edge adjoint, bit2 node kernels on tensor cores
   *out = reinterpret_cast<gnnis_handle>(c);

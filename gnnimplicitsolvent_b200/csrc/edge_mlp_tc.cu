@@ -45,7 +45,7 @@ using namespace umma;
 // (tcgen05.mma.kind::f16, fp32 accumulate) and tanh-based activations.  kBf16: GNNIS_FLAG_MLP_BF16; kFp16: the same
 // kernels with fp16 operands (GNNIS_FLAG_MLP_FP16: 3 more mantissa bits; every operand of these MLPs fits fp16's range)
 constexpr int kBf16 = 2, kFp16 = 4;
-constexpr int kTanh3 = 7;   // forward only (experiment, GNNIS_ACT=1): 3xTF32 products with the tanh-based activations
+constexpr int kTanh3 = 7;   // forward only: 3xTF32 products with the tanh-based activations (the default, Ctx::act_tanh)
 __host__ __device__ constexpr bool is_half(int terms) { return terms == kBf16 || terms == kFp16; }
 template <int TERMS>
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {

@@ -286,7 +286,8 @@ def test_cuda_core_path_vs_golden(name, weights):
     # silu'(w) back from 16-bit codes (absolute error <= 9.6e-6 per activation derivative), which shows up as a few
     # 1e-5 relative in the forces -- two decades inside the 1e-3 gate
     assert rel_rms(f2.cpu().numpy(), f.cpu().numpy()) < 1e-4
-    np.testing.assert_allclose(e2.cpu().numpy(), e.cpu().numpy(), rtol=2e-6)
+    # (the tensor-core forward takes its sigmoid from MUFU.TANH, the CUDA-core kernels from ex2 + rcp: a few 1e-6)
+    np.testing.assert_allclose(e2.cpu().numpy(), e.cpu().numpy(), rtol=2e-5)
 
 
 def test_cuda_graph_capture(weights):
