@@ -577,10 +577,10 @@ __device__ __forceinline__ void reduce_targets_global_256(const float* __restric
 // fetched four at a time (independent loads) and added in order
 __device__ __forceinline__ void reduce_sources_table_256(const float* __restrict__ sX, const TileKeys* __restrict__ tk,
                                                          float* __restrict__ table, int ld, int gt) {
-  const int cq = gt & 15, slot = gt >> 4;
-  constexpr int kSlots = 16;
+  const int cq = gt & 15;
   const int nseg = tk->n_seg_s;
-  for (int s = slot; s < nseg; s += kSlots) {
+  constexpr int kSlots = 16;
+  for (int s = gt >> 4; s < nseg; s += kSlots) {
     const int p0 = tk->seg_s[s], p1 = tk->seg_s[s + 1];
     const int row0 = tk->perm[p0];
     float4* dst = reinterpret_cast<float4*>(table + (size_t)tk->src[row0] * ld + 4 * cq);

@@ -181,34 +181,6 @@ __device__ __forceinline__ void silu_fd4_sum2_tanh(const uint32_t* __restrict__ 
   upk(d23, d[2], d[3]);
 }
 
-// plain float4 forms of the tanh-based activations (node kernels)
-__device__ __forceinline__ float4 silu4_tanh(float4 x) {
-  float4 y;
-  upk(silu2_tanh(pk(x.x, x.y)), y.x, y.y);
-  upk(silu2_tanh(pk(x.z, x.w)), y.z, y.w);
-  return y;
-}
-__device__ __forceinline__ float4 silu_d4_scaled_tanh(float4 x, float4 g) {
-  f2_t d01, d23;
-  silu2_tanh_fd(pk(x.x, x.y), d01);
-  silu2_tanh_fd(pk(x.z, x.w), d23);
-  float4 y;
-  upk(mul2(pk(g.x, g.y), d01), y.x, y.y);
-  upk(mul2(pk(g.z, g.w), d23), y.z, y.w);
-  return y;
-}
-__device__ __forceinline__ float4 silu_d4_sum2_scaled_tanh(const uint32_t* __restrict__ a, float4 b, float4 g) {
-  const f2_t x01 = add2(pk(__uint_as_float(a[0]), __uint_as_float(a[1])), pk(b.x, b.y));
-  const f2_t x23 = add2(pk(__uint_as_float(a[2]), __uint_as_float(a[3])), pk(b.z, b.w));
-  f2_t d01, d23;
-  silu2_tanh_fd(x01, d01);
-  silu2_tanh_fd(x23, d23);
-  float4 y;
-  upk(mul2(pk(g.x, g.y), d01), y.x, y.y);
-  upk(mul2(pk(g.z, g.w), d23), y.z, y.w);
-  return y;
-}
-
 // ---- 16-bit fixed-point codes of silu'(x) (the activations that the forward edge kernel leaves for the adjoint) -------
 // silu' lies in [-0.0998, 1.0998]; code = round(d * 2^16 / 1.25) + 6656 covers [-0.1270, 1.1230] in steps of 1.9e-5
 // (absolute error <= 9.6e-6, ~25x finer than fp16 over [0.25, 1.1]).  Encoding rounds inside one FMA that lands the

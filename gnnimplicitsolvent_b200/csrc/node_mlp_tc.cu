@@ -21,12 +21,6 @@
 #include "umma.cuh"
 #include "fastmath.cuh"
 
-#ifdef GNNIS_NODE_TANH   // A/B switch: SiLU of the node MLPs from MUFU.TANH as in the edge forward kernels
-#define silu4_sum2 silu4_sum2_tanh
-#define silu4 silu4_tanh
-#define silu_d4_scaled silu_d4_scaled_tanh
-#define silu_d4_sum2_scaled silu_d4_sum2_scaled_tanh
-#endif
 namespace gnnis {
 
 using namespace umma;
