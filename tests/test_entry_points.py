@@ -174,3 +174,39 @@ def test_create_gnn_model_entry_point():
     e2, f2 = eng.energy_force(pos.detach().reshape(1, 21, 3))
     assert abs(float(e) - float(e2[0])) < 1e-4 * abs(float(e2[0])) + 1e-4
     assert torch.allclose(-pos.grad, f2[0], rtol=1e-4, atol=1e-3)
+
+
+def test_helper_plumbing_without_gpu():
+    """Solvent lists (interleaving of helper_functions.py:738-743), trajectory assembly and the write-back into the molecule."""
+    sm, sd = H._solvent_lists("DMSO", H.SOLVENT_DICT, 3)
+    assert sm == [3, 3, 3] and sd == [47.24] * 3
+    sm, sd = H._solvent_lists(["tip3p", "DMSO"], H.SOLVENT_DICT, 4)
+    assert sm == [0, 3, 0, 3] and sd == [78.5, 47.24, 78.5, 47.24]
+    mol = synth.synth_mol_object(7, 5, seed=1)
+    blocks = [np.full((2 * 7, 3), 1.0), np.full((2 * 7, 3), 2.0), np.full((1 * 7, 3), 3.0)]     # strides=2 + one left over
+    traj = H.get_traj_from_positions(mol, blocks, num_iters=2, num_confs=2)
+    assert traj.n_frames == 5 and traj.n_atoms == 7
+    assert np.all(traj.xyz[0] == 1.0) and np.all(traj.xyz[3] == 2.0) and np.all(traj.xyz[4] == 3.0)
+    H.set_positions_in_mol(mol, [np.concatenate(blocks, axis=0)])
+    assert np.allclose(mol.conformers_nm[2], 2.0) and np.allclose(mol.GetConformer(4).GetPositions(), 30.0)
+    assert abs(H.get_boltzmann_mean(np.zeros(4))) < 1e-12
+
+
+@pytest.mark.gpu
+def test_entropy_reminimises_conformers_with_imaginary_modes():
+    """calculate_entropy_from_simulation on conformers that are NOT at a minimum: their lowest mode is imaginary, and
+    the reference's minimization_cycles loop (helper_functions.py:1986-2015) re-minimises exactly those until the
+    modes are real; conformers already at a minimum are left alone."""
+    sd = _sd()
+    mol = synth.synth_mol_object(10, 4, seed=11, sigma=0.02)
+    sim = H.get_gnn_sim(mol, "tip3p", {"model": sd}, H.SOLVENT_DICT, constraints=None, num_confs=4)
+    start = mol.conformers_nm.astype(np.float32)
+    from gnnimplicitsolvent_b200 import entropy as E
+    _, nus0 = E.conformer_entropies(sim._ref_system._engine, start, mol.masses, 0, 78.5)
+    assert any(nu[0] < 0 for nu in nus0)                       # displaced start points: imaginary modes
+    S, nus, pos = H.calculate_entropy_from_simulation(sim._ref_system, start)
+    assert np.all(np.isfinite(S)) and S.shape == (4,)
+    assert sum(nu[0] > 0 for nu in nus) >= 3                   # re-minimised: real lowest modes (a ledge may keep one)
+    assert not np.allclose(pos, start)
+    S2, nus2, pos2 = H.calculate_entropy_from_simulation(sim._ref_system, pos, use_minimisation_cycles=False)
+    assert np.allclose(S2, S, rtol=1e-4)                       # without the loop the (already minimised) input is evaluated as it is

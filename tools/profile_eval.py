@@ -15,6 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--replicas", type=int, default=1024)
 ap.add_argument("--atoms", type=int, default=50)
 ap.add_argument("--evals", type=int, default=2)
+ap.add_argument("--fp16", action="store_true", help="half-precision mode of the edge MLPs (GNNIS_FLAG_MLP_FP16)")
+ap.add_argument("--bf16", action="store_true")
 a = ap.parse_args()
 z = np.load(os.path.join(ROOT, "tests", "golden", "gnn_weights.npz"))
 sd = {k: torch.from_numpy(z[k]) for k in z.files}
@@ -23,6 +25,6 @@ pos = torch.from_numpy(synth.conformers(mol["pos"], a.replicas, 0.01, seed=1)).c
 eng = Engine(mol["params"], sd)
 eng.set_replicas(a.replicas, [0] * a.replicas, [78.5] * a.replicas)
 for _ in range(a.evals):
-    e, f = eng.energy_force(pos)
+    e, f = eng.energy_force(pos, fp16=a.fp16, bf16=a.bf16)
 torch.cuda.synchronize()
 print("E sum", float(e.double().sum()), "edges", eng.last_edge_count(), "launches", eng.launch_count())
