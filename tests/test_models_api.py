@@ -170,6 +170,21 @@ def test_gbneck2_parameter_table_layout():
     assert radii == gbneck.DEFAULT_UNIQUE_RADII
 
 
+def test_gbneck2_element_table_vs_reference_notebook_output():
+    """N2 pinned where the reference allows it: OpenMM is absent, but the reference's own notebook prints the first
+    columns of `atomfeatures` rows that its Trainer.get_gbneck2_param produced (/root/reference/Data/deposit_database.ipynb,
+    cell 77 output: `[[q, rho, s, alpha, ...`).  rho = r - 0.0195141, s = screen * rho and alpha of C, O, N and S from
+    gbneck.gbneck2_parameters must reproduce those printed digits."""
+    from gnnimplicitsolvent_b200 import gbneck
+    printed = {"C": (0.1504859, 0.15929745, 0.733756), "O": (0.1304859, 0.13845063, 0.867814),
+               "N": (0.1354859, 0.09939232, 0.503364), "S": (0.1604859, -0.11289686, 0.867814)}
+    els = list(printed)
+    p, _ = gbneck.gbneck2_parameters(els, [], [0.0] * len(els))
+    for i, el in enumerate(els):
+        rho, s_, alpha = printed[el]
+        assert abs(p[i, 1] - rho) < 5e-8 and abs(p[i, 2] - s_) < 5e-8 and abs(p[i, 3] - alpha) < 5e-7, (el, p[i])
+
+
 @pytest.mark.gpu
 def test_data_model_ragged_batch(weights):
     """A PyG-style batch mixing two different molecules (13 and 21 atoms, interleaved graphs, mixed solvents)."""
