@@ -76,6 +76,8 @@ FLAG_MLP_TF32X1 = 0x80
 FLAG_MLP_FP16 = 0x100
 FLAG_DATA_PREDICATE = 0x20
 FLAG_VACUUM_ONLY = 0x40
+FLAG_CELL_LIST, FLAG_ALL_PAIRS = 0x200, 0x400
+PREDICATE_CELL_LIST, PREDICATE_ALL_PAIRS = 0x10, 0x20
 
 _lib = None
 

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgnnis.so")
-SOURCES = ["api.cu", "pair_kernels.cu", "edge_mlp.cu", "edge_mlp_tc.cu", "node_mlp.cu", "node_mlp_tc.cu", "dynamics.cu", "forcefield.cu"]
+SOURCES = ["api.cu", "pair_kernels.cu", "cell_list.cu", "edge_mlp.cu", "edge_mlp_tc.cu", "node_mlp.cu", "node_mlp_tc.cu", "dynamics.cu", "forcefield.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

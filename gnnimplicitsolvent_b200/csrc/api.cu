@@ -11,6 +11,7 @@
 namespace gnnis {
 int launch_born_count(Ctx*, const float*, int, cudaStream_t);
 int launch_fill_edges(Ctx*, const float*, int, int*, int*, uint32_t*, float*, int64_t, cudaStream_t);
+int launch_cell_neighbors(Ctx*, const float*, int, int*, int*, uint32_t*, float*, int64_t, cudaStream_t);
 int launch_gb_energy(Ctx*, const float*, const float*, int, int, float*, cudaStream_t);
 int launch_born_adjoint(Ctx*, const float*, int, int, float*, cudaStream_t);
 int launch_reduce_energy(Ctx*, const float*, float*, cudaStream_t);
@@ -99,13 +100,20 @@ static int ensure_workspace(Ctx* c) {
   // unit, at least ~6 target atoms (one to two edge tiles) per part, at most split_max parts.  Splitting further (to
   // even out the waves of mid-size batches) does not pay: every part loads the replica's tables, ends on a partly
   // filled tile and writes a partial Qbar table (measured: R = 1024 1.81 -> 1.96 ms, R = 2496 4.06 -> 4.55 ms with 2 parts).
+  // What does pay for mid-size batches is splitting only the replicas of the LAST, partly filled wave (Ctx::split_from):
+  // R = 1024 on 296 groups = 3 full waves + 136 replicas, which as 272 half-units take ~0.6 instead of 1.0 wave.
   c->split = 1;
+  c->split_from = 0;
   if (c->G == 1) {
     const int groups = 2 * (c->num_sms > 0 ? c->num_sms : 148);
-    int s_ = groups / c->R;
+    const int rem = c->R % groups;
+    int s_ = c->R < groups ? groups / c->R : ((rem > 0 && c->tail_split) ? groups / rem : 1);
     if (s_ > c->N / 6) s_ = c->N / 6;
     if (s_ > c->split_max) s_ = c->split_max;
-    if (s_ > 1) c->split = s_;
+    if (s_ > 1) {
+      c->split = s_;
+      if (c->R >= groups) c->split_from = c->R - rem;
+    }
   }
   size_t n = (size_t)c->R * c->N;
   int64_t cap = (int64_t)n * (c->N - 1);
@@ -118,7 +126,7 @@ static int ensure_workspace(Ctx* c) {
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   int nblk = (int)((n + kPairThreads - 1) / kPairThreads);
   if (dev_alloc(c, &c->deg, n) || dev_alloc(c, &c->row_ptr, n + 1) || dev_alloc(c, &c->blk_sum, (size_t)nblk + 1) ||
-      dev_alloc(c, &c->col, (size_t)cap) || dev_alloc(c, &c->pair, (size_t)cap) || dev_alloc(c, &c->perm, (size_t)cap + 128) || dev_alloc(c, &c->r_e, (size_t)cap))
+      dev_alloc(c, &c->nbr_mask, n * (size_t)((c->N + 31) / 32)) || dev_alloc(c, &c->col, (size_t)cap) || dev_alloc(c, &c->pair, (size_t)cap) || dev_alloc(c, &c->perm, (size_t)cap + 128) || dev_alloc(c, &c->r_e, (size_t)cap))
     return -1;
   float** scal[] = {&c->born, &c->dBdI, &c->born_s, &c->dE_dBs, &c->Bbar, &c->e_atom, &c->sa_atom};
   for (float** p : scal)
@@ -180,6 +188,13 @@ static int check_ready(Ctx* c, bool need_weights) {
 
 static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* force, uint32_t flags, cudaStream_t st,
                                StageTimer* tm);
+
+// neighbour back-end of a call: request 1 = cell list, 0 = all pairs, -1 = the handle's default (GNNIS_NEIGHBORS, else by size)
+static bool use_cell_list(const Ctx* c, int request) {
+  if (request >= 0) return request == 1;
+  if (c->nbr_mode >= 0) return c->nbr_mode == 1;
+  return c->N > c->nbr_cell_min;
+}
 
 static void graph_entry_clear(Ctx::GraphEntry& g) {
   if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -299,9 +314,12 @@ static int energy_force_direct(Ctx* c, const float* pos, float* e_rep, float* fo
   const int stash = (want_grad && tc_fwd && tc_bwd && c->stash_on) ? 1 : 0;
   if (want_grad) GNNIS_CUDA_OK(cudaMemsetAsync(c->unit_ctr, 0, 8 * sizeof(unsigned), st));
   if (tm) tm->mark(kStNeighborBorn);
-  if (launch_born_count(c, pos, predicate, st)) return -1;
+  const bool cells = !gb_only && use_cell_list(c, (flags & GNNIS_FLAG_CELL_LIST) ? 1 : ((flags & GNNIS_FLAG_ALL_PAIRS) ? 0 : -1));
+  if (launch_born_count(c, pos, cells ? -1 : predicate, st)) return -1;
   if (!gb_only) {
-    if (launch_fill_edges(c, pos, predicate, c->row_ptr, nullptr, c->pair, c->r_e, c->edge_cap, st)) return -1;
+    if (cells ? launch_cell_neighbors(c, pos, predicate, c->row_ptr, nullptr, c->pair, c->r_e, c->edge_cap, st)
+              : launch_fill_edges(c, pos, predicate, c->row_ptr, nullptr, c->pair, c->r_e, c->edge_cap, st))
+      return -1;
     if (want_grad && launch_tile_perm(c, st)) return -1;
     if (tm) tm->mark(kStNodeFwd);
     if (launch_node_pre1(c, st)) return -1;
@@ -381,6 +399,9 @@ int gnnis_create(gnnis_handle* out, int device) {
     return -1;
   }
   if (const char* e = getenv("GNNIS_GRAPHS")) c->use_graphs = atoi(e);   // debug: 0 = no CUDA-graph replay of evaluations
+  if (const char* e = getenv("GNNIS_NEIGHBORS")) c->nbr_mode = !strcmp(e, "cell") ? 1 : (!strcmp(e, "allpairs") ? 0 : -1);
+  if (const char* e = getenv("GNNIS_CELL_MIN")) c->nbr_cell_min = atoi(e);
+  if (const char* e = getenv("GNNIS_TAIL_SPLIT")) c->tail_split = atoi(e) != 0;
   if (const char* e = getenv("GNNIS_SPLIT")) c->split_max = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
   if (const char* e = getenv("GNNIS_STASH")) c->use_stash = atoi(e);      // 0: the edge adjoint always recomputes its activations
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
@@ -435,6 +456,7 @@ int gnnis_destroy(gnnis_handle h) {
                 &c->lb_count, &c->lb_active, &c->lb_stall, &c->lb_nevals};
   for (int** p : ip) dev_free(p);
   dev_free(&c->pair);
+  dev_free(&c->nbr_mask);
   dev_free(&c->perm);
   dev_free(&c->n_edges_dev);
   dev_free(&c->unit_ctr);
@@ -691,8 +713,12 @@ int gnnis_build_neighbors(gnnis_handle h, const float* pos_dev, int32_t predicat
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
   const int n = c->R * c->N;
-  if (launch_born_count(c, pos_dev, predicate, st)) return -1;
-  if (launch_fill_edges(c, pos_dev, predicate, row_ptr_dev, col_dev, nullptr, r_dev, col_dev ? capacity : 0, st)) return -1;
+  const bool cells = use_cell_list(c, (predicate & GNNIS_PREDICATE_CELL_LIST) ? 1 : ((predicate & GNNIS_PREDICATE_ALL_PAIRS) ? 0 : -1));
+  predicate &= 1;
+  if (launch_born_count(c, pos_dev, cells ? -1 : predicate, st)) return -1;
+  if (cells ? launch_cell_neighbors(c, pos_dev, predicate, row_ptr_dev, col_dev, nullptr, r_dev, col_dev ? capacity : 0, st)
+            : launch_fill_edges(c, pos_dev, predicate, row_ptr_dev, col_dev, nullptr, r_dev, col_dev ? capacity : 0, st))
+    return -1;
   GNNIS_CUDA_OK(cudaMemcpyAsync(row_ptr_dev + n, c->row_ptr + n, sizeof(int), cudaMemcpyDeviceToDevice, st));
   GNNIS_CUDA_OK(cudaMemcpyAsync(n_edges_host, c->n_edges_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   GNNIS_CUDA_OK(cudaStreamSynchronize(st));
@@ -847,13 +873,15 @@ const char* gnnis_describe(gnnis_handle h) {
   if (!c) return "";
   const bool tc = tc_path_fits(c);
   std::string d = "N=" + std::to_string(c->N) + " R=" + std::to_string(c->R) + " replicas_per_unit=" + std::to_string(c->G) +
-                  " units=" + std::to_string(c->n_units) + " split=" + std::to_string(c->split);
+                  " units=" + std::to_string(c->n_units) + " split=" + std::to_string(c->split) +
+                  (c->split > 1 && c->split_from > 0 ? " (replicas " + std::to_string(c->split_from) + ".." + std::to_string(c->R - 1) + " only)" : "");
   d += std::string(" edge_kernels=") + (tc ? "tcgen05" : "cuda-cores (unit tables do not fit next to the operand images)");
   if (tc) {
     d += std::string(" adjoint=") + (c->stash_on ? "stash" : (c->use_stash ? "recompute (stash exceeds the memory budget)" : "recompute (GNNIS_STASH=0)"));
     d += " tables=" + std::to_string(c->stash_on ? st_fwd_tables(c) : c->tab_mode);
   }
   d += " stash_bytes=" + std::to_string(c->stash_on ? (size_t)6 * ((size_t)c->edge_cap + kTileE) * 128 : (size_t)0);
+  d += std::string(" neighbors=") + (use_cell_list(c, -1) ? "cell-list" : "all-pairs");
   c->desc = d;
   return c->desc.c_str();
 }

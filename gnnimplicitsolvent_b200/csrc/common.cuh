@@ -120,6 +120,13 @@ struct Ctx {
   int split_max = 16;   // GNNIS_SPLIT=1 disables the split (debug / A-B)
   int split = 1;        // chosen by gnnis_set_replicas
   int split_eff = 1;    // used by the current evaluation (1 unless all edge kernels run on the tensor-core path)
+  // Tail split: with at least one full wave of units (R >= warp groups) only the replicas of the last, partly filled wave
+  // [split_from, R) are split, into as many parts as fit the idle groups -- the tail then takes 1/split of a wave (plus the
+  // overhead of a split) instead of a whole one.  0 = every replica is split (small batches).  GNNIS_TAIL_SPLIT=0 disables it.
+  int split_from = 0;
+  int tail_split = 1;
+  // units the tensor-core edge kernels and the tile permutation walk in the current evaluation
+  int eff_units() const { return split_eff > 1 ? split_from + (R - split_from) * split_eff : n_units; }
   // workspace (sized for R*N atoms, edge capacity grows on demand)
   size_t ws_atoms = 0;
   int ws_split = 0;   // split the workspace (Qbar parts) was sized for
@@ -128,6 +135,10 @@ struct Ctx {
   uint32_t* pair = nullptr;
   uint8_t* perm = nullptr;
   float* r_e = nullptr;
+  // cell-list neighbour back-end (cell_list.cu): bit mask of accepted sources per target, [n][ceil(N/32)]
+  uint32_t* nbr_mask = nullptr;
+  int nbr_mode = -1;        // GNNIS_NEIGHBORS: 0 all pairs, 1 cell list, -1 by size (cell list above nbr_cell_min atoms)
+  int nbr_cell_min = 768;   // GNNIS_CELL_MIN (measured: profiles/r2_h_neighbor_backends.jsonl)
   float *born = nullptr, *dBdI = nullptr, *born_s = nullptr, *dE_dBs = nullptr, *Bbar = nullptr, *dBs_dB = nullptr;
   float *P[3] = {nullptr, nullptr, nullptr}, *Q[3] = {nullptr, nullptr, nullptr}, *a[3] = {nullptr, nullptr, nullptr};
   float *o[3] = {nullptr, nullptr, nullptr};
@@ -204,9 +215,17 @@ struct Ctx {
 struct UnitSpan {
   int atom_base, n_tab, a0, a1, part;
 };
-__device__ __forceinline__ UnitSpan unit_span(int unit, int G, int N, int R, int S) {
+// With S > 1 the units [0, U0) are whole replicas and the sub-units of the replicas [U0, R) follow (U0 = 0: every replica
+// is split; U0 > 0: only the replicas of the last, partly filled wave are, Ctx::split_from).
+__device__ __forceinline__ UnitSpan unit_span(int unit, int G, int N, int R, int S, int U0 = 0) {
   UnitSpan u;
-  if (S <= 1) {
+  if (S > 1 && unit < U0) {
+    u.atom_base = unit * N;
+    u.n_tab = N;
+    u.a0 = 0;
+    u.a1 = N;
+    u.part = 0;
+  } else if (S <= 1) {
     const int rep0 = unit * G, rep1 = min(R, rep0 + G);
     u.atom_base = rep0 * N;
     u.n_tab = (rep1 - rep0) * N;
@@ -214,8 +233,9 @@ __device__ __forceinline__ UnitSpan unit_span(int unit, int G, int N, int R, int
     u.a1 = u.n_tab;
     u.part = 0;
   } else {
-    const int rep = unit / S;
-    u.part = unit - rep * S;
+    const int v = unit - U0;
+    const int rep = U0 + v / S;
+    u.part = v - (v / S) * S;
     u.atom_base = rep * N;
     u.n_tab = N;
     u.a0 = (u.part * N) / S;
@@ -256,6 +276,18 @@ __device__ __forceinline__ float eps_dist(float sx, float sy, float sz, float tx
   acc = __fmaf_rn(dy, dy, acc);
   acc = __fmaf_rn(dz, dz, acc);
   return __fsqrt_rn(acc);
+}
+
+// GNN edge predicate of an ordered pair (source s -> target t), shared by every neighbour back-end (all pairs and cell
+// list) and by the Born adjoint: predicate 0 = run path (eps-distance r < cutoff, GNN_Models.py:794-804), 1 = data path
+// (torch_cluster.radius_graph: sum((x_i - x_j)^2) < r^2, plain fp32 left-to-right); negative = "do not count"
+__device__ __forceinline__ bool in_cutoff(int predicate, float r, float sx, float sy, float sz, float tx, float ty,
+                                          float tz, float cutoff) {
+  if (predicate < 0) return false;
+  if (predicate == 0) return r < cutoff;
+  float ax = __fsub_rn(tx, sx), ay = __fsub_rn(ty, sy), az = __fsub_rn(tz, sz);
+  float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+  return d2 < __fmul_rn(cutoff, cutoff);
 }
 
 // MUFU-based reciprocal / log / exp / rsqrt (1-2 ulp) for the all-pairs kernels, which are bound by instruction issue:

@@ -174,13 +174,13 @@ __device__ __forceinline__ void zero_rows(float* __restrict__ dst, int nfloat) {
 // ------------------------------------------------------------------------------------------ tile permutation
 // For every 128-edge tile of every unit: positions sorted by (source, edge) -> tile-local edge index (uint8).
 // Computed once per evaluation (after the CSR fill), reused by the three adjoint launches.
-__global__ void __launch_bounds__(kTileE) tile_perm_kernel(int n_units, int G, int N, int R, int S,
+__global__ void __launch_bounds__(kTileE) tile_perm_kernel(int n_units, int G, int N, int R, int S, int U0,
                                                            const int* __restrict__ row_ptr,
                                                            const uint32_t* __restrict__ pair,
                                                            uint8_t* __restrict__ perm) {
   __shared__ int sKey[kTileE];
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const UnitSpan us = unit_span(unit, G, N, R, S);
+    const UnitSpan us = unit_span(unit, G, N, R, S, U0);
     const int e_begin = row_ptr[us.atom_base + us.a0], e_end = row_ptr[us.atom_base + us.a1];
     for (int t0 = e_begin; t0 < e_end; t0 += kTileE) {
       const int e = t0 + threadIdx.x;
@@ -560,7 +560,7 @@ static EdgeArgs make_args(Ctx* c, int l) {
 // barriers; the warps of a CTA share a unit and take its tiles round-robin): the warp walks its rows 32 at a time in
 // order, lanes with equal sources are grouped (ballots), so the rank inside a bin follows the edge order; the bins live in
 // the warp's own shared-memory slice.
-__global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, int G, int N, int R, int S,
+__global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, int G, int N, int R, int S, int U0,
                                                                  const int* __restrict__ row_ptr,
                                                                  const uint32_t* __restrict__ pair,
                                                                  uint8_t* __restrict__ perm) {
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, in
   int* bins = sbins[warp];
   constexpr int kWarps = kTileE / 32;
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const UnitSpan us = unit_span(unit, G, N, R, S);
+    const UnitSpan us = unit_span(unit, G, N, R, S, U0);
     const int e_begin = row_ptr[us.atom_base + us.a0], e_end = row_ptr[us.atom_base + us.a1];
     for (int t0 = e_begin + warp * kTileE; t0 < e_end; t0 += kWarps * kTileE) {
       int key[4], in_bin[4];   // in_bin: rows of this tile with the same source that come before this one
@@ -632,11 +632,11 @@ __global__ void __launch_bounds__(kTileE) tile_perm_count_kernel(int n_units, in
 }
 
 int launch_tile_perm(Ctx* c, cudaStream_t st) {
-  const int nu = c->n_units * c->split_eff;
+  const int nu = c->eff_units();
   if (c->G * c->N <= 128)
-    tile_perm_count_kernel<<<(nu < 16 * c->num_sms ? nu : 16 * c->num_sms), kTileE, 0, st>>>(nu, c->G, c->N, c->R, c->split_eff, c->row_ptr, c->pair, c->perm);
+    tile_perm_count_kernel<<<(nu < 16 * c->num_sms ? nu : 16 * c->num_sms), kTileE, 0, st>>>(nu, c->G, c->N, c->R, c->split_eff, c->split_eff > 1 ? c->split_from : 0, c->row_ptr, c->pair, c->perm);
   else
-    tile_perm_kernel<<<(nu < 8 * c->num_sms ? nu : 8 * c->num_sms), kTileE, 0, st>>>(nu, c->G, c->N, c->R, c->split_eff, c->row_ptr, c->pair, c->perm);
+    tile_perm_kernel<<<(nu < 8 * c->num_sms ? nu : 8 * c->num_sms), kTileE, 0, st>>>(nu, c->G, c->N, c->R, c->split_eff, c->split_eff > 1 ? c->split_from : 0, c->row_ptr, c->pair, c->perm);
   GNNIS_LAUNCH_CHECK();
   return 0;
 }

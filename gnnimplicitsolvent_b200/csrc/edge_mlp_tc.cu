@@ -71,6 +71,7 @@ struct EdgeTcArgs {
   int unit_atoms;
   unsigned* unit_counter; // dynamic unit hand-out of the adjoint, zeroed at the start of every evaluation
   int S;                  // sub-units per replica (Ctx::split_eff)
+  int U0;                 // first split replica (Ctx::split_from): units [0, U0) are whole replicas
   size_t qbar_stride;     // floats between the partial Qbar tables of consecutive parts
   // activation stash (forward with forces -> adjoint): 16-bit codes of silu'(u) and silu'(w), [E][64] each, row e =
   // 128 bytes whose 16-byte chunks are XOR-swizzled with (row in tile & 7) -- the shared-memory image of a tile
@@ -360,8 +361,9 @@ int st_bwd_tables(const Ctx* c) {
 // ---------------------------------------------------------------------------------------------- launchers
 static EdgeTcArgs make_tc_args(Ctx* c, int l, int terms = 3) {
   EdgeTcArgs g{};
-  g.n_units = c->n_units * c->split_eff;
+  g.n_units = c->eff_units();
   g.S = c->split_eff;
+  g.U0 = c->split_eff > 1 ? c->split_from : 0;
   g.unit_counter = c->unit_ctr ? c->unit_ctr + l : nullptr;
   g.qbar_stride = (size_t)c->R * c->N * 64;
   g.G = c->G;
@@ -422,7 +424,7 @@ bool tc_path_fits(const Ctx* c) { return fwd_tc_smem(c) <= 227 * 1024 && bwd_tc_
 // Units are dealt out CTA-first (unit u -> CTA u % grid, group (u / grid) % 2), so that with fewer units than
 // 2 x #SM every unit gets an SM of its own before any SM runs two groups.
 static int tc_grid(const Ctx* c) {
-  const int nu = c->n_units * c->split_eff;
+  const int nu = c->eff_units();
   return nu < c->num_sms ? nu : c->num_sms;
 }
 
@@ -651,7 +653,7 @@ __device__ __forceinline__ void issue_next_unit(IssueState& x, const EdgeTcArgs&
       x.done = true;
       return;
     }
-    const UnitSpan us = unit_span(x.unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
+    const UnitSpan us = unit_span(x.unit, g.G, g.N, g.R, SPLIT ? g.S : 1, g.U0);
     const int e_begin = g.row_ptr[us.atom_base + us.a0], e_end = g.row_ptr[us.atom_base + us.a1];
     if (e_begin < e_end) {
       x.t0 = e_begin;
@@ -770,7 +772,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
-      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
+      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1, g.U0);
       const int atom0 = us.atom_base, natoms = us.n_tab;
       const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
       float* gA = g.a_out + (size_t)atom0 * 64;
@@ -1046,14 +1048,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
     // adjoint 3.59 -> 3.57 ms at C2)
     __shared__ int s_next[kGroups];
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit = s_next[grp]) {
-      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
+      const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1, g.U0);
       const int atom0 = us.atom_base, natoms = us.n_tab;
       const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
       const float* gP = g.P + (size_t)atom0 * 64;
       const float* gAb = g.abar + (size_t)atom0 * 64;
       float* gPb = g.Pbar + (size_t)atom0 * 64;
       // this part's (partial) Qbar rows; recomputed where it is needed instead of kept in registers across the tiles
-      auto qbar_rows = [&]() { return g.Qbar + (SPLIT ? (size_t)(unit % g.S) * g.qbar_stride : (size_t)0) + (size_t)atom0 * 64; };
+      auto qbar_rows = [&]() { return g.Qbar + (SPLIT ? (size_t)us.part * g.qbar_stride : (size_t)0) + (size_t)atom0 * 64; };
       const float* tQ;
       float* tQb;
       constexpr int ldq = Q_SM ? kTabLd : 64, ld = QB_SM ? kTabLd : 64;   // ld: row pitch of the Qbar accumulator
@@ -1428,12 +1430,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
 
   // the first unit of a group is fixed, the following ones come from a global counter (see edge_bwd_ws_kernel)
   for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit = s_next[grp]) {
-    const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1);
+    const UnitSpan us = unit_span(unit, g.G, g.N, g.R, SPLIT ? g.S : 1, g.U0);
     const int atom0 = us.atom_base, natoms = us.n_tab;
     const int e_begin = g.row_ptr[atom0 + us.a0], e_end = g.row_ptr[atom0 + us.a1];
     const float* gAb = g.abar + (size_t)atom0 * 64;
     float* gPb = g.Pbar + (size_t)atom0 * 64;
-    auto qbar_rows = [&]() { return g.Qbar + (SPLIT ? (size_t)(unit % g.S) * g.qbar_stride : (size_t)0) + (size_t)atom0 * 64; };
+    auto qbar_rows = [&]() { return g.Qbar + (SPLIT ? (size_t)us.part * g.qbar_stride : (size_t)0) + (size_t)atom0 * 64; };
     constexpr int ld = QB_SM ? kTabLd : 64;   // row pitch of the Qbar accumulator
     float* tQb = QB_SM ? sTab : qbar_rows();
     if (SPLIT) zero_rows_n(gPb + (size_t)us.a0 * 64, 64, us.a1 - us.a0, gt, kWsGroupThreads);   // the targets this unit owns
@@ -1667,8 +1669,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
 }
 
 // Qbar = sum over the parts of a split replica, in part order (deterministic)
-__global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t n4, size_t stride4, int S) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+__global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t first4, size_t n4, size_t stride4, int S) {
+  for (size_t i = first4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 a = qbar[i];
     for (int p = 1; p < S; ++p) {
       const float4 b = qbar[i + (size_t)p * stride4];
@@ -1787,9 +1789,10 @@ int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, int stash,
   if (rc) return rc;
   GNNIS_LAUNCH_CHECK();
   if (c->split_eff > 1) {
-    const size_t n4 = (size_t)c->R * c->N * 16;
-    const int blocks = (int)((n4 + 255) / 256 < 4 * (size_t)c->num_sms ? (n4 + 255) / 256 : 4 * (size_t)c->num_sms);
-    sum_qbar_parts_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(c->Qbar), n4, n4, c->split_eff);
+    const size_t n4 = (size_t)c->R * c->N * 16, first4 = (size_t)c->split_from * c->N * 16;   // only split replicas have parts
+    const size_t w4 = n4 - first4;
+    const int blocks = (int)((w4 + 255) / 256 < 4 * (size_t)c->num_sms ? (w4 + 255) / 256 : 4 * (size_t)c->num_sms);
+    sum_qbar_parts_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(c->Qbar), first4, n4, n4, c->split_eff);
     GNNIS_LAUNCH_CHECK();
   }
   return 0;

@@ -75,15 +75,6 @@ __device__ __forceinline__ float born_integral_dr(float r, float rho_i, float rh
   return g;
 }
 
-__device__ __forceinline__ bool in_cutoff(int predicate, float r, float sx, float sy, float sz, float tx, float ty,
-                                          float tz, float cutoff) {
-  if (predicate == 0) return r < cutoff;
-  // torch_cluster radius_graph: sum((x_i - x_j)^2) < r^2, plain fp32 left-to-right
-  float ax = __fsub_rn(tx, sx), ay = __fsub_rn(ty, sy), az = __fsub_rn(tz, sz);
-  float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
-  return d2 < __fmul_rn(cutoff, cutoff);
-}
-
 // The all-pairs kernels come in two shapes (template LANES): one thread per target (LANES = 1: large batches, where
 // they are bound by instruction issue) or four lanes per target that share the source loop and combine their partial
 // sums with two shuffles in a fixed order (LANES = 4: small batches, where one thread's 50-iteration dependent chain
@@ -161,8 +152,9 @@ born_count_kernel(const float* __restrict__ pos, int n, int N, int U, const floa
   I = lanes_sum<LANES>(I);
   mydeg = lanes_sum_int<LANES>(mydeg);
   if (sub != 0) mydeg = 0;           // one lane per target carries the degree into the block sum
+  const bool count = predicate >= 0;   // negative: the cell-list back-end (cell_list.cu) produces deg / blk_sum
   if (skipped && sub == 0) {
-    deg[i] = 0;   // finished replica: no edges, nothing downstream touches it
+    if (count) deg[i] = 0;   // finished replica: no edges, nothing downstream touches it
   } else if (act && sub == 0) {
     float rho_i = srho[a];
     float radius = rho_i + kOffset;
@@ -173,8 +165,9 @@ born_count_kernel(const float* __restrict__ pos, int n, int N, int U, const floa
     float B = 1.0f / (1.0f / rho_i - T / radius);
     born[i] = B;
     dBdI[i] = B * B * (1.0f - T * T) * (al - 2.0f * be * psi + 3.0f * ga * psi * psi) * rho_i / radius;
-    deg[i] = mydeg;
+    if (count) deg[i] = mydeg;
   }
+  if (!count) return;
   atomicAdd(&s_blk, mydeg);   // integer: order-independent
   __syncthreads();
   if (threadIdx.x == 0) blk_sum[blockIdx.x] = s_blk;
@@ -472,6 +465,14 @@ __global__ void reduce_energy_kernel(const float* __restrict__ e_atom, const flo
 // ---------------------------------------------------------------- host launchers
 static size_t stage_atoms_max(int N) { return (size_t)kPairThreads + 2 * (size_t)N; }
 
+int launch_scan_blocks(Ctx* c, cudaStream_t st) {
+  const int n = c->R * c->N;
+  const int nblk = (n + kPairThreads - 1) / kPairThreads;
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(c->blk_sum, nblk, c->n_edges_dev, c->row_ptr + n);
+  GNNIS_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_born_count(Ctx* c, const float* pos, int predicate, cudaStream_t st) {
   int n = c->R * c->N;
   int nblk = (n + kPairThreads - 1) / kPairThreads;
@@ -488,9 +489,8 @@ int launch_born_count(Ctx* c, const float* pos, int predicate, cudaStream_t st) 
                                                           c->deg, c->blk_sum, c->skip_state);
   }
   GNNIS_LAUNCH_CHECK();
-  scan_blocks_kernel<<<1, 1024, 0, st>>>(c->blk_sum, nblk, c->n_edges_dev, c->row_ptr + n);
-  GNNIS_LAUNCH_CHECK();
-  return 0;
+  if (predicate < 0) return 0;   // degrees, block sums and their scan come from the cell-list back-end
+  return launch_scan_blocks(c, st);
 }
 
 int launch_fill_edges(Ctx* c, const float* pos, int predicate, int* row_ptr, int* col, uint32_t* pair, float* r_e,

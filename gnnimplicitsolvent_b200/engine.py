@@ -180,7 +180,7 @@ class Engine:
 
     # ------------------------------------------------------------------ hot path
     def energy_force(self, positions: torch.Tensor, *, delta=False, forces=True, gb_only=False, cuda_cores=False,
-                     data_predicate=False, vacuum_only=False, tf32x1=False, bf16=False, fp16=False, extra_flags: int = 0,
+                     data_predicate=False, vacuum_only=False, tf32x1=False, bf16=False, fp16=False, cell_list=False, extra_flags: int = 0,
                      out_energy: Optional[torch.Tensor] = None, out_force: Optional[torch.Tensor] = None):
         """positions [R,N,3] (or [R*N,3]) fp32 on the engine's device -> (E[R], F[R,N,3] or None)."""
         p = self._pos(positions)
@@ -191,7 +191,8 @@ class Engine:
         flags = ((_lib.FLAG_DELTA if delta else 0) | (0 if forces else _lib.FLAG_NO_FORCES)
                  | (_lib.FLAG_GB_ONLY if gb_only else 0) | (_lib.FLAG_MLP_CUDA_CORES if cuda_cores else 0)
                  | (_lib.FLAG_DATA_PREDICATE if data_predicate else 0) | (_lib.FLAG_VACUUM_ONLY if vacuum_only else 0)
-                 | (_lib.FLAG_MLP_TF32X1 if tf32x1 else 0) | (_lib.FLAG_MLP_BF16 if bf16 else 0) | (_lib.FLAG_MLP_FP16 if fp16 else 0) | int(extra_flags))
+                 | (_lib.FLAG_MLP_TF32X1 if tf32x1 else 0) | (_lib.FLAG_MLP_BF16 if bf16 else 0) | (_lib.FLAG_MLP_FP16 if fp16 else 0)
+                 | (_lib.FLAG_CELL_LIST if cell_list else 0) | int(extra_flags))
         self._check(self.lib.gnnis_energy_force(self._h, p.data_ptr(), e.data_ptr(), f.data_ptr() if forces else None,
                                                 flags, self._stream()))
         return e, f
@@ -238,12 +239,13 @@ class Engine:
         self._check(self.lib.gnnis_last_edge_count(self._h, C.byref(v), self._stream()))
         return int(v.value)
 
-    def build_neighbors(self, positions: torch.Tensor, predicate: str = "run"):
-        """Sorted CSR radius graph (target-major, ascending source): (row_ptr[n+1], col[E], r[E])."""
+    def build_neighbors(self, positions: torch.Tensor, predicate: str = "run", backend: Optional[str] = None):
+        """Sorted CSR radius graph (target-major, ascending source): (row_ptr[n+1], col[E], r[E]).  backend: "cell" (cell
+        list), "allpairs", or None = the handle's default; both give the same bytes."""
         p = self._pos(positions)
         n = self.n_rep * self.n_atoms
         row_ptr = torch.empty(n + 1, dtype=torch.int32, device=self.device)
-        pred = 0 if predicate == "run" else 1
+        pred = (0 if predicate == "run" else 1) | {None: 0, "cell": _lib.PREDICATE_CELL_LIST, "allpairs": _lib.PREDICATE_ALL_PAIRS}[backend]
         ne = C.c_int64(0)
         cap = max(1, n * min(self.n_atoms - 1, 64))
         while True:

@@ -47,6 +47,12 @@ typedef struct gnnis_ctx* gnnis_handle;
                                       (data path, GNN_Models.py:345-357), instead of eps-distance r < cutoff */
 #define GNNIS_FLAG_VACUUM_ONLY 0x40u  /* only the vacuum force field of gnnis_set_forcefield (no GB, no GNN): the
                                       reference's vacuum "_ref_system" simulation                          */
+#define GNNIS_FLAG_CELL_LIST 0x200u   /* build the GNN graph with the cell-list back-end (csrc/cell_list.cu: atoms binned into
+                                      cells >= cutoff wide, 27-cell candidate search, bit-mask rows) instead of the
+                                      all-pairs sweep; the CSR arrays are bit-identical.  Default for replicas of more than
+                                      GNNIS_CELL_MIN atoms (environment, default 768); GNNIS_NEIGHBORS=cell|allpairs
+                                      forces one back-end for every call                                    */
+#define GNNIS_FLAG_ALL_PAIRS 0x400u   /* the opposite: the all-pairs sweep of pair_kernels.cu for this call                */
 #define GNNIS_FLAG_MLP_CUDA_CORES 0x10u /* force the fp32 CUDA-core edge kernels instead of the default
                                       tcgen05 tensor-core kernels (3xTF32, fp32-accurate)                 */
 
@@ -95,7 +101,11 @@ int gnnis_set_model_constants(gnnis_handle h, float fraction, float scaling_fact
  * predicate 1 = data path  sum((x_i-x_j)^2) < cutoff^2 (torch_cluster semantics).
  * row_ptr_dev [R*N+1] int32, col_dev [capacity] int32 (global source index), r_dev [capacity] fp32
  * eps-distance (may be NULL).  *n_edges_host receives E (this call synchronises the stream).
+ * predicate | GNNIS_PREDICATE_CELL_LIST selects the cell-list back-end, predicate | GNNIS_PREDICATE_ALL_PAIRS the
+ * all-pairs sweep (neither: the handle's default, see GNNIS_FLAG_CELL_LIST); both give the same bytes.
  * Returns -2 (nothing written to col/r) when capacity < E. */
+#define GNNIS_PREDICATE_CELL_LIST 0x10
+#define GNNIS_PREDICATE_ALL_PAIRS 0x20
 int gnnis_build_neighbors(gnnis_handle h, const float* pos_dev, int32_t predicate, int32_t* row_ptr_dev,
                           int32_t* col_dev, float* r_dev, int64_t capacity, int64_t* n_edges_host, void* stream);
 

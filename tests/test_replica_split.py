@@ -94,3 +94,45 @@ def test_table_mode_and_split_boundaries(N, R, monkeypatch):
     assert bool(torch.isfinite(o["forces"]).all()) and bool(torch.isfinite(f).all())
     np.testing.assert_allclose(e[:k].cpu().numpy(), o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
     assert rel_rms(f[:k].cpu().numpy(), o["forces"].numpy()) < F_RRMS
+
+
+@pytest.mark.parametrize("N,R", [(50, 297), (50, 300), (50, 433), (50, 444), (50, 1024), (100, 592 + 37), (37, 296 + 150)])
+def test_tail_split_vs_unsplit_and_oracle(N, R, monkeypatch):
+    """Batches of at least one full wave (296 warp groups): only the replicas of the last, partly filled wave are split
+    (Ctx::split_from).  Same inputs with GNNIS_TAIL_SPLIT=0 (no split at all) -- only the summation order of the split
+    replicas may differ --, the first / boundary / last replicas against the CPU oracle, bitwise reproducibility."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    from oracle import gnn_oracle as O
+    monkeypatch.delenv("GNNIS_SPLIT", raising=False)
+    mol = synth.synth_molecule(N, seed=N + 11)
+    sd = O.random_state_dict(seed=N + 5)
+    pos_h = synth.conformers(mol["pos"], R, 0.01, seed=R + 3).astype(np.float32)
+    pos = torch.from_numpy(pos_h).cuda()
+    sids = [(7 * r + 1) % 39 for r in range(R)]
+    diel = [synth.SOLVENT_DIELECTRICS[s] for s in sids]
+    out = {}
+    for tail in ("0", "1"):
+        monkeypatch.setenv("GNNIS_TAIL_SPLIT", tail)
+        eng = Engine(mol["params"], sd)
+        eng.set_replicas(R, sids, diel)
+        desc = eng.describe()
+        e, f = eng.energy_force(pos)
+        e2, f2 = eng.energy_force(pos)
+        e3, f3 = eng.energy_force(pos)                      # third call: CUDA-graph replay
+        assert torch.equal(e, e2) and torch.equal(f, f2) and torch.equal(e, e3) and torch.equal(f, f3)
+        out[tail] = (e.cpu().numpy(), f.cpu().numpy(), desc)
+        eng.close()
+    assert "split=1" in out["0"][2]
+    rem = R % 296
+    first = R - rem
+    if 296 // rem >= 2:
+        assert f"only)" in out["1"][2] and f"replicas {first}.." in out["1"][2], out["1"][2]
+        # whole replicas ahead of the tail are computed exactly as without the split
+        assert np.array_equal(out["0"][0][:first], out["1"][0][:first]) and np.array_equal(out["0"][1][:first], out["1"][1][:first])
+    np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=2e-6, atol=1e-4)
+    assert rel_rms(out["1"][1], out["0"][1]) < 2e-5
+    idx = sorted({0, first - 1, first, min(first + 1, R - 1), R - 1})
+    o = O.evaluate(mol["params"], pos_h[idx], [sids[i] for i in idx], [diel[i] for i in idx], sd)
+    np.testing.assert_allclose(out["1"][0][idx], o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
+    assert rel_rms(out["1"][1][idx], o["forces"].numpy()) < F_RRMS
