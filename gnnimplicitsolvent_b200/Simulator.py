@@ -206,10 +206,9 @@ class Simulator:
 
     @property
     def hdf5_loc(self):
-        """Trajectory location (Simulator.py:405-417).  h5py is absent in this image: run_simulation writes the
-        trajectory as `<stub>_output.coordinates.npy` + `<stub>_output.meta.npz` (trajectory.TrajectoryWriter, same
-        dataset names and units as the MDTraj HDF5 file) and trajectory.export_mdtraj_h5 converts them to this path
-        where h5py exists."""
+        """Trajectory location (Simulator.py:405-417): the MDTraj-convention HDF5 file run_simulation leaves behind.  During
+        the run the frames go to `<stub>_output.coordinates.npy` + `<stub>_output.meta.npz` (trajectory.TrajectoryWriter,
+        memory-mapped); trajectory.export_mdtraj_h5 converts them to this path when the run ends."""
         return self._work_folder + self._file_stub() + "_output.h5"
 
     @property
@@ -240,6 +239,8 @@ class Simulator:
                                   elements=self._mol.elements, n_constraints=self._n_constraints,
                                   first_step=self._steps_done, eval_flags=self._flags())
         self._steps_done += (n_steps // n_interval) * n_interval
+        if n_steps // n_interval > 0:
+            trajectory.export_mdtraj_h5(prefix, prefix + "_output.h5")    # = self.hdf5_loc when workfolder is the default
         return prefix
 
 

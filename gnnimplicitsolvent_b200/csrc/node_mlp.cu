@@ -111,12 +111,26 @@ __global__ void node_pre1_kernel(int n, int N, const float* __restrict__ born, c
                                  const float* __restrict__ rho, const float* __restrict__ Wi_t,
                                  const float* __restrict__ Wj_t, const float* __restrict__ b1, float* __restrict__ P,
                                  float* __restrict__ Q) {
+  // one thread per (atom, four channels): 16-byte stores, the per-channel arithmetic is unchanged
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)n * 64) return;
-  int i = (int)(t >> 6), c = (int)(t & 63), a = i % N;
-  float h0 = born[i], h1 = q[a], h2 = rho[a];
-  P[t] = fmaf(h2, Wi_t[128 + c], fmaf(h1, Wi_t[64 + c], h0 * Wi_t[c])) + b1[c];
-  Q[t] = fmaf(h2, Wj_t[128 + c], fmaf(h1, Wj_t[64 + c], h0 * Wj_t[c]));
+  if (t >= (size_t)n * 16) return;
+  const int i = (int)(t >> 4), c = (int)(t & 15) * 4, a = i % N;
+  const float h0 = born[i], h1 = q[a], h2 = rho[a];
+  const float4 wi0 = *reinterpret_cast<const float4*>(Wi_t + c), wi1 = *reinterpret_cast<const float4*>(Wi_t + 64 + c),
+               wi2 = *reinterpret_cast<const float4*>(Wi_t + 128 + c), bb = *reinterpret_cast<const float4*>(b1 + c);
+  const float4 wj0 = *reinterpret_cast<const float4*>(Wj_t + c), wj1 = *reinterpret_cast<const float4*>(Wj_t + 64 + c),
+               wj2 = *reinterpret_cast<const float4*>(Wj_t + 128 + c);
+  float4 p, qv;
+  p.x = fmaf(h2, wi2.x, fmaf(h1, wi1.x, h0 * wi0.x)) + bb.x;
+  p.y = fmaf(h2, wi2.y, fmaf(h1, wi1.y, h0 * wi0.y)) + bb.y;
+  p.z = fmaf(h2, wi2.z, fmaf(h1, wi1.z, h0 * wi0.z)) + bb.z;
+  p.w = fmaf(h2, wi2.w, fmaf(h1, wi1.w, h0 * wi0.w)) + bb.w;
+  qv.x = fmaf(h2, wj2.x, fmaf(h1, wj1.x, h0 * wj0.x));
+  qv.y = fmaf(h2, wj2.y, fmaf(h1, wj1.y, h0 * wj0.y));
+  qv.z = fmaf(h2, wj2.z, fmaf(h1, wj1.z, h0 * wj0.z));
+  qv.w = fmaf(h2, wj2.w, fmaf(h1, wj1.w, h0 * wj0.w));
+  *reinterpret_cast<float4*>(P + (size_t)i * 64 + c) = p;
+  *reinterpret_cast<float4*>(Q + (size_t)i * 64 + c) = qv;
 }
 
 // smem: sA[64][68] | sG[64][132]
@@ -389,7 +403,7 @@ static NodeArgs base_args(Ctx* c, int l) {
 
 int launch_node_pre1(Ctx* c, cudaStream_t st) {
   int n = c->R * c->N;
-  size_t total = (size_t)n * 64;
+  size_t total = (size_t)n * 16;
   node_pre1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, c->N, c->born, c->q, c->rho, c->L[0].Wi_t,
                                                                     c->L[0].Wj_t, c->L[0].b1, c->P[0], c->Q[0]);
   GNNIS_LAUNCH_CHECK();

@@ -12,15 +12,17 @@ Reference behaviour that is mirrored here:
 * `get_energies(sim, traj)` (`Simulation/helper_functions.py:901-918`) re-evaluates a trajectory frame by frame on a
   one-replica system -> `get_energies(engine, xyz)` evaluates all frames as replicas of one batched call.
 
-File format.  HDF5 (h5py / mdtraj) is not available in this image, so the writer produces plain numpy files that hold
-exactly the datasets of an MDTraj HDF5 file with the same names, shapes and units:
+File format.  While a run is in progress the frames go to plain numpy files (memory-mapped, so that device-to-host copies
+land in the file directly) that hold exactly the datasets of an MDTraj HDF5 file with the same names, shapes and units:
 
     <prefix>_output.coordinates.npy   float32 [n_frames, R * N, 3]  nanometers   (memory-mapped while it is written)
     <prefix>_output.meta.npz          time [n_frames] picoseconds, potentialEnergy [n_frames, R] kJ/mol,
                                       temperature [n_frames, R] kelvin, chainid [R * N], element [N], n_replicas, n_atoms
     <prefix>_log.txt                  the StateDataReporter columns
 
-`export_mdtraj_h5` converts them to a real MDTraj HDF5 file on a machine that has h5py.
+`export_mdtraj_h5` converts them to the MDTraj-convention HDF5 file `<prefix>_output.h5` that the reference's
+`HDF5Reporter` writes and `mdtraj.load` reads (h5py where present; here the bytes come from `hdf5_min.py`, a writer for the
+"earliest" HDF5 structures -- unpinned against libhdf5, which does not exist in this image).
 """
 from __future__ import annotations
 
@@ -110,7 +112,13 @@ def load_trajectory(prefix: str):
 
 def load_parallel_traj(file: str, nrep: int) -> List[np.ndarray]:
     """One [frames, N, 3] array per replica (chain), as `Analysis/analysis.py:2032-2037` returns one trajectory per
-    `chainid`.  `file` is the prefix given to TrajectoryWriter."""
+    `chainid`.  `file` is the prefix given to TrajectoryWriter, or the `.h5` file export_mdtraj_h5 wrote from it (selected
+    by chain id, as `traj.top.select('chainid %i')` does)."""
+    if file.endswith(".h5"):
+        xyz, _, chainid, _ = load_mdtraj_h5(file)
+        if nrep > int(chainid.max()) + 1:
+            raise ValueError(f"trajectory holds {int(chainid.max()) + 1} replicas, {nrep} requested")
+        return [xyz[:, chainid == r, :] for r in range(nrep)]
     xyz, meta = load_trajectory(file)
     R, N = int(meta["n_replicas"]), int(meta["n_atoms"])
     if nrep > R:
@@ -205,15 +213,8 @@ def get_energies(engine, xyz, solvent_id: int = 0, dielectric: float = 78.5, bat
     return out
 
 
-def export_mdtraj_h5(prefix: str, out_file: str, residue_name: str = "MOL"):
-    """Writes an MDTraj-convention HDF5 file (what the reference's HDF5Reporter produces: `coordinates` nm, `time` ps,
-    `topology` JSON with one chain per replica) from a TrajectoryWriter output.  Needs h5py; that package is not in
-    this image, so this function is NOT exercised by the tests here."""
-    import h5py  # noqa: PLC0415  (deliberately late: optional dependency)
-
-    xyz, meta = load_trajectory(prefix)
-    R, N = int(meta["n_replicas"]), int(meta["n_atoms"])
-    elements = [str(e) for e in meta["element"]]
+def _mdtraj_topology(R: int, N: int, elements, residue_name: str = "MOL") -> dict:
+    """MDTraj's JSON topology: one chain (and one residue) per replica, as the reference's replicated OpenMM system."""
     chains, idx = [], 0
     for r in range(R):
         atoms = []
@@ -221,19 +222,55 @@ def export_mdtraj_h5(prefix: str, out_file: str, residue_name: str = "MOL"):
             atoms.append({"index": idx, "name": f"{elements[a]}{a + 1}", "element": elements[a]})
             idx += 1
         chains.append({"index": r, "residues": [{"index": r, "name": residue_name, "resSeq": 1, "atoms": atoms}]})
-    topology = {"chains": chains, "bonds": []}
+    return {"chains": chains, "bonds": []}
+
+
+def export_mdtraj_h5(prefix: str, out_file: str, residue_name: str = "MOL"):
+    """Writes the MDTraj-convention HDF5 file the reference's HDF5Reporter produces (`Simulation/Simulator.py:364-401`:
+    `coordinates` nm, `time` ps, `potentialEnergy` kJ/mol, `topology` JSON with one chain per replica, the Pande-convention
+    root attributes) from a TrajectoryWriter output.  Uses h5py where it exists; in this image (no h5py / PyTables /
+    libhdf5) the bytes are laid out by `hdf5_min.write` (contiguous datasets, "earliest" HDF5 structures)."""
+    xyz, meta = load_trajectory(prefix)
+    R, N = int(meta["n_replicas"]), int(meta["n_atoms"])
+    topology = json.dumps(_mdtraj_topology(R, N, [str(e) for e in meta["element"]], residue_name)).encode("ascii")
+    root = {"conventions": "Pande", "conventionVersion": "1.1", "program": "gnnimplicitsolvent_b200", "programVersion": "0.1",
+            "application": "gnnis", "title": os.path.basename(prefix)}
+    data = {"coordinates": np.asarray(xyz, np.float32), "time": meta["time"].astype(np.float32),
+            "potentialEnergy": np.nansum(meta["potentialEnergy"], axis=1).astype(np.float32),
+            "topology": np.array([topology], dtype=f"S{len(topology)}")}
+    units = {"coordinates": {"units": "nanometers"}, "time": {"units": "picoseconds"},
+             "potentialEnergy": {"units": "kilojoules_per_mole"}}
+    try:
+        import h5py  # noqa: PLC0415  (optional dependency)
+    except ImportError:
+        from . import hdf5_min
+        hdf5_min.write(out_file, data, root, units)
+        return out_file
     with h5py.File(out_file, "w") as f:
-        f.attrs["conventions"] = "Pande"
-        f.attrs["conventionVersion"] = "1.1"
-        f.attrs["program"] = "gnnimplicitsolvent_b200"
-        f.attrs["programVersion"] = "0.1"
-        f.attrs["application"] = "gnnis"
-        f.attrs["title"] = os.path.basename(prefix)
-        c = f.create_dataset("coordinates", data=np.asarray(xyz), dtype="f4")
-        c.attrs["units"] = "nanometers"
-        t = f.create_dataset("time", data=meta["time"].astype("f4"))
-        t.attrs["units"] = "picoseconds"
-        pe = f.create_dataset("potentialEnergy", data=np.nansum(meta["potentialEnergy"], axis=1).astype("f4"))
-        pe.attrs["units"] = "kilojoules_per_mole"
-        f.create_dataset("topology", data=np.array([json.dumps(topology).encode("ascii")]))
+        for k, v in root.items():
+            f.attrs[k] = v
+        for k, v in data.items():
+            d = f.create_dataset(k, data=v)
+            for ak, av in units.get(k, {}).items():
+                d.attrs[ak] = av
     return out_file
+
+
+def load_mdtraj_h5(file: str):
+    """-> (coordinates [frames, atoms, 3] nm, time [frames] ps, chainid [atoms], elements [atoms]) of an MDTraj-convention
+    HDF5 file written by export_mdtraj_h5 (h5py where present, hdf5_min.read otherwise)."""
+    try:
+        import h5py  # noqa: PLC0415
+        with h5py.File(file, "r") as f:
+            data = {k: f[k][...] for k in ("coordinates", "time", "topology")}
+    except ImportError:
+        from . import hdf5_min
+        data, _, _ = hdf5_min.read(file)
+    top = json.loads(bytes(data["topology"].reshape(-1)[0]).decode("ascii"))
+    chainid, elements = [], []
+    for ch in top["chains"]:
+        for res in ch["residues"]:
+            for at in res["atoms"]:
+                chainid.append(ch["index"])
+                elements.append(at["element"])
+    return data["coordinates"], data["time"], np.asarray(chainid), elements

@@ -158,6 +158,9 @@ def test_run_simulation_writes_trajectory_and_log(tmp_path):
     log = open(sim.log_loc).read().strip().splitlines()
     assert len(log) == 5 and log[0].startswith('#"Step"')
     assert sim.hdf5_loc == prefix + "_output.h5" and sim.log_loc == prefix + "_log.txt"
+    # the HDF5 container the reference's analysis reads (analysis.py:2032-2037): one chain per replica
+    per_rep = trajectory.load_parallel_traj(sim.hdf5_loc, 2)
+    np.testing.assert_array_equal(per_rep[1], np.asarray(xyz)[:, 13:26])
 
 
 @pytest.mark.gpu

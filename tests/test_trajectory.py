@@ -91,3 +91,72 @@ def test_run_simulation_and_get_energies(tmp_path):
     rep0 = trajectory.load_parallel_traj(prefix, 1)[0]
     e_frames = trajectory.get_energies(eng, rep0)
     np.testing.assert_allclose(e_frames, meta["potentialEnergy"][:, 0], rtol=2e-5, atol=1e-3)
+
+
+def test_hdf5_container_round_trip_and_structure(tmp_path):
+    """The MDTraj-convention HDF5 file (Simulator.py:364-401 writes it through HDF5Reporter, analysis.py:2032-2037 reads it
+    with mdtraj.load).  libhdf5 / h5py do not exist in this image, so the writer of hdf5_min.py is checked (a) by reading
+    the file back with the module's independent parser and (b) field by field against the HDF5 File Format Specification
+    (version-0 superblock, symbol-table root group, version-1 object headers)."""
+    import struct
+    from gnnimplicitsolvent_b200 import hdf5_min
+    R, N, F = 3, 5, 4
+    rng = np.random.default_rng(1)
+    frames = rng.normal(size=(F, R, N, 3)).astype(np.float32)
+    prefix = str(tmp_path / "mol_GNN_0_7")
+    with trajectory.TrajectoryWriter(prefix, F, R, N, elements=["C", "H", "H", "O", "N"]) as w:
+        for f in range(F):
+            w.append(frames[f], time_ps=0.2 * (f + 1), step=100 * (f + 1), potential=np.arange(R) + f, temperature=np.full(R, 300.0))
+    h5 = trajectory.export_mdtraj_h5(prefix, prefix + "_output.h5")
+    # (a) round trip: datasets, units, root attributes, topology JSON, the reference's per-chain reader
+    data, attrs, dattrs = hdf5_min.read(h5)
+    assert sorted(data) == ["coordinates", "potentialEnergy", "time", "topology"]
+    assert data["coordinates"].dtype == np.float32 and data["coordinates"].shape == (F, R * N, 3)
+    np.testing.assert_array_equal(data["coordinates"].reshape(F, R, N, 3), frames)
+    np.testing.assert_allclose(data["time"], [0.2, 0.4, 0.6, 0.8], rtol=1e-6)
+    np.testing.assert_allclose(data["potentialEnergy"], [3.0, 6.0, 9.0, 12.0])
+    assert attrs["conventions"] == "Pande" and attrs["conventionVersion"] == "1.1"
+    assert dattrs["coordinates"]["units"] == "nanometers" and dattrs["time"]["units"] == "picoseconds"
+    xyz, time_ps, chainid, elements = trajectory.load_mdtraj_h5(h5)
+    np.testing.assert_array_equal(chainid, np.repeat(np.arange(R), N))
+    assert elements == ["C", "H", "H", "O", "N"] * R
+    per_rep = trajectory.load_parallel_traj(h5, R)
+    for r in range(R):
+        np.testing.assert_array_equal(per_rep[r], frames[:, r])
+    with pytest.raises(ValueError):
+        trajectory.load_parallel_traj(h5, R + 1)
+    # (b) structure
+    raw = open(h5, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n"
+    assert raw[8] == 0 and raw[13] == 8 and raw[14] == 8                      # superblock v0, 8-byte offsets and lengths
+    base, free, eof, drv = struct.unpack_from("<QQQQ", raw, 24)
+    assert base == 0 and free == drv == 0xFFFFFFFFFFFFFFFF and eof == len(raw)
+    name_off, root_hdr, cache, _, btree, heap = struct.unpack_from("<QQIIQQ", raw, 56)
+    assert cache == 1 and raw[btree:btree + 4] == b"TREE" and raw[heap:heap + 4] == b"HEAP"
+    assert raw[root_hdr] == 1 and root_hdr % 8 == 0                            # version-1 object header, 8-byte aligned
+    node_type, level, used, left, right = struct.unpack_from("<BBHQQ", raw, btree + 4)
+    assert (node_type, level, used) == (0, 0, 1) and left == right == 0xFFFFFFFFFFFFFFFF
+    key0, snod, key1 = struct.unpack_from("<QQQ", raw, btree + 24)
+    assert key0 == 0 and raw[snod:snod + 4] == b"SNOD" and struct.unpack_from("<H", raw, snod + 6)[0] == 4
+    seg_size, free_head, seg = struct.unpack_from("<QQQ", raw, heap + 8)
+    assert raw[seg:seg + 1] == b"\0"                                           # offset 0 of the heap = the empty name
+    nxt, fsize = struct.unpack_from("<QQ", raw, seg + free_head)               # one free block closes the heap
+    assert nxt == 1 and free_head + fsize == seg_size
+    names = [raw[seg + struct.unpack_from("<Q", raw, snod + 8 + 40 * i)[0]:].split(b"\0")[0] for i in range(4)]
+    assert names == sorted(names) == [b"coordinates", b"potentialEnergy", b"time", b"topology"]   # entries ordered by name
+    assert raw[seg + key1:].split(b"\0")[0] == names[-1]                       # right key of the B-tree = largest name
+    for i in range(4):
+        hdr = struct.unpack_from("<Q", raw, snod + 8 + 40 * i + 8)[0]
+        assert hdr % 8 == 0 and raw[hdr] == 1
+    # other dtypes / a scalar-free file
+    p2 = str(tmp_path / "misc.h5")
+    hdf5_min.write(p2, {"i": np.arange(6, dtype=np.int32).reshape(2, 3), "d": np.linspace(0, 1, 5), "u": np.array([7], np.uint8)},
+                   {"n": np.int64(3)}, {"d": {"scale": np.array([1.5, 2.5], np.float32)}})
+    d2, a2, da2 = hdf5_min.read(p2)
+    np.testing.assert_array_equal(d2["i"], np.arange(6).reshape(2, 3))
+    np.testing.assert_array_equal(d2["d"], np.linspace(0, 1, 5))
+    assert d2["d"].dtype == np.float64 and d2["u"].dtype == np.uint8 and int(np.asarray(a2["n"]).reshape(-1)[0]) == 3
+    np.testing.assert_array_equal(da2["d"]["scale"], [1.5, 2.5])
+    with pytest.raises(ValueError):
+        open(p2, "ab").write(b"x")                                             # a truncated / grown file is refused
+        hdf5_min.read(p2)
