@@ -375,7 +375,7 @@ gb_energy_kernel(const int* __restrict__ skip, const float* __restrict__ pos, in
 // (12 CTAs of 128 threads per SM = 42 registers: 204 800 targets of the C2 batch are then resident in ONE wave of 227 k
 // thread slots instead of 1.2 waves of 170 k at the 52 registers the compiler would take)
 template <int LANES>
-__global__ void __launch_bounds__(kPairThreads * LANES, 12 / LANES)
+__global__ void __launch_bounds__(kPairThreads * LANES, LANES == 1 ? 12 : 1)
 born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos, int n, int N, int U, const float* __restrict__ rho,
                     const float* __restrict__ s, const int* __restrict__ radidx, const float* __restrict__ d0,
                     const float* __restrict__ m0, float cutoff, int predicate, const float* __restrict__ Bbar,

@@ -159,7 +159,13 @@ def test_replica_invariance_full_size(weights):
     eng.set_replicas(R, [0] * R, [78.5] * R)
     pos = torch.from_numpy(np.repeat(pos1, R, axis=0)).cuda()
     e, f = eng.energy_force(pos)
-    assert torch.equal(e, e[:1].expand(R)) and torch.equal(f, f[:1].expand(R, -1, -1))
+    # 1024 replicas on 296 warp groups = three full waves of whole replicas + 136 replicas that are split in two (tail
+    # split, Ctx::split_from): bit-equal inside either set, equal up to the summation order of the split between them
+    T = R - R % 296
+    assert "replicas %d.." % T in eng.describe()
+    assert torch.equal(e[:T], e[:1].expand(T)) and torch.equal(f[:T], f[:1].expand(T, -1, -1))
+    assert torch.equal(e[T:], e[T:T + 1].expand(R - T)) and torch.equal(f[T:], f[T:T + 1].expand(R - T, -1, -1))
+    assert abs(float(e[T]) - float(e[0])) <= 2e-6 * abs(float(e[0])) and rel_rms(f[T].cpu().numpy(), f[0].cpu().numpy()) < 2e-5
     assert abs(float(e[0]) - float((c["e_atom"] + c["sa_atom"])[:50].sum())) < E_RTOL * abs(float(e[0]))
 
 
