@@ -290,6 +290,50 @@ __device__ __forceinline__ bool in_cutoff(int predicate, float r, float sx, floa
   return d2 < __fmul_rn(cutoff, cutoff);
 }
 
+// L1 cache policy of the tensor-core edge kernels.  They run with ~221 KB of shared memory per SM, which leaves ~30 KB of L1:
+// the rows gathered per edge (P of the forward, abar of the adjoint; 12.8 KB per unit, reused by all of its tiles) compete
+// with the streamed per-edge arrays (pair, r_e, perm, rbar).  Gathered rows are therefore loaded `evict_last`, streamed data
+// `no_allocate` (GNNIS_L1_POLICY=0 at compile time restores plain loads for A/B runs).
+#ifndef GNNIS_L1_POLICY
+#define GNNIS_L1_POLICY 1
+#endif
+__device__ __forceinline__ float4 ldg_keep4(const float4* p) {
+#if GNNIS_L1_POLICY
+  float4 v;
+  asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t ldg_stream(const uint32_t* p) {
+#if GNNIS_L1_POLICY
+  uint32_t v;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+#if GNNIS_L1_POLICY
+  float v;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ uint8_t ldg_stream(const uint8_t* p) {
+#if GNNIS_L1_POLICY
+  uint32_t v;
+  asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return (uint8_t)v;
+#else
+  return *p;
+#endif
+}
+
 // MUFU-based reciprocal / log / exp / rsqrt (1-2 ulp) for the all-pairs kernels, which are bound by instruction issue:
 // an IEEE division costs ~9 instructions, MUFU.RCP one.  The exact-rounding operations are kept where bits matter
 // (eps_dist and the neighbour predicate).  The parity gates (Born radii 2e-5, energies 1e-4, forces 1e-3) guard this.

@@ -140,6 +140,13 @@ int launch_build_operand(Ctx* c, uint8_t* hi, uint8_t* lo, const float* src, int
   GNNIS_LAUNCH_CHECK();
   return 0;
 }
+__device__ __forceinline__ void st_rbar(float* p, float v) {
+#if GNNIS_L1_POLICY >= 2
+  __stcg(p, v);
+#else
+  *p = v;
+#endif
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // radial basis row in registers (GNN_Layers.py:2194-2208): d = r/cutoff, env = 1/d - 28 d^5 + 48 d^6 - 21 d^7,
@@ -801,12 +808,12 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       float r = 0.3f, r_n = 0.3f;
       bool valid = e_begin + row < e_end;
       if (valid) {
-        pr = g.pair[e_begin + row];
-        if (ch == 0) r = g.r_e[e_begin + row];
+        pr = ldg_stream(g.pair + e_begin + row);
+        if (ch == 0) r = ldg_stream(g.r_e + e_begin + row);
       }
       if (e_begin + kTileE + row < e_end) {
-        pr_n = g.pair[e_begin + kTileE + row];
-        if (ch == 0) r_n = g.r_e[e_begin + kTileE + row];
+        pr_n = ldg_stream(g.pair + e_begin + kTileE + row);
+        if (ch == 0) r_n = ldg_stream(g.r_e + e_begin + kTileE + row);
       }
       TileKeys* tk = keys + kidx;
       if (ch == 0) tk->tgt[row] = valid ? (int)(pr >> 16) : -1;
@@ -846,8 +853,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           float4 p[4], q[4];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            p[j4] = P_SM ? pp[j4] : __ldg(pp + j4);
-            q[j4] = Q_SM ? qq[j4] : __ldg(qq + j4);
+            p[j4] = P_SM ? pp[j4] : ldg_keep4(pp + j4);
+            q[j4] = Q_SM ? qq[j4] : ldg_keep4(qq + j4);
           }
           tmem_ld_wait();
           float v[16];
@@ -890,8 +897,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           if (ch == 0) tkn->tgt[row] = valid_n ? (int)(pr_n >> 16) : -1;
           if (!P_SM) prefetch_l1(gP + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
           if (t0 + 2 * kTileE + row < e_end) {
-            pr_nn = g.pair[t0 + 2 * kTileE + row];
-            if (ch == 0) r_nn = g.r_e[t0 + 2 * kTileE + row];
+            pr_nn = ldg_stream(g.pair + t0 + 2 * kTileE + row);
+            if (ch == 0) r_nn = ldg_stream(g.r_e + t0 + 2 * kTileE + row);
           }
           if (ch == 0) {
             float o[32], od[32];
@@ -1462,17 +1469,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
     uint8_t pm = (uint8_t)row, pm_n = (uint8_t)row;
     bool valid = e_begin + row < e_end;
     if (valid) {
-      pr = g.pair[e_begin + row];
+      pr = ldg_stream(g.pair + e_begin + row);
       if (ch == 0) {
-        r = g.r_e[e_begin + row];
-        pm = g.perm[e_begin + row];
+        r = ldg_stream(g.r_e + e_begin + row);
+        pm = ldg_stream(g.perm + e_begin + row);
       }
     }
     if (e_begin + kTileE + row < e_end) {
-      pr_n = g.pair[e_begin + kTileE + row];
+      pr_n = ldg_stream(g.pair + e_begin + kTileE + row);
       if (ch == 0) {
-        r_n = g.r_e[e_begin + kTileE + row];
-        pm_n = g.perm[e_begin + kTileE + row];
+        r_n = ldg_stream(g.r_e + e_begin + kTileE + row);
+        pm_n = ldg_stream(g.perm + e_begin + kTileE + row);
       }
     }
     TileKeys* tk = keys + kidx;
@@ -1517,7 +1524,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
         const uint4 c0 = *reinterpret_cast<const uint4*>(sLW + row * 128 + ((q0 ^ swz) << 4));
         const uint4 c1 = *reinterpret_cast<const uint4*>(sLW + row * 128 + (((q0 + 1u) ^ swz) << 4));
         const float4* ab = reinterpret_cast<const float4*>(gAb + (size_t)tgc * 64 + col0);
-        const float4 a0 = __ldg(ab), a1 = __ldg(ab + 1), a2 = __ldg(ab + 2), a3 = __ldg(ab + 3);
+        const float4 a0 = ldg_keep4(ab), a1 = ldg_keep4(ab + 1), a2 = ldg_keep4(ab + 2), a3 = ldg_keep4(ab + 3);
         float wb[16];
         upk(mul2(stash_dec2(c0.x), pk(a0.x, a0.y)), wb[0], wb[1]);
         upk(mul2(stash_dec2(c0.y), pk(a0.z, a0.w)), wb[2], wb[3]);
@@ -1538,7 +1545,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
         mbar_wait(tileB, ph_b);
         ph_b ^= 1u;
         const TileKeys* tkp = keys + (kidx + 2) % 3;
-        if (ch == 0 && valid_p) g.rbar[rslot_p] = rold_p + (racc_p + sPart[grp][row]);   // channels 0..31 + 32..63
+        if (ch == 0 && valid_p) st_rbar(g.rbar + rslot_p, rold_p + (racc_p + sPart[grp][row]));   // channels 0..31 + 32..63
         reduce_targets_global_256(sU, tkp, gPb, gt);
         reduce_sources_table_256(sU, tkp, tQb, ld, gt);
       }
@@ -1569,10 +1576,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
         }
         prefetch_l1(gAb + (size_t)(valid_n ? (pr_n >> 16) : 0u) * 64 + 32 * ch);
         if (t0 + 2 * kTileE + row < e_end) {
-          pr_nn = g.pair[t0 + 2 * kTileE + row];
+          pr_nn = ldg_stream(g.pair + t0 + 2 * kTileE + row);
           if (ch == 0) {
-            r_nn = g.r_e[t0 + 2 * kTileE + row];
-            pm_nn = g.perm[t0 + 2 * kTileE + row];
+            r_nn = ldg_stream(g.r_e + t0 + 2 * kTileE + row);
+            pm_nn = ldg_stream(g.perm + t0 + 2 * kTileE + row);
           }
         }
       }
@@ -1588,7 +1595,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
       float rold = 0.0f;
       if (ch == 0 && valid) {
         rslot = ((size_t)atom0 + tg) * g.N + (sr - (tg / g.N) * g.N);
-        if (g.rbar_accumulate) rold = g.rbar[rslot];
+        if (g.rbar_accumulate) rold = GNNIS_L1_POLICY >= 2 ? __ldcg(g.rbar + rslot) : g.rbar[rslot];
       }
       mbar_wait(d_full, ph_d);
       __syncwarp();
@@ -1654,7 +1661,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
     // ---- last tile of the unit
     mbar_wait(tileB, ph_b);
     ph_b ^= 1u;
-    if (ch == 0 && valid_p) g.rbar[rslot_p] = rold_p + (racc_p + sPart[grp][row]);
+    if (ch == 0 && valid_p) st_rbar(g.rbar + rslot_p, rold_p + (racc_p + sPart[grp][row]));
     reduce_targets_global_256(sU, keys + (kidx + 2) % 3, gPb, gt);
     reduce_sources_table_256(sU, keys + (kidx + 2) % 3, tQb, ld, gt);
     ws_group_sync(grp);
