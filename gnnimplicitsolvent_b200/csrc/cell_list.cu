@@ -31,7 +31,7 @@ int launch_scan_blocks(Ctx* c, cudaStream_t st);
 
 constexpr int kCellDim = 8;                              // cells per dimension, at most
 constexpr int kCellMax = kCellDim * kCellDim * kCellDim;
-constexpr int kCellThreads = 256;
+constexpr int kCellThreads = 512;                       // 16 warps: 8 targets per warp and chunk
 constexpr int kCellWarps = kCellThreads / 32;
 constexpr int kCellChunk = 128;                          // targets per CTA (blockIdx.y)
 
@@ -196,39 +196,47 @@ __global__ void __launch_bounds__(kPairThreads) deg_block_sum_kernel(const int* 
   }
 }
 
-// dynamic smem: pos of the replicas this block's atoms belong to
-__global__ void __launch_bounds__(kPairThreads)
+// dynamic smem: pos of the replicas this block's atoms belong to.  One block = kPairThreads consecutive targets (the layout
+// of blk_sum) worked on by kFillThreads threads: the first kPairThreads compute the row offsets, then the 16 warps take the
+// block's targets round-robin (a target is one mask row per warp: short, latency-bound work that needs many warps in flight)
+constexpr int kFillThreads = 512;
+__global__ void __launch_bounds__(kFillThreads)
 mask_fill_kernel(const float* __restrict__ pos, int n, int N, int G, int W, const uint32_t* __restrict__ mask,
                  const int* __restrict__ deg, const int* __restrict__ blk_off, int64_t capacity, int* __restrict__ row_ptr,
                  int* __restrict__ col, uint32_t* __restrict__ pair, float* __restrict__ r_e) {
   extern __shared__ float sm[];
   __shared__ int sdeg[kPairThreads];
+  __shared__ int soff[kPairThreads];
   const int a0 = blockIdx.x * kPairThreads, a1 = min(n, a0 + kPairThreads) - 1;
   const int first_rep = a0 / N, last_rep = a1 / N;
   const int n_stage = (last_rep - first_rep + 1) * N;
   float* spos = sm;
-  for (int t = threadIdx.x; t < 3 * n_stage; t += kPairThreads) spos[t] = pos[(size_t)first_rep * N * 3 + t];
+  for (int t = threadIdx.x; t < 3 * n_stage; t += kFillThreads) spos[t] = pos[(size_t)first_rep * N * 3 + t];
   const int i = a0 + threadIdx.x;
-  const int mydeg = (i < n) ? deg[i] : 0;
-  sdeg[threadIdx.x] = mydeg;
+  const int mydeg = (threadIdx.x < kPairThreads && i < n) ? deg[i] : 0;
+  if (threadIdx.x < kPairThreads) sdeg[threadIdx.x] = mydeg;
   __syncthreads();
   for (int off = 1; off < kPairThreads; off <<= 1) {
-    int v = (threadIdx.x >= off) ? sdeg[threadIdx.x - off] : 0;
+    int v = (threadIdx.x < kPairThreads && threadIdx.x >= off) ? sdeg[threadIdx.x - off] : 0;
     __syncthreads();
-    sdeg[threadIdx.x] += v;
+    if (threadIdx.x < kPairThreads) sdeg[threadIdx.x] += v;
     __syncthreads();
   }
-  int64_t w = 0;
-  if (i < n) {
-    w = (int64_t)blk_off[blockIdx.x] + sdeg[threadIdx.x] - mydeg;
-    row_ptr[i] = (int)w;
+  if (threadIdx.x < kPairThreads) {
+    int w = -1;   // -1: nothing to emit (past the end, empty row, or the row does not fit the caller's capacity)
+    if (i < n) {
+      const int64_t w64 = (int64_t)blk_off[blockIdx.x] + sdeg[threadIdx.x] - mydeg;
+      row_ptr[i] = (int)w64;
+      if (mydeg > 0 && w64 + mydeg <= capacity) w = (int)w64;
+    }
+    soff[threadIdx.x] = w;
   }
-  const int lane = threadIdx.x & 31;
-  const unsigned todo = __ballot_sync(0xffffffffu, i < n && mydeg > 0 && w + mydeg <= capacity);
-  for (unsigned m = todo; m; m &= m - 1) {
-    const int t = __ffs(m) - 1;
-    const int it = __shfl_sync(0xffffffffu, i, t);
-    const int64_t wt = __shfl_sync(0xffffffffu, w, t);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < kPairThreads; t += kFillThreads / 32) {
+    const int wt = soff[t];
+    if (wt < 0) continue;
+    const int it = a0 + t;
     const int rep = it / N, a = it - rep * N;
     const float* rp = spos + (size_t)(rep - first_rep) * N * 3;
     const float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
@@ -242,7 +250,7 @@ mask_fill_kernel(const float* __restrict__ pos, int n, int N, int G, int W, cons
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    int64_t at = wt + (incl - cnt);
+    int64_t at = (int64_t)wt + (incl - cnt);
     for (; word; word &= word - 1, ++at) {
       const int j = 32 * lane + __ffs(word) - 1;
       float dx, dy, dz;
@@ -268,7 +276,7 @@ int launch_cell_neighbors(Ctx* c, const float* pos, int predicate, int* row_ptr,
   if (launch_scan_blocks(c, st)) return -1;
   const size_t smem_fill = 3 * ((size_t)kPairThreads + 2 * (size_t)N) * sizeof(float);
   if (smem_fill > 48 * 1024) cudaFuncSetAttribute(mask_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fill);
-  mask_fill_kernel<<<nblk, kPairThreads, smem_fill, st>>>(pos, n, N, c->G, W, c->nbr_mask, c->deg, c->blk_sum, capacity, row_ptr,
+  mask_fill_kernel<<<nblk, kFillThreads, smem_fill, st>>>(pos, n, N, c->G, W, c->nbr_mask, c->deg, c->blk_sum, capacity, row_ptr,
                                                          col, pair, r_e);
   GNNIS_LAUNCH_CHECK();
   return 0;
