@@ -102,6 +102,7 @@ struct LbArgs {
   float* grms_out;  // [R] gradient RMS at the last accepted point
   float grad_tol, max_disp;
   int stall_limit;
+  int sd;   // steepest descent: no curvature pairs are kept, the first trial step follows the last accepted displacement
 };
 
 // one CTA per replica: accept / reject the trial point, update the history, build the next direction and trial.
@@ -161,7 +162,12 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
   if (accept) {
     // curvature pair
     float sy = 0.f, yy = 0.f, gg = 0.f;
-    if (state == LB_SEARCH) {
+    float disp = 0.f;   // steepest descent: largest coordinate displacement of the step that was just accepted
+    if (a.sd && state == LB_SEARCH) {
+      for (int t = threadIdx.x; t < D; t += kLbThreads) disp = fmaxf(disp, fabsf(xt[t] - x[t]));
+      disp = block_max(disp, red);
+    }
+    if (state == LB_SEARCH && !a.sd) {
       for (int t = threadIdx.x; t < D; t += kLbThreads) {
         float s = xt[t] - x[t], y = -ft[t] - g[t];
         sy += s * y;
@@ -299,6 +305,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_update_kernel(LbArgs a) {
     }
     // unit step for quasi-Newton directions, displacement-capped; tiny first step for steepest descent
     step = cnt > 0 ? 1.0f : fminf(1.0f, 0.002f / dmax);
+    if (a.sd && disp > 0.f) step = fminf(1.0f, 2.0f * disp / dmax);   // twice the displacement that worked last time
     if (step * dmax > a.max_disp) step = a.max_disp / dmax;
     __syncthreads();
     for (int t = threadIdx.x; t < D; t += kLbThreads) xt[t] = x[t] + step * d[t];
@@ -653,7 +660,9 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GNNIS_CUDA_OK(cudaSetDevice(c->device));
-  if (history <= 0) history = 8;
+  const int steepest = history < 0 ? 1 : 0;   // history < 0: steepest descent with the same line search and stopping rules
+  if (history < 0) history = 1;
+  if (history == 0) history = 8;
   if (history > 32) history = 32;
   if (max_iter <= 0) max_iter = 1000;
   const int R = c->R, D = 3 * c->N;
@@ -698,6 +707,7 @@ int gnnis_minimize(gnnis_handle h, float* pos_dev, float* e_rep_dev, int32_t* st
   a.grad_tol = grad_tol;
   a.max_disp = c->lb_max_disp;
   a.stall_limit = c->lb_stall_limit;
+  a.sd = steepest;
   lbfgs_init_kernel<<<(R + 127) / 128, 128, 0, st>>>(R, a.state, a.hist, a.status, a.n_active, a.n_evals, a.grms_out);
   GNNIS_LAUNCH_CHECK();
   GNNIS_CUDA_OK(cudaMemcpyAsync(a.xt, pos_dev, n3 * sizeof(float), cudaMemcpyDeviceToDevice, st));

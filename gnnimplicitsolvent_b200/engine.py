@@ -263,7 +263,8 @@ class Engine:
 
     def minimize(self, positions: torch.Tensor, grad_tol: float = 1.0, max_iter: int = 500, history: int = 8,
                  delta=False, gb_only=False, vacuum_only=False):
-        """Batched per-replica L-BFGS; returns (positions[R,N,3], E[R], status[R] int32, n_rounds)."""
+        """Batched per-replica L-BFGS (history = curvature pairs per replica; history=-1: steepest descent with the same line
+        search); returns (positions[R,N,3], E[R], status[R] int32, n_rounds)."""
         p = self._pos(positions).clone()
         e = torch.empty(self.n_rep, dtype=torch.float32, device=self.device)
         status = torch.empty(self.n_rep, dtype=torch.int32, device=self.device)

@@ -171,7 +171,9 @@ int gnnis_set_forcefield(gnnis_handle h, const gnnis_forcefield* ff);
 /* Batched per-replica L-BFGS (replaces simulation.minimizeEnergy(tolerance, maxIterations) driven by
  * OpenMM's LocalEnergyMinimizer, helper_functions.py:614-624; semantics differ by design: one optimiser
  * per replica, SURVEY.md §7 hard part 5).  pos_dev is updated in place.  Stops a replica when its
- * gradient RMS < grad_tol (kJ/mol/nm) or after max_iter iterations (0 = 1000).
+ * gradient RMS < grad_tol (kJ/mol/nm) or after max_iter iterations (0 = 1000).  history = number of curvature pairs
+ * per replica (0 = 8, at most 32); history < 0 selects steepest descent (no pairs; the first trial step of an iteration is
+ * twice the displacement accepted last) with the same acceptance and stopping rules.
  * status_dev [R] int32: 0 converged (gradient RMS below grad_tol), 1 iteration limit, 2 non-finite energy/force
  * (positions restored), 3 stopped with a gradient RMS above grad_tol because the line search can no longer lower
  * the energy at fp32 resolution (20 accepted steps without a gain, or a step below 2e-7 nm) -- the model's energy

@@ -198,3 +198,30 @@ def test_langevin_with_hbond_constraints(weights):
     assert 0.8 < t_kin < 1.2, t_kin
     p2, v2 = run(5, 1500)
     assert torch.equal(p, p2) and torch.equal(v, v2)
+
+
+def test_steepest_descent_mode_reaches_the_same_minima():
+    """history = -1 selects steepest descent (`north_star`: "a batched L-BFGS / steepest-descent minimiser"): same line search
+    and stopping rules, no curvature pairs.  On a smooth single-basin potential (GB-Neck2 + elastic network; the GNN term is
+    left out because its energy surface has ledges at the graph cutoff, DESIGN.md 3, on which two optimisers need not stop
+    at the same one) it must arrive where L-BFGS arrives, just with more evaluations."""
+    from gnnimplicitsolvent_b200.engine import Engine
+    mol, pos, bonds, r0, k = _system(21, 24, seed=6)
+    eng = Engine(mol["params"], None)
+    eng.set_replicas(24, [0] * 24, [78.5] * 24)
+    eng.set_bonds(bonds, r0, k)
+    p0 = torch.from_numpy(pos).cuda()
+    e0, _ = eng.energy_force(p0, gb_only=True)
+    p_l, e_l, st_l, rounds_l = eng.minimize(p0, grad_tol=2.0, max_iter=600, gb_only=True)
+    n_l, _ = eng.minimize_stats()
+    p_s, e_s, st_s, rounds_s = eng.minimize(p0, grad_tol=2.0, max_iter=6000, history=-1, gb_only=True)
+    n_s, g_s = eng.minimize_stats()
+    assert int((st_s == 2).sum()) == 0 and bool((e_s <= e0 + 1e-3).all())
+    ok = (st_l == 0) & (st_s == 0)
+    assert int(ok.sum()) >= 20, (st_l.tolist(), st_s.tolist())               # both below the threshold
+    assert bool((g_s[st_s == 0] < 2.0).all())
+    # same minimum: the energies agree to the flatness a 2 kJ/mol/nm gradient threshold leaves
+    assert float((e_l[ok] - e_s[ok]).abs().max()) < 0.05
+    assert float(n_s[ok].float().median()) > float(n_l[ok].float().median())  # steepest descent needs more evaluations
+    e_chk, _ = eng.energy_force(p_s, gb_only=True)
+    np.testing.assert_allclose(e_s.cpu().numpy(), e_chk.cpu().numpy(), rtol=1e-5, atol=1e-2)
