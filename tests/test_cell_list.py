@@ -115,3 +115,22 @@ def test_evaluation_on_cell_list_graph_is_bit_identical(weights):
             e1, f1 = eng.energy_force(pos, cell_list=True, **kw)
             assert torch.equal(e0, e1) and torch.equal(f0, f1)
     assert "neighbors=" in eng.describe()
+
+
+def test_cell_list_non_finite_positions():
+    """A NaN coordinate and an infinite coordinate: the atom has no edges with either back-end (every predicate involving
+    it is false), the bounding box / cell assignment of the others is not disturbed."""
+    from gnnimplicitsolvent_b200.engine import Engine
+    N, R = 40, 3
+    pos = np.stack([_chain(N, 0.12, 77 + r) for r in range(R)])
+    pos[0, 7, 1] = np.nan
+    pos[1, 0, 2] = np.inf
+    pos[2, 39, 0] = -np.inf
+    eng = Engine(_params(N), None)
+    eng.set_replicas(R, [0] * R, [78.5] * R)
+    for predicate in ("run", "data"):
+        a, b = _lists(eng, pos, predicate)
+        _assert_same(a, b)
+        deg = np.diff(b[0]).reshape(R, N)
+        assert deg[0, 7] == 0 and deg[1, 0] == 0 and deg[2, 39] == 0 and deg.sum() > 0
+        assert not np.isin(b[1], [7, N + 0, 2 * N + 39]).any()
