@@ -640,8 +640,9 @@ __device__ __forceinline__ void reduce_sources_table_256(const float* __restrict
 //     u_ok (12 arrivals), a_full (8 arrivals), d_full (tcgen05.commit)
 constexpr int kWsiThreads = kGroups * kWsGroupThreads + 32;
 struct WsiBars {
-  uint64_t d_full[kGroups], a_full[kGroups], u_ok[kGroups];
+  uint64_t d_full[kGroups], a_full[kGroups], u_ok[kGroups], tile_b[kGroups];
 };
+__device__ __forceinline__ void warp_arrive_bar(uint64_t* bar, int lane);
 __device__ __forceinline__ void warp_arrive_i(uint64_t* bar, int lane) {
   fence_before_sync();
   __syncwarp();
@@ -681,6 +682,12 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   constexpr int TERMS = TM == kTanh3 ? 3 : TM;                 // arithmetic of the products
   constexpr bool FAST = is_half(TM) || TM == kTanh3;           // tanh-based activations
   constexpr bool Q_SM = TAB >= 1, P_SM = TAB == 2;   // which node tables of the unit live in shared memory
+  // How a tile is closed.  With the unit's tables in shared memory: a group barrier (B) after the second epilogue.  Without
+  // tables (more than 64 atoms with the stash: both row gathers go through L1 / L2 and the warps drift apart): an mbarrier
+  // arrival -- a warp goes on to the next tile's first epilogue at once, warp 4 (no radial work) sends the tile's silu'(w)
+  // image as soon as all eight arrivals are in, and the tile is reduced under the next w product by whoever has waited.
+  // Measured (edge forward, ms): N = 100, R = 1024 1.967 -> 1.925; N = 50, R = 4096 1.986 -> 2.000 (hence the barrier there)
+  constexpr bool TB = !Q_SM;
   constexpr uint32_t kStg = STASH ? kStageBytes : 0u;
   extern __shared__ uint8_t smraw[];
   __shared__ WsiBars bars;
@@ -699,6 +706,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       mbar_init(&bars.d_full[i], 1);
       mbar_init(&bars.a_full[i], 8);
       mbar_init(&bars.u_ok[i], 12);
+      mbar_init(&bars.tile_b[i], 8);
     }
   }
   __shared__ uint64_t ibar;
@@ -774,8 +782,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     const uint32_t swz = (uint32_t)(row & 7);         // chunk swizzle of this thread's image row
     const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
     const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
-    uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp];
-    uint32_t ph_d = 0, ph_a = 0, cur = 0;
+    uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp], *tile_b = &bars.tile_b[grp];
+    uint32_t ph_d = 0, ph_a = 0, ph_b = 0, cur = 0;
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
@@ -836,6 +844,10 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           if (lane == 0) {
             tk->n_seg_t = ns;
             tk->cont_prev = (t0 > e_begin && keys[(kidx + 2) % 3].tgt[kTileE - 1] == tk->tgt[0]) ? 1 : 0;
+          }
+          if (TB && t0 > e_begin) {                    // this warp sends the previous tile's silu'(w) image as soon as it is complete
+            mbar_wait(tile_b, ph_b);
+            if (STASH && lane == 0) bulk_store(g.st_w + (size_t)(t0 - kTileE) * 128, sStW, (uint32_t)kTileE * 128u);
           }
         }
         mbar_wait(d_full, ph_d);
@@ -917,7 +929,13 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         }
         ph_a ^= 1u;
         // ---- a[tgt] += z of the PREVIOUS tile while the tensor pipe works on w of this one
-        if (t0 > e_begin) reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);
+        if (t0 > e_begin) {
+          if (TB) {
+            mbar_wait(tile_b, ph_b);                 // every warp has written its rows of the previous tile
+            ph_b ^= 1u;
+          }
+          reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);
+        }
         mbar_wait(d_full, ph_d);
         __syncwarp();
         ph_d ^= 1u;
@@ -927,7 +945,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         tmem_ld32(lane_addr + (cur ^ 64u) + 32 * ch, wr);
         tmem_ld_wait();
         if (has_next) warp_arrive_i(u_ok, lane);
-        if (STASH && gt == 0) bulk_store_wait_read();   // the silu'(w) image of the previous tile has left shared memory
+        if (STASH && (gt == 0 || (TB && gt == 128))) bulk_store_wait_read();   // the images sent so far have left shared memory
         ws_group_sync(grp);                          // (A) the reduction of the previous tile is complete
         {
           const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * ch);
@@ -959,9 +977,15 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             }
           }
         }
-        if (STASH && gt == 0) bulk_store_wait_read();   // the silu'(u) image of this tile has left shared memory
-        ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
-        if (STASH && gt == 0) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
+        if (TB) {
+          // (B) tile complete: an arrival, not a barrier.  The silu'(u) image of this tile is known to have left shared
+          // memory at (A) of this tile (wait_read of thread 0)
+          warp_arrive_bar(tile_b, lane);
+        } else {
+          if (STASH && gt == 0) bulk_store_wait_read();   // the silu'(u) image of this tile has left shared memory
+          ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
+          if (STASH && gt == 0) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
+        }
         pr = pr_n;
         r = r_n;
         valid = valid_n;
@@ -971,10 +995,18 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         kidx = (kidx + 1) % 3;
         cur ^= 64u;
       }
+      if (TB) {
+        mbar_wait(tile_b, ph_b);
+        ph_b ^= 1u;
+        if (STASH && gt == 128) {
+          const int t_last = e_begin + ((e_end - e_begin - 1) / kTileE) * kTileE;
+          bulk_store(g.st_w + (size_t)t_last * 128, sStW, (uint32_t)(e_end - t_last) * 128u);
+        }
+      }
       reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);   // last tile of the unit
       ws_group_sync(grp);   // all rows of the unit written before its tables are replaced
     }
-    if (STASH && gt == 0) bulk_store_wait_all();     // every image has reached global memory before the CTA retires
+    if (STASH && (gt == 0 || (TB && gt == 128))) bulk_store_wait_all();   // every image has reached global memory before the CTA retires
   }
   fence_before_sync();
   __syncthreads();
