@@ -142,7 +142,11 @@ def write(path: str, datasets: Dict[str, np.ndarray], attrs: Dict[str, object] |
         f.write(out)
         for n in names:
             f.write(bytes(data_addr[n] - f.tell()))
-            f.write(arrays[n].tobytes())
+            a = arrays[n]
+            if a.ndim and a.nbytes:      # no copy: memory-mapped coordinates are streamed from the page cache
+                f.write(memoryview(a.reshape(-1).view(np.uint8)))
+            else:
+                f.write(a.tobytes())
         assert f.tell() == eof
 
 

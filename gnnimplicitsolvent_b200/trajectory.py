@@ -235,7 +235,7 @@ def export_mdtraj_h5(prefix: str, out_file: str, residue_name: str = "MOL"):
     topology = json.dumps(_mdtraj_topology(R, N, [str(e) for e in meta["element"]], residue_name)).encode("ascii")
     root = {"conventions": "Pande", "conventionVersion": "1.1", "program": "gnnimplicitsolvent_b200", "programVersion": "0.1",
             "application": "gnnis", "title": os.path.basename(prefix)}
-    data = {"coordinates": np.asarray(xyz, np.float32), "time": meta["time"].astype(np.float32),
+    data = {"coordinates": xyz, "time": meta["time"].astype(np.float32),   # xyz: float32 memmap, written without a copy
             "potentialEnergy": np.nansum(meta["potentialEnergy"], axis=1).astype(np.float32),
             "topology": np.array([topology], dtype=f"S{len(topology)}")}
     units = {"coordinates": {"units": "nanometers"}, "time": {"units": "picoseconds"},
