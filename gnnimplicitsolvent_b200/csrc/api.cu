@@ -142,23 +142,33 @@ static int ensure_workspace(Ctx* c) {
     return -1;
   if (dev_alloc(c, &c->h_pos_dev, n * 3) || dev_alloc(c, &c->h_f_dev, n * 3) || dev_alloc(c, &c->h_e_dev, (size_t)c->R))
     return -1;
-  // activation stash: 2 x 128 bytes per edge of capacity and layer (+ one tile of slack: partial tiles are addressed,
-  // never written, past their last row)
+  // activation stash: 2 x 128 bytes per edge and layer (+ one tile of slack: partial tiles are addressed, never written,
+  // past their last row).  Sized for the edge CAPACITY when that fits the budget; otherwise for as many edges as the
+  // budget holds, provided that is at least half of the capacity (real molecules fill 15-60 % of it) -- the kernels then
+  // compare the edge count of each evaluation with Ctx::stash_cap on the device (launch_edge_*_ws).
   {
     dev_free(&c->stash);
     c->stash_on = false;
-    const size_t per_arr = ((size_t)cap + kTileE) * 128;
+    c->stash_cap = 0;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     double budget = 0.45 * (double)free_b;
     if (c->stash_max_gb >= 0 && c->stash_max_gb * 1e9 < budget) budget = c->stash_max_gb * 1e9;
-    if (c->use_stash && (double)(6 * per_arr) <= budget && st_fwd_tables(c) >= 0 && st_bwd_tables(c) >= 0) {
+    int64_t hold = cap;
+    if ((double)(6 * ((size_t)cap + kTileE) * 128) > budget) {
+      hold = (int64_t)(budget / (6.0 * 128.0)) - kTileE;
+      hold -= hold % kTileE;
+      if (2 * hold < cap) hold = 0;
+    }
+    if (c->use_stash && hold > 0 && st_fwd_tables(c) >= 0 && st_bwd_tables(c) >= 0) {
+      const size_t per_arr = ((size_t)hold + kTileE) * 128;
       if (dev_alloc(c, &c->stash, 6 * per_arr)) return -1;
       for (int l = 0; l < 3; ++l) {
         c->st_u[l] = c->stash + (size_t)(2 * l) * per_arr;
         c->st_w[l] = c->stash + (size_t)(2 * l + 1) * per_arr;
       }
       c->stash_on = true;
+      c->stash_cap = hold;
     }
   }
   if (!c->n_edges_dev && dev_alloc(c, &c->n_edges_dev, 1)) return -1;
@@ -877,10 +887,11 @@ const char* gnnis_describe(gnnis_handle h) {
                   (c->split > 1 && c->split_from > 0 ? " (replicas " + std::to_string(c->split_from) + ".." + std::to_string(c->R - 1) + " only)" : "");
   d += std::string(" edge_kernels=") + (tc ? "tcgen05" : "cuda-cores (unit tables do not fit next to the operand images)");
   if (tc) {
-    d += std::string(" adjoint=") + (c->stash_on ? "stash" : (c->use_stash ? "recompute (stash exceeds the memory budget)" : "recompute (GNNIS_STASH=0)"));
+    d += std::string(" adjoint=") + (c->stash_on ? (c->stash_cap < c->edge_cap ? "stash up to " + std::to_string(c->stash_cap) + " edges, recompute beyond (decided per evaluation on the device)" : std::string("stash"))
+                                                 : (c->use_stash ? "recompute (stash exceeds the memory budget)" : "recompute (GNNIS_STASH=0)"));
     d += " tables=" + std::to_string(c->stash_on ? st_fwd_tables(c) : c->tab_mode);
   }
-  d += " stash_bytes=" + std::to_string(c->stash_on ? (size_t)6 * ((size_t)c->edge_cap + kTileE) * 128 : (size_t)0);
+  d += " stash_bytes=" + std::to_string(c->stash_on ? (size_t)6 * ((size_t)c->stash_cap + kTileE) * 128 : (size_t)0);
   d += std::string(" neighbors=") + (use_cell_list(c, -1) ? "cell-list" : "all-pairs");
   c->desc = d;
   return c->desc.c_str();

@@ -147,10 +147,14 @@ struct Ctx {
   float *rbar = nullptr;
   // activation stash of the edge MLPs (edge_mlp_tc.cu): 16-bit codes of silu'(u), silu'(w) per edge, channel and layer,
   // written by the forward edge kernels of an evaluation with forces and consumed by edge_bwd_st_kernel.  768 bytes per
-  // edge of CAPACITY; used when that fits the memory budget (ensure_workspace), otherwise the adjoint recomputes.
+  // edge of CAPACITY when that fits the memory budget (ensure_workspace).  When only a part of the worst case fits
+  // (at least half of it), the stash holds `stash_cap` < edge_cap edges and the kernels decide ON THE DEVICE, from the
+  // edge count of the evaluation, whether the stash is written / read or the adjoint recomputes (EdgeTcArgs::n_edges);
+  // below that the adjoint always recomputes.
   uint8_t* stash = nullptr;
   uint8_t *st_u[3] = {nullptr, nullptr, nullptr}, *st_w[3] = {nullptr, nullptr, nullptr};
   bool stash_on = false;
+  int64_t stash_cap = 0;      // edges the stash holds (== edge_cap: every edge list fits)
   // SiLU of the forward edge kernels from ONE MUFU.TANH (silu(x) = h + h tanh(h), h = x / 2; fastmath.cuh) instead of
   // ex2 + rcp: 2 issue slots + 1 MUFU instead of ~5.5 + 1.25.  Measured on the goldens / C2 / C5 points: energies
   // 1.1e-6 -> 2.2e-6, forces 2.9e-5 -> 3.6e-5 relative (gates 1e-4 / 1e-3), forward 2.22 -> 2.02 ms.  GNNIS_ACT=0

@@ -76,7 +76,15 @@ struct EdgeTcArgs {
   // activation stash (forward with forces -> adjoint): 16-bit codes of silu'(u) and silu'(w), [E][64] each, row e =
   // 128 bytes whose 16-byte chunks are XOR-swizzled with (row in tile & 7) -- the shared-memory image of a tile
   uint8_t *st_u, *st_w;
+  // capacity-limited stash (Ctx::stash_cap < edge_cap): edge count of this evaluation and the edges the stash holds.
+  // n_edges == nullptr: the stash holds every possible edge list.  stash_role: 0 = not a stash-dependent launch,
+  // 1 = runs only when the edge list fits the stash (stash adjoint), 2 = runs only when it does not (recomputing adjoint)
+  const int64_t* n_edges;
+  int64_t stash_cap;
+  int stash_role;
 };
+// does the edge list of this evaluation fit the stash?  (uniform over the grid: one 8-byte load per thread)
+__device__ __forceinline__ bool stash_fits(const EdgeTcArgs& g) { return !g.n_edges || *g.n_edges <= g.stash_cap; }
 
 // ---------------------------------------------------------------------------------------------- helpers
 // stage a K-major B operand [rows][kdim] (element (n,k) = src[n*ld_n + k*ld_k], zero outside n_valid x k_valid)
@@ -393,6 +401,9 @@ static EdgeTcArgs make_tc_args(Ctx* c, int l, int terms = 3) {
   g.unit_atoms = c->G * c->N;
   g.st_u = c->st_u[l];
   g.st_w = c->st_w[l];
+  g.n_edges = (c->stash_on && c->stash_cap < c->edge_cap) ? c->n_edges_dev : nullptr;
+  g.stash_cap = c->stash_cap;
+  g.stash_role = 0;
   return g;
 }
 
@@ -699,6 +710,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + (BF ? 8192 : 16384), *sW2L = sm + 32768;
   float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // capacity-limited stash: an edge list that does not fit is not stashed (the adjoint of this evaluation recomputes)
+  const bool st_ok = STASH && stash_fits(g);
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -847,7 +860,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
           }
           if (TB && t0 > e_begin) {                    // this warp sends the previous tile's silu'(w) image as soon as it is complete
             mbar_wait(tile_b, ph_b);
-            if (STASH && lane == 0) bulk_store(g.st_w + (size_t)(t0 - kTileE) * 128, sStW, (uint32_t)kTileE * 128u);
+            if (st_ok && lane == 0) bulk_store(g.st_w + (size_t)(t0 - kTileE) * 128, sStW, (uint32_t)kTileE * 128u);
           }
         }
         mbar_wait(d_full, ph_d);
@@ -917,7 +930,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             rbf_regs<false>(r_n, g.inv_cutoff, o, od);
             mbar_wait(a_full, ph_a);                 // every warp has finished reading u of this tile
             __syncwarp();
-            if (STASH && gt == 0) bulk_store(g.st_u + (size_t)t0 * 128, sStU, (uint32_t)min(kTileE, e_end - t0) * 128u);
+            if (st_ok && gt == 0) bulk_store(g.st_u + (size_t)t0 * 128, sStU, (uint32_t)min(kTileE, e_end - t0) * 128u);
             st_split24<TERMS>(lane_addr + cur, lane_addr + cur + 32, o);
             tmem_st_wait();
             warp_arrive_i(u_ok, lane);
@@ -925,7 +938,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         } else if (STASH && w8 == 0) {
           mbar_wait(a_full, ph_a);                   // all eight warps have written their rows of the silu'(u) image
           __syncwarp();
-          if (gt == 0) bulk_store(g.st_u + (size_t)t0 * 128, sStU, (uint32_t)min(kTileE, e_end - t0) * 128u);
+          if (st_ok && gt == 0) bulk_store(g.st_u + (size_t)t0 * 128, sStU, (uint32_t)min(kTileE, e_end - t0) * 128u);
         }
         ph_a ^= 1u;
         // ---- a[tgt] += z of the PREVIOUS tile while the tensor pipe works on w of this one
@@ -984,7 +997,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         } else {
           if (STASH && gt == 0) bulk_store_wait_read();   // the silu'(u) image of this tile has left shared memory
           ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
-          if (STASH && gt == 0) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
+          if (st_ok && gt == 0) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
         }
         pr = pr_n;
         r = r_n;
@@ -998,7 +1011,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       if (TB) {
         mbar_wait(tile_b, ph_b);
         ph_b ^= 1u;
-        if (STASH && gt == 128) {
+        if (st_ok && gt == 128) {
           const int t_last = e_begin + ((e_end - e_begin - 1) / kTileE) * kTileE;
           bulk_store(g.st_w + (size_t)t_last * 128, sStW, (uint32_t)(e_end - t_last) * 128u);
         }
@@ -1027,6 +1040,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
   uint8_t *sW2tH = sm + 49152, *sW2tL = sm + 65536;
   float* sb2 = reinterpret_cast<float*>(sm + kBwdWeights);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // capacity-limited stash: this launch is the alternative to edge_bwd_st_kernel and runs only when the edge list of the
+  // evaluation did not fit the stash (uniform over the grid, before anything is allocated)
+  if (g.stash_role == 2 && stash_fits(g)) return;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -1385,7 +1401,8 @@ __device__ __forceinline__ void warp_arrive_bar(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-template <int TAB, int TERMS, bool SPLIT>
+// GATED: the instantiation launched for a capacity-limited stash (the default one stays free of the test)
+template <int TAB, int TERMS, bool SPLIT, bool GATED>
 __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g, uint32_t grp_bytes) {
   constexpr bool QB_SM = TAB >= 1;   // Qbar accumulator of the unit in shared memory
   extern __shared__ uint8_t smraw[];
@@ -1400,6 +1417,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
   constexpr bool BF = is_half(TERMS);
   uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2tH = sm + (BF ? 8192 : 16384), *sW2tL = sm + 32768;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (GATED && !stash_fits(g)) return;   // nothing was stashed: edge_bwd_ws_kernel (stash_role 2) takes over
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -1746,16 +1764,16 @@ static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint
   }
   return 0;
 }
+template <int T, int TERMS, bool SPLIT, bool GATED>
+static int launch_bwd_st_k(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
+  GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_st_kernel<T, TERMS, SPLIT, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_bwd_st_kernel<T, TERMS, SPLIT, GATED><<<grid, kWsThreads, smem, st>>>(g, gb);
+  return 0;
+}
 template <int T, int TERMS>
 static int launch_bwd_st_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
-  if (g.S > 1) {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_st_kernel<T, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_st_kernel<T, TERMS, true><<<grid, kWsThreads, smem, st>>>(g, gb);
-  } else {
-    GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_st_kernel<T, TERMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_st_kernel<T, TERMS, false><<<grid, kWsThreads, smem, st>>>(g, gb);
-  }
-  return 0;
+  if (g.n_edges) return g.S > 1 ? launch_bwd_st_k<T, TERMS, true, true>(c, g, grid, smem, gb, st) : launch_bwd_st_k<T, TERMS, false, true>(c, g, grid, smem, gb, st);
+  return g.S > 1 ? launch_bwd_st_k<T, TERMS, true, false>(c, g, grid, smem, gb, st) : launch_bwd_st_k<T, TERMS, false, false>(c, g, grid, smem, gb, st);
 }
 
 // terms = 3: 3xTF32 (fp32-accurate, default); terms = 1: one TF32 product per contraction (GNNIS_FLAG_MLP_TF32X1).
@@ -1805,6 +1823,7 @@ int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
 }
 
 int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, int stash, cudaStream_t st) {
+  const int terms_in = terms;
   if (!stash && is_half(terms)) terms = 1;   // the recomputing adjoint has no 16-bit form: single-pass TF32 products instead
   EdgeTcArgs g = make_tc_args(c, l, terms);
   g.rbar_accumulate = rbar_accumulate;
@@ -1818,17 +1837,30 @@ int launch_edge_bwd_ws(Ctx* c, int l, int rbar_accumulate, int terms, int stash,
     }
     const size_t smem = st_bwd_smem(c, tab);
     const uint32_t gb = (uint32_t)st_group_bytes(c, tab);
+    g.stash_role = 1;
     if (tab == 1) rc = launch_bwd_st_terms<1>(c, g, terms, grid, smem, gb, st);
     else rc = launch_bwd_st_terms<0>(c, g, terms, grid, smem, gb, st);
-  } else {
+    if (rc) return rc;
+    GNNIS_LAUNCH_CHECK();
+    if (!g.n_edges) stash = -1;   // the stash holds every edge list: no alternative launch
+  }
+  if (stash >= 0) {
+    // the recomputing adjoint: the only launch without a stash, the alternative launch of a capacity-limited one (it
+    // returns at once when the stash adjoint above has run; the products then follow the default arithmetic)
+    if (stash) {
+      terms = is_half(terms_in) ? 1 : (terms_in == 1 ? 1 : 3);
+      g = make_tc_args(c, l, terms);
+      g.rbar_accumulate = rbar_accumulate;
+      g.stash_role = 2;
+    }
     const size_t smem = bwd_tc_smem(c);
     const uint32_t gb = (uint32_t)group_bytes(c);
     if (c->tab_mode == 2) rc = terms == 1 ? launch_bwd_t<2, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<2, 3>(c, g, grid, smem, gb, st);
     else if (c->tab_mode == 1) rc = terms == 1 ? launch_bwd_t<1, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<1, 3>(c, g, grid, smem, gb, st);
     else rc = terms == 1 ? launch_bwd_t<0, 1>(c, g, grid, smem, gb, st) : launch_bwd_t<0, 3>(c, g, grid, smem, gb, st);
+    if (rc) return rc;
+    GNNIS_LAUNCH_CHECK();
   }
-  if (rc) return rc;
-  GNNIS_LAUNCH_CHECK();
   if (c->split_eff > 1) {
     const size_t n4 = (size_t)c->R * c->N * 16, first4 = (size_t)c->split_from * c->N * 16;   // only split replicas have parts
     const size_t w4 = n4 - first4;

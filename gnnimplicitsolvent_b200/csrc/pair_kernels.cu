@@ -223,22 +223,28 @@ fill_edges_kernel(const float* __restrict__ pos, int n, int N, int G, float cuto
     __syncthreads();
   }
   int64_t w = 0;
+  int rep_i = 0, key_i = 0;   // replica of this thread's target; its atom | offset of the replica in its unit << 16
   if (i < n) {
     w = (int64_t)blk_off[blockIdx.x] + sdeg[threadIdx.x] - mydeg;
     row_ptr[i] = (int)w;
+    rep_i = i / N;
+    key_i = (i - rep_i * N) | (((rep_i % G) * N) << 16);
   }
   // The rows are filled by whole warps, one target at a time: the lanes take the sources j = lane, lane + 32, ...,
   // a ballot compacts the accepted ones, and the row is written with consecutive addresses (ascending source).
+  // (replica / atom / unit offset are computed once per thread above and handed round by shuffles: the integer divisions
+  // were a third of the instructions of a target.)
   const int lane = threadIdx.x & 31;
   const unsigned todo = __ballot_sync(0xffffffffu, i < n && mydeg > 0 && w + mydeg <= capacity);   // E > capacity: caller
+  const int w32 = (int)w;   // capacity < 2^31 (ensure_workspace)
   for (unsigned m = todo; m; m &= m - 1) {
     const int t = __ffs(m) - 1;
-    const int it = __shfl_sync(0xffffffffu, i, t);
-    int64_t wt = __shfl_sync(0xffffffffu, w, t);
-    const int rep = it / N, a = it - rep * N;
+    const int rep = __shfl_sync(0xffffffffu, rep_i, t), key = __shfl_sync(0xffffffffu, key_i, t);
+    int64_t wt = __shfl_sync(0xffffffffu, w32, t);
+    const int a = key & 0xFFFF;
     const float* rp = spos + (size_t)(rep - st.first_rep) * N * 3;
     const float tx = rp[3 * a], ty = rp[3 * a + 1], tz = rp[3 * a + 2];
-    const uint32_t ul_base = (uint32_t)(rep % G) * (uint32_t)N;
+    const uint32_t ul_base = (uint32_t)key >> 16;
     const uint32_t tgt_ul = (ul_base + (uint32_t)a) << 16;
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int j = j0 + lane;

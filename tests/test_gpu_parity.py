@@ -376,6 +376,74 @@ def test_half_precision_modes(name, mode, weights):
     assert torch.equal(eb, eb2) and torch.equal(fb, fb2)
 
 
+def test_capacity_limited_stash(weights, monkeypatch):
+    """A stash that holds less than the worst-case edge capacity (Ctx::stash_cap; here forced with GNNIS_STASH_GB): the
+    kernels compare the edge count of the evaluation with it ON THE DEVICE.  A list that fits takes the stash adjoint
+    (bit-identical to the unlimited stash), one that does not fit is not stashed and the recomputing adjoint runs
+    (bit-identical to GNNIS_STASH=0); below half of the capacity no stash is allocated at all."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+
+    def engines(make):
+        eng_s = make()
+        monkeypatch.setenv("GNNIS_STASH", "0")
+        eng_r = make()
+        monkeypatch.delenv("GNNIS_STASH")
+        return eng_s, eng_r
+
+    def limited(make, hold):
+        # ensure_workspace: hold = floor(budget / 768) - 128, rounded down to whole tiles of 128 edges
+        monkeypatch.setenv("GNNIS_STASH_GB", repr(((hold + 128) * 768 + 64) / 1e9))
+        eng = make()
+        monkeypatch.delenv("GNNIS_STASH_GB")
+        return eng
+
+    mol = synth.synth_molecule(50, seed=50)
+    R = 600                                                    # two full waves of units + a split tail
+    pos_big = torch.from_numpy(synth.conformers(mol["pos"], R, 0.01, seed=3)).cuda()
+
+    def make_big():
+        eng = Engine(mol["params"], weights, device=0)
+        eng.set_replicas(R, [0] * R, [78.5] * R)
+        return eng
+
+    cases = [(lambda c=load_case(n): _engine(c, weights), torch.from_numpy(load_case(n)["pos"]).cuda())
+             for n in ("c2_n50_water", "n100_mixed")] + [(make_big, pos_big)]
+    seen_fit = seen_nofit = 0
+    for make, pos in cases:
+        Rr, N, _ = pos.shape
+        cap = Rr * N * (N - 1)
+        eng_s, eng_r = engines(make)
+        es, fs = eng_s.energy_force(pos)
+        er, fr = eng_r.energy_force(pos)
+        E = eng_s.last_edge_count()
+        half = -(-cap // 2)
+        # (a) holds the list, not the capacity
+        hold = max(-(-E // 128) * 128, -(-half // 128) * 128) + 128
+        if hold < cap:
+            eng = limited(make, hold)
+            assert f"adjoint=stash up to {hold} edges" in eng.describe(), eng.describe()
+            for _ in range(3):                                 # plain launches, then graph capture and replay
+                e, f = eng.energy_force(pos)
+                assert torch.equal(e, es) and torch.equal(f, fs)
+            seen_fit += 1
+        # (b) at least half of the capacity, but not the list: decided on the device, nothing is stashed
+        hold = -(-half // 128) * 128
+        if hold + 128 <= E:
+            eng = limited(make, hold)
+            assert f"adjoint=stash up to {hold} edges" in eng.describe(), eng.describe()
+            for _ in range(3):
+                e, f = eng.energy_force(pos)
+                assert torch.equal(e, er) and torch.equal(f, fr)
+            seen_nofit += 1
+        # (c) less than half of the capacity: no stash
+        eng = limited(make, (half // 128 - 2) * 128)
+        assert "adjoint=recompute (stash exceeds the memory budget)" in eng.describe(), eng.describe()
+        e, f = eng.energy_force(pos)
+        assert torch.equal(e, er) and torch.equal(f, fr)
+    assert seen_fit >= 2 and seen_nofit >= 1
+
+
 def test_stash_adjoint_vs_recomputing_adjoint(weights, monkeypatch):
     """Default adjoint (activation stash written by the forward, edge_bwd_st_kernel) against the recomputing one
     (GNNIS_STASH=0, edge_bwd_ws_kernel): identical energies, forces equal to the stash's 16-bit resolution, both inside
