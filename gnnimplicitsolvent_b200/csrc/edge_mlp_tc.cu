@@ -354,17 +354,22 @@ int tc_table_mode(const Ctx* c) {
   return 0;
 }
 
-// stash kernels: X | two tile images | keys | tables (forward: Q [, P]; adjoint: Qbar); group size a multiple of 128
+// stash kernels: X | two tile images | keys | tables (forward: Q [, P]; adjoint: Qbar); group size a multiple of 128.
+// Forward table mode 3 = Q table + ONE image buffer that the silu'(u) and silu'(w) codes of a tile use in turn (the
+// second image is what keeps the Q table of a 62 ... 119-atom replica out of shared memory; edge_fwd_wsi_kernel).
 static size_t st_group_bytes(const Ctx* c, int tables) {
-  size_t b = kGrpTab + kStageBytes + (size_t)tables * c->G * c->N * kTabLd * 4;
+  const size_t images = tables == 3 ? kStageBytes / 2 : kStageBytes;
+  size_t b = kGrpTab + images + (size_t)(tables == 3 ? 1 : tables) * c->G * c->N * kTabLd * 4;
   return (b + 127) / 128 * 128;
 }
 constexpr size_t kDynSmemMax = 227 * 1024 - 2048;   // 2 KB: static shared memory of the kernels
 static size_t st_fwd_smem(const Ctx* c, int tables) { return kFwdWeights + 256 + kGroups * st_group_bytes(c, tables) + 1024; }
 static size_t st_bwd_smem(const Ctx* c, int tables) { return 49152 + 256 + kGroups * st_group_bytes(c, tables) + 1024; }
 int st_fwd_tables(const Ctx* c) {
-  for (int t = 2; t >= 0; --t)
-    if (st_fwd_smem(c, t) <= kDynSmemMax) return t;
+  static const int one_buf = getenv("GNNIS_ONEBUF") ? atoi(getenv("GNNIS_ONEBUF")) : 1;   // 0: never mode 3 (A/B)
+  const int order[4] = {2, 1, 3, 0};
+  for (int t : order)
+    if ((t != 3 || one_buf) && st_fwd_smem(c, t) <= kDynSmemMax) return t;
   return -1;
 }
 int st_bwd_tables(const Ctx* c) {
@@ -652,6 +657,7 @@ __device__ __forceinline__ void reduce_sources_table_256(const float* __restrict
 constexpr int kWsiThreads = kGroups * kWsGroupThreads + 32;
 struct WsiBars {
   uint64_t d_full[kGroups], a_full[kGroups], u_ok[kGroups], tile_b[kGroups];
+  uint64_t img_free[kGroups];   // table mode 3: the silu'(w) image of the previous tile has left the shared image buffer
 };
 __device__ __forceinline__ void warp_arrive_bar(uint64_t* bar, int lane);
 __device__ __forceinline__ void warp_arrive_i(uint64_t* bar, int lane) {
@@ -693,13 +699,22 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   constexpr int TERMS = TM == kTanh3 ? 3 : TM;                 // arithmetic of the products
   constexpr bool FAST = is_half(TM) || TM == kTanh3;           // tanh-based activations
   constexpr bool Q_SM = TAB >= 1, P_SM = TAB == 2;   // which node tables of the unit live in shared memory
+  // TAB == 3 (stash only): Q table as in mode 1, and ONE 16 KB image buffer instead of two.  The silu'(u) image of a tile
+  // has left it when the second epilogue starts (thread 0 waits for that before barrier (A) in every mode); what is new is
+  // that the first epilogue of the NEXT tile may only write its codes once the silu'(w) image has left: thread 128 sends
+  // that image after barrier (B), waits until the TMA engine has read it and arrives on img_free, on which every thread
+  // waits just before its first code store (by then it has evaluated 16 activations).  Measured (edge forward, ms; results
+  // bit-identical): N = 100, R = 4096 7.59 -> 5.57; N = 80 4.87 -> 3.63; N = 116, R = 1024 2.03 -> 1.48.  The same trade for
+  // 50 atoms (P and Q tables + one buffer instead of Q table + two buffers) loses: 1.988 -> 2.064.
+  constexpr bool ONEBUF = STASH && TAB == 3;
+  static_assert(TAB != 3 || STASH, "table mode 3 exists for the stash kernels only");
   // How a tile is closed.  With the unit's tables in shared memory: a group barrier (B) after the second epilogue.  Without
   // tables (more than 64 atoms with the stash: both row gathers go through L1 / L2 and the warps drift apart): an mbarrier
   // arrival -- a warp goes on to the next tile's first epilogue at once, warp 4 (no radial work) sends the tile's silu'(w)
   // image as soon as all eight arrivals are in, and the tile is reduced under the next w product by whoever has waited.
   // Measured (edge forward, ms): N = 100, R = 1024 1.967 -> 1.925; N = 50, R = 4096 1.986 -> 2.000 (hence the barrier there)
   constexpr bool TB = !Q_SM;
-  constexpr uint32_t kStg = STASH ? kStageBytes : 0u;
+  constexpr uint32_t kStg = STASH ? (ONEBUF ? kStageBytes / 2 : kStageBytes) : 0u;
   extern __shared__ uint8_t smraw[];
   __shared__ WsiBars bars;
   __shared__ uint32_t tmem_slot;
@@ -720,6 +735,8 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       mbar_init(&bars.a_full[i], 8);
       mbar_init(&bars.u_ok[i], 12);
       mbar_init(&bars.tile_b[i], 8);
+      mbar_init(&bars.img_free[i], 1);
+      if (ONEBUF) mbar_arrive(&bars.img_free[i]);   // the buffer starts out free (phase 0 complete)
     }
   }
   __shared__ uint64_t ibar;
@@ -789,14 +806,15 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
     uint8_t* gsm = sm + kFwdWeights + 256 + (size_t)grp * grp_bytes;
     float* sZ = reinterpret_cast<float*>(gsm + kGrpX);
     uint8_t* sStU = gsm + kGrpStage;                  // STASH: tile images of the silu'(u) / silu'(w) codes
-    uint8_t* sStW = gsm + kGrpStage + kStageBytes / 2;
+    uint8_t* sStW = ONEBUF ? sStU : gsm + kGrpStage + kStageBytes / 2;
     TileKeys* keys = reinterpret_cast<TileKeys*>(gsm + kGrpKeys + kStg);
     float* sTab = reinterpret_cast<float*>(gsm + kGrpTab + kStg);
     const uint32_t swz = (uint32_t)(row & 7);         // chunk swizzle of this thread's image row
     const uint32_t tm = tmem_slot + (uint32_t)grp * 256u;
     const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);
     uint64_t *d_full = &bars.d_full[grp], *a_full = &bars.a_full[grp], *u_ok = &bars.u_ok[grp], *tile_b = &bars.tile_b[grp];
-    uint32_t ph_d = 0, ph_a = 0, ph_b = 0, cur = 0;
+    uint64_t* img_free = &bars.img_free[grp];
+    uint32_t ph_d = 0, ph_a = 0, ph_b = 0, ph_f = 0, cur = 0;
     int kidx = 0;   // TileKeys buffer of the current tile; (kidx + 1) % 3 = next tile, (kidx + 2) % 3 = previous tile
 
     for (int unit = blockIdx.x + grp * gridDim.x; unit < g.n_units; unit += gridDim.x * kGroups) {
@@ -895,6 +913,10 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
             }
             const uint32_t q0 = (uint32_t)(4 * ch + 2 * c);
             uint8_t* img = sStU + row * 128;
+            if (ONEBUF && c == 0) {   // the silu'(w) image of the previous tile has left the buffer
+              mbar_wait(img_free, ph_f);
+              ph_f ^= 1u;
+            }
             *reinterpret_cast<uint4*>(img + ((q0 ^ swz) << 4)) = make_uint4(code[0], code[1], code[2], code[3]);
             *reinterpret_cast<uint4*>(img + (((q0 + 1u) ^ swz) << 4)) = make_uint4(code[4], code[5], code[6], code[7]);
           } else {
@@ -958,7 +980,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         tmem_ld32(lane_addr + (cur ^ 64u) + 32 * ch, wr);
         tmem_ld_wait();
         if (has_next) warp_arrive_i(u_ok, lane);
-        if (STASH && (gt == 0 || (TB && gt == 128))) bulk_store_wait_read();   // the images sent so far have left shared memory
+        if (STASH && (gt == 0 || ((TB || ONEBUF) && gt == 128))) bulk_store_wait_read();   // the images sent so far have left shared memory
         ws_group_sync(grp);                          // (A) the reduction of the previous tile is complete
         {
           const float4* bb = reinterpret_cast<const float4*>(sb2 + 32 * ch);
@@ -997,7 +1019,13 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
         } else {
           if (STASH && gt == 0) bulk_store_wait_read();   // the silu'(u) image of this tile has left shared memory
           ws_group_sync(grp);                          // (B) tile complete; it is reduced under the next tile's w GEMM
-          if (st_ok && gt == 0) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
+          if (ONEBUF) {
+            if (gt == 128) {
+              if (st_ok) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
+              bulk_store_wait_read();
+              mbar_arrive(img_free);
+            }
+          } else if (st_ok && gt == 0) bulk_store(g.st_w + (size_t)t0 * 128, sStW, (uint32_t)min(kTileE, e_end - t0) * 128u);
         }
         pr = pr_n;
         r = r_n;
@@ -1019,7 +1047,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
       reduce_targets_global_256(sZ, keys + (kidx + 2) % 3, gA, gt);   // last tile of the unit
       ws_group_sync(grp);   // all rows of the unit written before its tables are replaced
     }
-    if (STASH && (gt == 0 || (TB && gt == 128))) bulk_store_wait_all();   // every image has reached global memory before the CTA retires
+    if (STASH && (gt == 0 || ((TB || ONEBUF) && gt == 128))) bulk_store_wait_all();   // every image has reached global memory before the CTA retires
   }
   fence_before_sync();
   __syncthreads();
@@ -1809,6 +1837,7 @@ int launch_edge_fwd_ws(Ctx* c, int l, int terms, int stash, cudaStream_t st) {
     const uint32_t gb = (uint32_t)st_group_bytes(c, tab);
     if (tab == 2) rc = launch_fwd_terms<2, true>(c, g, terms, grid, smem, gb, st);
     else if (tab == 1) rc = launch_fwd_terms<1, true>(c, g, terms, grid, smem, gb, st);
+    else if (tab == 3) rc = launch_fwd_terms<3, true>(c, g, terms, grid, smem, gb, st);
     else rc = launch_fwd_terms<0, true>(c, g, terms, grid, smem, gb, st);
   } else {
     const size_t smem = fwd_tc_smem(c);
