@@ -162,6 +162,7 @@ struct Ctx {
   int act_tanh = 1;
   int adj_terms = 0;          // 0: the adjoint's products follow the mode of the evaluation
   int use_stash = 1;          // GNNIS_STASH=0: always recompute (A/B, debug)
+  int one_buf = 1;            // GNNIS_ONEBUF=0: no table mode 3 of the stash forward (Q table + one image buffer, 67 ... 126 atoms)
   double stash_max_gb = -1;   // GNNIS_STASH_GB: upper bound of the stash allocation (default: 45 % of the free memory)
   float *e_atom = nullptr, *sa_atom = nullptr;
   int64_t* n_edges_dev = nullptr;

@@ -356,7 +356,7 @@ int tc_table_mode(const Ctx* c) {
 
 // stash kernels: X | two tile images | keys | tables (forward: Q [, P]; adjoint: Qbar); group size a multiple of 128.
 // Forward table mode 3 = Q table + ONE image buffer that the silu'(u) and silu'(w) codes of a tile use in turn (the
-// second image is what keeps the Q table of a 62 ... 119-atom replica out of shared memory; edge_fwd_wsi_kernel).
+// second image is what keeps the Q table of a 67 ... 126-atom replica out of shared memory; edge_fwd_wsi_kernel).
 static size_t st_group_bytes(const Ctx* c, int tables) {
   const size_t images = tables == 3 ? kStageBytes / 2 : kStageBytes;
   size_t b = kGrpTab + images + (size_t)(tables == 3 ? 1 : tables) * c->G * c->N * kTabLd * 4;
@@ -366,10 +366,9 @@ constexpr size_t kDynSmemMax = 227 * 1024 - 2048;   // 2 KB: static shared memor
 static size_t st_fwd_smem(const Ctx* c, int tables) { return kFwdWeights + 256 + kGroups * st_group_bytes(c, tables) + 1024; }
 static size_t st_bwd_smem(const Ctx* c, int tables) { return 49152 + 256 + kGroups * st_group_bytes(c, tables) + 1024; }
 int st_fwd_tables(const Ctx* c) {
-  static const int one_buf = getenv("GNNIS_ONEBUF") ? atoi(getenv("GNNIS_ONEBUF")) : 1;   // 0: never mode 3 (A/B)
   const int order[4] = {2, 1, 3, 0};
   for (int t : order)
-    if ((t != 3 || one_buf) && st_fwd_smem(c, t) <= kDynSmemMax) return t;
+    if ((t != 3 || c->one_buf) && st_fwd_smem(c, t) <= kDynSmemMax) return t;
   return -1;
 }
 int st_bwd_tables(const Ctx* c) {

@@ -444,6 +444,64 @@ def test_capacity_limited_stash(weights, monkeypatch):
     assert seen_fit >= 2 and seen_nofit >= 1
 
 
+def test_forward_table_mode_3(weights, monkeypatch):
+    """67 ... 126 atoms: the stash forward keeps its Q table in shared memory next to ONE image buffer that the silu'(u) and
+    silu'(w) codes of a tile share (table mode 3).  Same arithmetic as the table-less kernel (GNNIS_ONEBUF=0): bit-identical
+    results, for whole replicas, split tails and split small batches, in the default and the half-precision arithmetic, and
+    with a capacity-limited stash whose edge list does not fit."""
+    from gnnimplicitsolvent_b200 import synth
+    from gnnimplicitsolvent_b200.engine import Engine
+    from oracle import gnn_oracle as O
+    nofit = 0
+    for N, R, squeeze in ((100, 600, 1.0), (126, 5, 1.0), (67, 300, 1.0), (70, 320, 0.8), (80, 310, 0.7)):
+        mol = synth.synth_molecule(N, seed=N)
+        pos_h = (synth.conformers(mol["pos"], R, 0.01, seed=N + R) * squeeze).astype(np.float32)
+        pos = torch.from_numpy(pos_h).cuda()
+
+        def make():
+            eng = Engine(mol["params"], weights, device=0)
+            eng.set_replicas(R, [r % 39 for r in range(R)], [synth.SOLVENT_DIELECTRICS[r % 39] for r in range(R)])
+            return eng
+
+        eng3 = make()
+        assert "tables=3" in eng3.describe(), eng3.describe()
+        monkeypatch.setenv("GNNIS_ONEBUF", "0")
+        eng0 = make()
+        monkeypatch.delenv("GNNIS_ONEBUF")
+        assert "tables=0" in eng0.describe(), eng0.describe()
+        for kw in ({}, {"fp16": True}, {"delta": True}):
+            e3, f3 = eng3.energy_force(pos, **kw)
+            e0, f0 = eng0.energy_force(pos, **kw)
+            assert torch.equal(e3, e0) and torch.equal(f3, f0), (N, R, kw)
+        if squeeze == 1.0 and R <= 8:                      # against the oracle as well (small case)
+            sids = [r % 39 for r in range(R)]
+            o = O.evaluate(mol["params"], pos_h, sids, [synth.SOLVENT_DIELECTRICS[s_] for s_ in sids],
+                           {k: v for k, v in weights.items()})
+            e3, f3 = eng3.energy_force(pos)
+            np.testing.assert_allclose(e3.cpu().numpy(), o["energy_rep"].numpy(), rtol=E_RTOL, atol=1e-3)
+            assert rel_rms(f3.cpu().numpy(), o["forces"].numpy()) < F_RRMS
+        # capacity-limited stash that holds half of the capacity but not this edge list: nothing is stashed, the
+        # recomputing adjoint runs behind the table-mode-3 forward
+        e3, f3 = eng3.energy_force(pos)
+        E, cap = eng3.last_edge_count(), R * N * (N - 1)
+        hold = -(-(-(-cap // 2)) // 128) * 128
+        if hold + 128 <= E:
+            monkeypatch.setenv("GNNIS_STASH", "0")
+            eng_r = make()
+            monkeypatch.delenv("GNNIS_STASH")
+            er, fr = eng_r.energy_force(pos)
+            monkeypatch.setenv("GNNIS_STASH_GB", repr(((hold + 128) * 768 + 64) / 1e9))
+            eng_c = make()
+            monkeypatch.delenv("GNNIS_STASH_GB")
+            d = eng_c.describe()
+            assert f"adjoint=stash up to {hold} edges" in d and "tables=3" in d, d
+            for _ in range(2):
+                ec, fc = eng_c.energy_force(pos)
+                assert torch.equal(ec, er) and torch.equal(fc, fr)
+            nofit += 1
+    assert nofit >= 1
+
+
 def test_stash_adjoint_vs_recomputing_adjoint(weights, monkeypatch):
     """Default adjoint (activation stash written by the forward, edge_bwd_st_kernel) against the recomputing one
     (GNNIS_STASH=0, edge_bwd_ws_kernel): identical energies, forces equal to the stash's 16-bit resolution, both inside
