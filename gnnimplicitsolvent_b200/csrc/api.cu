@@ -416,6 +416,7 @@ int gnnis_create(gnnis_handle* out, int device) {
   if (const char* e = getenv("GNNIS_STASH")) c->use_stash = atoi(e);      // 0: the edge adjoint always recomputes its activations
   if (const char* e = getenv("GNNIS_STASH_GB")) c->stash_max_gb = atof(e);
   if (const char* e = getenv("GNNIS_ONEBUF")) c->one_buf = atoi(e);
+  if (const char* e = getenv("GNNIS_PDL")) c->pdl = atoi(e);
   if (const char* e = getenv("GNNIS_LB_STALL")) c->lb_stall_limit = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("GNNIS_LB_MAXDISP")) c->lb_max_disp = (float)atof(e);
   if (const char* e = getenv("GNNIS_ACT")) c->act_tanh = atoi(e);    // 0: exponential-based sigmoid in the forward edge kernels

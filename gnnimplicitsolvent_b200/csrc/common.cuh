@@ -162,6 +162,10 @@ struct Ctx {
   int act_tanh = 1;
   int adj_terms = 0;          // 0: the adjoint's products follow the mode of the evaluation
   int use_stash = 1;          // GNNIS_STASH=0: always recompute (A/B, debug)
+  // GNNIS_PDL: programmatic dependent launch of the tensor-core kernels: 0 off, 1 (default) for batches that do not fill
+  // the GPU (their successors' prologues then run on idle SMs), 2 always
+  int pdl = 1;
+  bool pdl_now() const { return pdl == 2 || (pdl == 1 && (size_t)R * N <= (size_t)64 * 148 && eff_units() <= 2 * 148); }
   int one_buf = 1;            // GNNIS_ONEBUF=0: no table mode 3 of the stash forward (Q table + one image buffer, 67 ... 126 atoms)
   double stash_max_gb = -1;   // GNNIS_STASH_GB: upper bound of the stash allocation (default: 45 % of the free memory)
   float *e_atom = nullptr, *sa_atom = nullptr;
@@ -247,6 +251,29 @@ __device__ __forceinline__ UnitSpan unit_span(int unit, int G, int N, int R, int
     u.a1 = ((u.part + 1) * N) / S;
   }
   return u;
+}
+
+// Programmatic dependent launch (small batches, Ctx::pdl_now()): a kernel launched with the attribute may become resident as
+// soon as every CTA of its predecessor in the stream has executed pdl_trigger(), runs its prologue (TMEM allocation,
+// mbarrier set-up, TMA copy of the weight images -- nothing that the evaluation writes) and then blocks in pdl_wait()
+// until the predecessor has completed and its writes are visible.  Every kernel that takes part calls pdl_wait() on
+// EVERY path before it exits (completion must stay transitive along the chain).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 #define GNNIS_CUDA_OK(call)                                                                   \

@@ -724,8 +724,7 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2H = sm + (BF ? 8192 : 16384), *sW2L = sm + 32768;
   float* sb2 = reinterpret_cast<float*>(sm + kFwdWeights);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // capacity-limited stash: an edge list that does not fit is not stashed (the adjoint of this evaluation recomputes)
-  const bool st_ok = STASH && stash_fits(g);
+  pdl_trigger();
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -750,6 +749,9 @@ __global__ void __launch_bounds__(kWsiThreads, 1) edge_fwd_wsi_kernel(EdgeTcArgs
   fence_after_sync();
   mbar_wait(&ibar, 0);
   __syncwarp();
+  pdl_wait();   // everything above touched only the weight images; the evaluation's data from here on
+  // capacity-limited stash: an edge list that does not fit is not stashed (the adjoint of this evaluation recomputes)
+  const bool st_ok = STASH && stash_fits(g);
   constexpr uint32_t VH = 128, VL = 192;
   constexpr uint32_t idesc64 = TERMS == kFp16 ? idesc_fp16(128, 64) : (BF ? idesc_bf16(128, 64) : idesc_tf32(128, 64));
 
@@ -1069,7 +1071,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // capacity-limited stash: this launch is the alternative to edge_bwd_st_kernel and runs only when the edge list of the
   // evaluation did not fit the stash (uniform over the grid, before anything is allocated)
-  if (g.stash_role == 2 && stash_fits(g)) return;
+  pdl_trigger();
+  if (g.stash_role == 2 && stash_fits(g)) {
+    pdl_wait();
+    return;
+  }
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -1092,6 +1098,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_ws_kernel(EdgeTcArgs g
   fence_after_sync();
   mbar_wait(&ibar, 0);
   __syncwarp();
+  pdl_wait();
   constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
   constexpr uint32_t idesc64 = idesc_tf32(128, 64);
 
@@ -1444,7 +1451,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
   constexpr bool BF = is_half(TERMS);
   uint8_t *sWrH = sm, *sWrL = sm + 8192, *sW2tH = sm + (BF ? 8192 : 16384), *sW2tL = sm + 32768;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (GATED && !stash_fits(g)) return;   // nothing was stashed: edge_bwd_ws_kernel (stash_role 2) takes over
+  pdl_trigger();
+  if (GATED && !stash_fits(g)) {   // nothing was stashed: edge_bwd_ws_kernel (stash_role 2) takes over
+    pdl_wait();
+    return;
+  }
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -1478,6 +1489,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
   fence_after_sync();
   mbar_wait(&ibar, 0);
   __syncwarp();
+  pdl_wait();
   constexpr uint32_t ACC = 0, DU = 64, XH = 128, XL = 192;
   constexpr uint32_t idesc64 = TERMS == kFp16 ? idesc_fp16(128, 64) : (BF ? idesc_bf16(128, 64) : idesc_tf32(128, 64));
 
@@ -1756,6 +1768,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) edge_bwd_st_kernel(EdgeTcArgs g
 
 // Qbar = sum over the parts of a split replica, in part order (deterministic)
 __global__ void sum_qbar_parts_kernel(float4* __restrict__ qbar, size_t first4, size_t n4, size_t stride4, int S) {
+  pdl_trigger();
   for (size_t i = first4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 a = qbar[i];
     for (int p = 1; p < S; ++p) {
@@ -1773,10 +1786,10 @@ template <int T, int TERMS, bool STASH>
 static int launch_fwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
   if (g.S > 1) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, true, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_wsi_kernel<T, TERMS, true, STASH><<<grid, kWsiThreads, smem, st>>>(g, gb);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), edge_fwd_wsi_kernel<T, TERMS, true, STASH>, grid, kWsiThreads, smem, st, g, gb));
   } else {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_fwd_wsi_kernel<T, TERMS, false, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_fwd_wsi_kernel<T, TERMS, false, STASH><<<grid, kWsiThreads, smem, st>>>(g, gb);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), edge_fwd_wsi_kernel<T, TERMS, false, STASH>, grid, kWsiThreads, smem, st, g, gb));
   }
   return 0;
 }
@@ -1784,17 +1797,17 @@ template <int T, int TERMS>
 static int launch_bwd_t(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
   if (g.S > 1) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<T, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_ws_kernel<T, TERMS, true><<<grid, kWsThreads, smem, st>>>(g, gb);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), edge_bwd_ws_kernel<T, TERMS, true>, grid, kWsThreads, smem, st, g, gb));
   } else {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_ws_kernel<T, TERMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_ws_kernel<T, TERMS, false><<<grid, kWsThreads, smem, st>>>(g, gb);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), edge_bwd_ws_kernel<T, TERMS, false>, grid, kWsThreads, smem, st, g, gb));
   }
   return 0;
 }
 template <int T, int TERMS, bool SPLIT, bool GATED>
 static int launch_bwd_st_k(Ctx* c, const EdgeTcArgs& g, int grid, size_t smem, uint32_t gb, cudaStream_t st) {
   GNNIS_CUDA_OK(cudaFuncSetAttribute(edge_bwd_st_kernel<T, TERMS, SPLIT, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_bwd_st_kernel<T, TERMS, SPLIT, GATED><<<grid, kWsThreads, smem, st>>>(g, gb);
+  GNNIS_CUDA_OK(launch_k(c->pdl_now(), edge_bwd_st_kernel<T, TERMS, SPLIT, GATED>, grid, kWsThreads, smem, st, g, gb));
   return 0;
 }
 template <int T, int TERMS>

@@ -111,6 +111,7 @@ __global__ void node_pre1_kernel(int n, int N, const float* __restrict__ born, c
                                  const float* __restrict__ rho, const float* __restrict__ Wi_t,
                                  const float* __restrict__ Wj_t, const float* __restrict__ b1, float* __restrict__ P,
                                  float* __restrict__ Q) {
+  pdl_trigger();   // the first edge forward kernel may set itself up while this one runs (common.cuh)
   // one thread per (atom, four channels): 16-byte stores, the per-channel arithmetic is unchanged
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * 16) return;

@@ -153,6 +153,7 @@ __device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
   uint8_t* sm = smraw + ((1024u - (base_ & 1023u)) & 1023u);                       \
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                   \
   const int grp = warp >> 3, ch = (warp >> 2) & 1, wq = warp & 3, row = 32 * wq + lane; \
+  pdl_trigger();                                                                   \
   if (warp == 0) tmem_alloc(&tmem_slot, 512);                                      \
   if (tid == 0) {                                                                  \
     mbar_init(&bar[0], 1);                                                         \
@@ -167,6 +168,7 @@ __device__ __forceinline__ float4 nt_add4(float4 a, float4 b) {
   fence_after_sync();                                                              \
   mbar_wait(&ibar, 0);   /* operand images have landed */                          \
   __syncwarp();                                                                    \
+  pdl_wait();            /* the evaluation's data from here on */                  \
   const uint32_t tm = tmem_slot + 256u * (uint32_t)grp;                            \
   const uint32_t lane_addr = tm + ((uint32_t)(32 * wq) << 16);                     \
   uint32_t phase = 0;                                                              \
@@ -575,11 +577,11 @@ int launch_node_fwd_tc(Ctx* c, int l, cudaStream_t st) {
   if (l == 2) {
     size_t smem = 65536 + 32768 + 2048 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    node_fwd_tc_kernel<true><<<nt_grid(c), kNtThreads, smem, st>>>(g);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), node_fwd_tc_kernel<true>, nt_grid(c), kNtThreads, smem, st, g));
   } else {
     size_t smem = 196608 + 32768 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    node_fwd_tc_kernel<false><<<nt_grid(c), kNtThreads, smem, st>>>(g);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), node_fwd_tc_kernel<false>, nt_grid(c), kNtThreads, smem, st, g));
   }
   GNNIS_LAUNCH_CHECK();
   return 0;
@@ -591,17 +593,17 @@ int launch_node_bwd_tc(Ctx* c, int l, cudaStream_t st) {
     g.img = c->img_nba[l];
     size_t smem = 131072 + 32768 + 1024;
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    node_bwd_a_tc_kernel<<<nt_grid(c), kNtThreads, smem, st>>>(g);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), node_bwd_a_tc_kernel, nt_grid(c), kNtThreads, smem, st, g));
     GNNIS_LAUNCH_CHECK();
   }
   g.img = c->img_nbb[l];
   size_t smem = 131072 + 32768 + 1024;
   if (l == 2) {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_b_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    node_bwd_b_tc_kernel<true><<<nt_grid(c), kNtThreads, smem, st>>>(g);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), node_bwd_b_tc_kernel<true>, nt_grid(c), kNtThreads, smem, st, g));
   } else {
     GNNIS_CUDA_OK(cudaFuncSetAttribute(node_bwd_b_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    node_bwd_b_tc_kernel<false><<<nt_grid(c), kNtThreads, smem, st>>>(g);
+    GNNIS_CUDA_OK(launch_k(c->pdl_now(), node_bwd_b_tc_kernel<false>, nt_grid(c), kNtThreads, smem, st, g));
   }
   GNNIS_LAUNCH_CHECK();
   return 0;

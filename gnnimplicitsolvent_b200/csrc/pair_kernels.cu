@@ -459,6 +459,7 @@ born_adjoint_kernel(const int* __restrict__ skip, const float* __restrict__ pos,
 // one warp per replica: E_rep = sum_i (e_i + sa_i), fixed order (lane-strided partials + shuffle tree)
 __global__ void reduce_energy_kernel(const float* __restrict__ e_atom, const float* __restrict__ sa_atom, int R, int N,
                                      float* __restrict__ e_rep) {
+  pdl_trigger();   // the first node adjoint kernel may set itself up while this one runs (common.cuh)
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= R) return;
   float acc = 0.0f;
